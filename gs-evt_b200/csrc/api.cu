@@ -1,0 +1,841 @@
+// extern "C" entry points of libgsevt.so (declared in include/gsevt.h) and the host-side runtime of
+// the tracking engine: buffer carving, launch sequencing, CUDA-graph capture of one iteration.
+#include "../../include/gsevt.h"
+#include "internal.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace gsevt {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- operator work-buffer layouts ----------------------------------------------------------------
+struct GeomLayout {
+    size_t vp, rec, rgb4, cov3D, radii, clamped, tiles_touched, point_offsets, scan_temp, scan_bytes, total;
+};
+static GeomLayout geom_layout(int P) {
+    GeomLayout L;
+    size_t o = 0;
+    const size_t p = (size_t)(P > 0 ? P : 1);
+    L.vp = o; o = align_up(o + sizeof(ViewParams));
+    L.rec = o; o = align_up(o + p * 32);
+    L.rgb4 = o; o = align_up(o + p * 16);
+    L.cov3D = o; o = align_up(o + p * 24);
+    L.radii = o; o = align_up(o + p * 4);
+    L.clamped = o; o = align_up(o + p);
+    L.tiles_touched = o; o = align_up(o + p * 4);
+    L.point_offsets = o; o = align_up(o + p * 4);
+    L.scan_bytes = scan_temp_bytes(P);
+    L.scan_temp = o; o = align_up(o + L.scan_bytes);
+    L.total = o + 256;  // slack for base alignment
+    return L;
+}
+struct ImgLayout { size_t accum_alpha, n_contrib, ranges, total; };
+static ImgLayout img_layout(int W, int H) {
+    ImgLayout L;
+    size_t o = 0;
+    const size_t hw = (size_t)W * H;
+    const size_t tiles = (size_t)((W + 15) / 16) * ((H + 15) / 16);
+    L.accum_alpha = o; o = align_up(o + hw * 4);
+    L.n_contrib = o; o = align_up(o + hw * 4);
+    L.ranges = o; o = align_up(o + tiles * 8);
+    L.total = o + 256;
+    return L;
+}
+struct BinLayout { size_t keys_unsorted, keys, list_unsorted, list, sort_temp, sort_bytes, total; };
+static BinLayout bin_layout(int R) {
+    BinLayout L;
+    size_t o = 0;
+    const size_t r = (size_t)(R > 0 ? R : 1);
+    L.keys_unsorted = o; o = align_up(o + r * 8);
+    L.keys = o; o = align_up(o + r * 8);
+    L.list_unsorted = o; o = align_up(o + r * 4);
+    L.list = o; o = align_up(o + r * 4);
+    L.sort_bytes = sort_temp_bytes(R);
+    L.sort_temp = o; o = align_up(o + L.sort_bytes);
+    L.total = o + 256;
+    return L;
+}
+struct BwdLayout { size_t vp, grad8, gradc, partials, total; };
+static BwdLayout bwd_layout(int P) {
+    BwdLayout L;
+    size_t o = 0;
+    const size_t p = (size_t)(P > 0 ? P : 1);
+    L.vp = o; o = align_up(o + sizeof(ViewParams));
+    L.grad8 = o; o = align_up(o + p * 32);
+    L.gradc = o; o = align_up(o + p * 8);
+    L.partials = o; o = align_up(o + (size_t)geom_bwd_blocks(P, 1) * GSEVT_NPART * 4);
+    L.total = o + 256;
+    return L;
+}
+static inline char* base_aligned(void* p) { return (char*)align_up((size_t)p); }
+
+static int debug_check(int debug, cudaStream_t s, const char* what) {
+    if (!debug) {
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return GSEVT_ECUDA; }
+        return 0;
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("[debug] %s: %s", what, cudaGetErrorString(e)); return GSEVT_ECUDA; }
+    return 0;
+}
+#define DBG(what) do { int rc__ = debug_check(a->debug, s, what); if (rc__) return rc__; } while (0)
+
+static int check_common(const GsevtRasterArgs* a) {
+    if (!a) { set_error("null args"); return GSEVT_EINVAL; }
+    if (a->P < 0 || a->width <= 0 || a->height <= 0) { set_error("bad sizes P=%d W=%d H=%d", a->P, a->width, a->height); return GSEVT_EINVAL; }
+    if (!a->means3D && a->P > 0) { set_error("means3D is null"); return GSEVT_EINVAL; }
+    if ((a->shs == nullptr) == (a->colors_precomp == nullptr)) {
+        set_error("Please provide excatly one of either SHs or precomputed colors!");
+        return GSEVT_EINVAL;
+    }
+    const bool sr = a->scales != nullptr && a->rotations != nullptr;
+    if (sr == (a->cov3D_precomp != nullptr) || ((a->scales != nullptr) != (a->rotations != nullptr))) {
+        set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        return GSEVT_EINVAL;
+    }
+    if (a->shs && (a->sh_degree < 0 || a->sh_degree > 3 || (a->sh_degree + 1) * (a->sh_degree + 1) > a->sh_coeffs)) {
+        set_error("sh_degree %d needs %d coefficients, shs has %d", a->sh_degree, (a->sh_degree + 1) * (a->sh_degree + 1), a->sh_coeffs);
+        return GSEVT_EINVAL;
+    }
+    return 0;
+}
+
+}  // namespace gsevt
+
+using namespace gsevt;
+
+extern "C" {
+
+GSEVT_API const char* gsevt_last_error(void) { return g_err; }
+GSEVT_API int gsevt_abi_version(void) { return GSEVT_ABI_VERSION; }
+GSEVT_API int gsevt_device_arch(void) {
+    int dev = 0;
+    GSEVT_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    GSEVT_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    return prop.major * 10 + prop.minor;
+}
+
+GSEVT_API int gsevt_raster_sizes(int32_t P, int32_t width, int32_t height, size_t* geom_bytes, size_t* img_bytes) {
+    if (P < 0 || width <= 0 || height <= 0) { set_error("bad sizes"); return GSEVT_EINVAL; }
+    if (geom_bytes) *geom_bytes = geom_layout(P).total;
+    if (img_bytes) *img_bytes = img_layout(width, height).total;
+    return 0;
+}
+GSEVT_API size_t gsevt_raster_binning_size(int32_t num_rendered) { return bin_layout(num_rendered).total; }
+GSEVT_API size_t gsevt_raster_backward_workspace_size(int32_t P) { return bwd_layout(P).total; }
+
+GSEVT_API int64_t gsevt_raster_geom_offset(const char* name, int32_t P) {
+    const GeomLayout L = geom_layout(P);
+    const std::string n(name ? name : "");
+    if (n == "view_params") return (int64_t)L.vp;
+    if (n == "rec") return (int64_t)L.rec;
+    if (n == "rgb4") return (int64_t)L.rgb4;
+    if (n == "cov3D") return (int64_t)L.cov3D;
+    if (n == "radii") return (int64_t)L.radii;
+    if (n == "clamped") return (int64_t)L.clamped;
+    if (n == "tiles_touched") return (int64_t)L.tiles_touched;
+    if (n == "point_offsets") return (int64_t)L.point_offsets;
+    return -1;
+}
+GSEVT_API int64_t gsevt_raster_binning_offset(const char* name, int32_t R) {
+    const BinLayout L = bin_layout(R);
+    const std::string n(name ? name : "");
+    if (n == "point_list_keys_unsorted") return (int64_t)L.keys_unsorted;
+    if (n == "point_list_keys") return (int64_t)L.keys;
+    if (n == "point_list_unsorted") return (int64_t)L.list_unsorted;
+    if (n == "point_list") return (int64_t)L.list;
+    return -1;
+}
+GSEVT_API int64_t gsevt_raster_img_offset(const char* name, int32_t W, int32_t H) {
+    const ImgLayout L = img_layout(W, H);
+    const std::string n(name ? name : "");
+    if (n == "accum_alpha") return (int64_t)L.accum_alpha;
+    if (n == "n_contrib") return (int64_t)L.n_contrib;
+    if (n == "ranges") return (int64_t)L.ranges;
+    return -1;
+}
+
+GSEVT_API int gsevt_raster_forward_geometry(const GsevtRasterArgs* a, void* stream) {
+    int rc = check_common(a);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->P == 0) return 0;
+    const GeomLayout L = geom_layout(a->P);
+    if (!a->geom_buffer || a->geom_bytes < L.total) { set_error("geom_buffer too small (%zu < %zu)", a->geom_bytes, L.total); return GSEVT_ENOMEM; }
+    if (!a->viewmatrix || !a->projmatrix || !a->campos || !a->opacities) { set_error("null camera / opacity input"); return GSEVT_EINVAL; }
+    char* g = base_aligned(a->geom_buffer);
+    ViewParams* vp = (ViewParams*)(g + L.vp);
+    launch_build_view_params(vp, a->viewmatrix, a->projmatrix, a->projmatrix_raw, a->campos, a->vel_transform,
+                             a->vel_transform_inv, a->background, a->tanfovx, a->tanfovy, a->width, a->height,
+                             a->delta_time, s);
+    PreAosArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.P = a->P; pa.D = a->sh_degree; pa.M = a->sh_coeffs; pa.vp = vp;
+    pa.means3D = a->means3D; pa.scales = a->scales; pa.rotations = a->rotations; pa.opacities = a->opacities;
+    pa.shs = a->shs; pa.colors_precomp = a->colors_precomp; pa.cov3D_precomp = a->cov3D_precomp;
+    pa.scale_modifier = a->scale_modifier;
+    pa.radii_internal = (int*)(g + L.radii); pa.radii_out = a->radii;
+    pa.tiles_touched = (uint32_t*)(g + L.tiles_touched);
+    pa.cov3D = (float*)(g + L.cov3D); pa.clamped = (uint8_t*)(g + L.clamped);
+    pa.rec = (float4*)(g + L.rec); pa.rgb4 = (float4*)(g + L.rgb4);
+    launch_preprocess_aos(pa, s);
+    DBG("preprocess");
+    launch_scan(g + L.scan_temp, L.scan_bytes, pa.tiles_touched, (uint32_t*)(g + L.point_offsets), a->P, s);
+    DBG("scan");
+    uint32_t n = 0;
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&n, (uint32_t*)(g + L.point_offsets) + (a->P - 1), 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    if (n > 0x7fffffffu) { set_error("num_rendered overflow"); return GSEVT_EOVERFLOW; }
+    return (int)n;
+}
+
+GSEVT_API int gsevt_raster_forward_render(const GsevtRasterArgs* a, void* stream) {
+    int rc = check_common(a);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!a->out_color || !a->out_depth || !a->out_opacity) { set_error("null output image"); return GSEVT_EINVAL; }
+    if (a->P == 0) return 0;
+    const GeomLayout L = geom_layout(a->P);
+    const ImgLayout I = img_layout(a->width, a->height);
+    const BinLayout B = bin_layout(a->num_rendered);
+    if (!a->geom_buffer || a->geom_bytes < L.total) { set_error("geom_buffer too small"); return GSEVT_ENOMEM; }
+    if (!a->img_buffer || a->img_bytes < I.total) { set_error("img_buffer too small (%zu < %zu)", a->img_bytes, I.total); return GSEVT_ENOMEM; }
+    if (!a->binning_buffer || a->binning_bytes < B.total) { set_error("binning_buffer too small (%zu < %zu)", a->binning_bytes, B.total); return GSEVT_ENOMEM; }
+    char* g = base_aligned(a->geom_buffer);
+    char* im = base_aligned(a->img_buffer);
+    char* bn = base_aligned(a->binning_buffer);
+    const ViewParams* vp = (const ViewParams*)(g + L.vp);
+    const int gx = (a->width + 15) / 16, gy = (a->height + 15) / 16;
+    const int R = a->num_rendered;
+    uint64_t* keys_u = (uint64_t*)(bn + B.keys_unsorted);
+    uint64_t* keys = (uint64_t*)(bn + B.keys);
+    uint32_t* list_u = (uint32_t*)(bn + B.list_unsorted);
+    uint32_t* list = (uint32_t*)(bn + B.list);
+    if (R > 0) {
+        launch_emit_keys(a->P, 1, vp, (const float4*)(g + L.rec), (const int*)(g + L.radii),
+                         (const uint32_t*)(g + L.point_offsets), keys_u, list_u, 0, nullptr, nullptr, s);
+        DBG("emit_keys");
+        const int bit = (int)higher_msb((uint32_t)(gx * gy));
+        launch_sort_pairs(bn + B.sort_temp, B.sort_bytes, keys_u, keys, list_u, list, R, 32 + bit, s);
+        DBG("sort");
+    }
+    launch_identify_ranges(keys, (uint2*)(im + I.ranges), gx * gy, R, nullptr, 0, s);
+    DBG("ranges");
+    BlendFwdArgs f;
+    memset(&f, 0, sizeof(f));
+    f.W = a->width; f.H = a->height; f.grid_x = gx; f.grid_y = gy; f.nviews = 1;
+    f.ranges = (const uint2*)(im + I.ranges); f.point_list = list;
+    f.rec = (const float4*)(g + L.rec); f.rgb4 = (const float4*)(g + L.rgb4);
+    f.view_stride_gauss = (size_t)a->P; f.bg = a->background; f.views = vp;
+    f.final_T = (float*)(im + I.accum_alpha); f.n_contrib = (uint32_t*)(im + I.n_contrib);
+    f.out_color = a->out_color; f.out_depth = a->out_depth; f.out_opacity = a->out_opacity;
+    f.n_touched = a->want_n_touched ? a->n_touched : nullptr;
+    if (!f.bg) { set_error("background is null"); return GSEVT_EINVAL; }
+    launch_blend_fwd_rgb(f, s);
+    DBG("blend_fwd");
+    return 0;
+}
+
+GSEVT_API int gsevt_raster_backward(const GsevtRasterArgs* a, void* stream) {
+    int rc = check_common(a);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!a->pose_grads) { set_error("pose_grads is null"); return GSEVT_EINVAL; }
+    if (a->P == 0) { GSEVT_CUDA_OK(cudaMemsetAsync(a->pose_grads, 0, 48, s)); return 0; }
+    if (!a->dL_dout_color) { set_error("dL_dout_color is null"); return GSEVT_EINVAL; }
+    if (!a->projmatrix_raw || !a->vel_transform || !a->vel_transform_inv) { set_error("backward needs projmatrix_raw and the velocity transforms"); return GSEVT_EINVAL; }
+    const GeomLayout L = geom_layout(a->P);
+    const ImgLayout I = img_layout(a->width, a->height);
+    const BinLayout B = bin_layout(a->num_rendered);
+    const BwdLayout W = bwd_layout(a->P);
+    if (!a->geom_buffer || a->geom_bytes < L.total || !a->img_buffer || a->img_bytes < I.total ||
+        !a->binning_buffer || a->binning_bytes < B.total) { set_error("forward buffers missing or too small"); return GSEVT_ENOMEM; }
+    if (!a->bwd_workspace || a->bwd_workspace_bytes < W.total) { set_error("bwd_workspace too small (%zu < %zu)", a->bwd_workspace_bytes, W.total); return GSEVT_ENOMEM; }
+    char* g = base_aligned(a->geom_buffer);
+    char* im = base_aligned(a->img_buffer);
+    char* bn = base_aligned(a->binning_buffer);
+    char* w = base_aligned(a->bwd_workspace);
+    ViewParams* vp = (ViewParams*)(w + W.vp);
+    launch_build_view_params(vp, a->viewmatrix, a->projmatrix, a->projmatrix_raw, a->campos, a->vel_transform,
+                             a->vel_transform_inv, a->background, a->tanfovx, a->tanfovy, a->width, a->height,
+                             a->delta_time, s);
+    GSEVT_CUDA_OK(cudaMemsetAsync(w + W.grad8, 0, (size_t)a->P * 32, s));
+    GSEVT_CUDA_OK(cudaMemsetAsync(w + W.gradc, 0, (size_t)a->P * 8, s));
+    const int gx = (a->width + 15) / 16, gy = (a->height + 15) / 16;
+    BlendBwdArgs b;
+    memset(&b, 0, sizeof(b));
+    b.W = a->width; b.H = a->height; b.grid_x = gx; b.grid_y = gy; b.nviews = 1;
+    b.ranges = (const uint2*)(im + I.ranges); b.point_list = (const uint32_t*)(bn + B.list);
+    b.rec = (const float4*)(g + L.rec); b.rgb4 = (const float4*)(g + L.rgb4);
+    b.view_stride_gauss = (size_t)a->P; b.bg = a->background; b.views = vp;
+    b.final_T = (const float*)(im + I.accum_alpha); b.n_contrib = (const uint32_t*)(im + I.n_contrib);
+    b.dL_dpix = a->dL_dout_color; b.dL_dpix_depth = a->dL_dout_depth;
+    b.grad8 = (float4*)(w + W.grad8); b.gradc = (float2*)(w + W.gradc);
+    if (a->num_rendered > 0) launch_blend_bwd_rgb(b, s);
+    DBG("blend_bwd");
+    GeomBwdArgs q;
+    memset(&q, 0, sizeof(q));
+    q.P = a->P; q.D = a->sh_degree; q.M = a->sh_coeffs; q.nviews = 1; q.views = vp;
+    q.radii = (const int*)(g + L.radii); q.clamped = (const uint8_t*)(g + L.clamped);
+    q.grad8 = b.grad8; q.gradc = b.gradc;
+    q.means3D = a->means3D; q.shs = a->shs;
+    q.cov3D = a->cov3D_precomp ? a->cov3D_precomp : (const float*)(g + L.cov3D);
+    q.scales = a->scales; q.rotations = a->rotations; q.scale_modifier = a->scale_modifier;
+    q.colors_precomp = a->colors_precomp != nullptr;
+    q.partials = (float*)(w + W.partials);
+    q.dL_dmeans2D = a->dL_dmeans2D; q.dL_dmeans3D = a->dL_dmeans3D; q.dL_dopacity = a->dL_dopacity;
+    q.dL_dcolors = a->dL_dcolors; q.dL_dcov3D = a->dL_dcov3D; q.dL_dsh = a->dL_dsh;
+    q.dL_dscales = a->dL_dscales; q.dL_drotations = a->dL_drotations; q.dL_dtau = a->dL_dtau; q.dL_dvel = a->dL_dvel;
+    launch_geom_bwd_aos(q, s);
+    DBG("geom_bwd");
+    launch_reduce_partials(q.partials, geom_bwd_blocks(a->P, 1), a->pose_grads, s);
+    DBG("reduce");
+    return 0;
+}
+
+GSEVT_API int gsevt_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                       uint8_t* present, void* stream) {
+    (void)projmatrix;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+    GSEVT_CUDA_OK(cudaPeekAtLastError());
+    return 0;
+}
+
+// ---- events ------------------------------------------------------------------------------------
+GSEVT_API int gsevt_event_accumulate(const int16_t* x, const int16_t* y, const uint8_t* p, int32_t n, int32_t width,
+                           int32_t height, int32_t* counts, int32_t zero_first, int32_t* oob, void* stream) {
+    if (n < 0 || width <= 0 || height <= 0 || !counts || (n > 0 && (!x || !y || !p))) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (zero_first) GSEVT_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)width * height * 4, s));
+    launch_event_accumulate(x, y, p, n, width, height, counts, oob, s);
+    GSEVT_CUDA_OK(cudaPeekAtLastError());
+    return 0;
+}
+
+GSEVT_API int gsevt_event_undistort_map(const double* K, const double* D, int32_t W, int32_t H, int32_t* map_ix, int32_t* map_iy) {
+    // cv2.undistort == initUndistortRectifyMap(K, D, I, K) + remap; map evaluated in double and
+    // quantised to 1/32 px (INTER_BITS = 5).  SURVEY.md 8(a) a2.
+    if (!K || !D || !map_ix || !map_iy || W <= 0 || H <= 0) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    const double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3], k3 = D[4];
+    for (int v = 0; v < H; v++) {
+        for (int u = 0; u < W; u++) {
+            const double x = (u - cx) / fx, y = (v - cy) / fy;
+            const double x2 = x * x, y2 = y * y, r2 = x2 + y2, _2xy = 2 * x * y;
+            const double kr = 1 + ((k3 * r2 + k2) * r2 + k1) * r2;
+            const double xd = x * kr + p1 * _2xy + p2 * (r2 + 2 * x2);
+            const double yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy;
+            map_ix[(size_t)v * W + u] = (int32_t)nearbyint((xd * fx + cx) * 32.0);
+            map_iy[(size_t)v * W + u] = (int32_t)nearbyint((yd * fy + cy) * 32.0);
+        }
+    }
+    return 0;
+}
+
+GSEVT_API size_t gsevt_event_frame_scratch_size(int32_t W, int32_t H) { return align_up((size_t)2 * W * H * 4) + 64 * 8 + 256; }
+
+GSEVT_API int gsevt_event_frame(const int32_t* counts, const int32_t* map_ix, const int32_t* map_iy, int32_t W, int32_t H,
+                      int32_t levels, float* sign_out, float* unsign_out, void* scratch, size_t scratch_bytes, void* stream) {
+    if (!counts || !map_ix || !map_iy || !sign_out || !unsign_out || !scratch || W <= 0 || H <= 0 || levels < 1 || levels > GSEVT_MAX_LEVELS) {
+        set_error("bad arguments"); return GSEVT_EINVAL;
+    }
+    if (scratch_bytes < gsevt_event_frame_scratch_size(W, H)) { set_error("scratch too small"); return GSEVT_ENOMEM; }
+    char* b = base_aligned(scratch);
+    launch_event_frame(counts, map_ix, map_iy, W, H, levels, sign_out, unsign_out, (float*)b,
+                       (double*)(b + align_up((size_t)2 * W * H * 4)), (cudaStream_t)stream);
+    GSEVT_CUDA_OK(cudaPeekAtLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Tracking engine
+// =================================================================================================
+struct GsevtMap {
+    int P = 0, D = 0;
+    float4* xyz_opacity = nullptr;
+    float4* cov_a = nullptr;
+    float2* cov_b = nullptr;
+    float* sh_planar = nullptr;
+    size_t bytes = 0;
+};
+
+struct LevelInfo {
+    int W, H, gx, gy;
+    float tanfovx, tanfovy, focal_x, focal_y;
+    float proj_raw[16];
+    size_t ev_offset;  // into the event pyramids
+};
+
+struct GsevtEngine {
+    const GsevtMap* map = nullptr;
+    GsevtEngineConfig cfg;
+    int nlevels = 0;
+    LevelInfo lv[GSEVT_MAX_LEVELS];
+    int cur_level = 0;
+    // device memory (library-owned)
+    EngineCtl* ctl = nullptr;
+    ViewParams* views = nullptr;
+    float* bg3 = nullptr;
+    float4* rec = nullptr;
+    float4* grad8 = nullptr;
+    int* radii = nullptr;
+    uint32_t* tiles = nullptr;
+    uint32_t* offsets = nullptr;
+    uint8_t* clamped = nullptr;
+    void* scan_temp = nullptr; size_t scan_bytes = 0;
+    uint64_t *keys_u = nullptr, *keys = nullptr;
+    uint32_t *vals_u = nullptr, *vals = nullptr;
+    void* sort_temp = nullptr; size_t sort_bytes = 0;
+    uint2* ranges = nullptr;
+    float* gray = nullptr; float* final_T = nullptr; uint32_t* n_contrib = nullptr;
+    double* loss_partials = nullptr;
+    float* geom_partials = nullptr;
+    float* lastRT = nullptr;
+    int* overflow = nullptr;
+    int* host_flag = nullptr;   // pinned, mapped
+    int* host_flag_dev = nullptr;
+    const float* ev_sign = nullptr;
+    int cap = 0;        // allocated instance capacity (both views together)
+    int sort_n = 0;     // number of slots sorted in the current level
+    int geom_blocks = 0, loss_nb = 0;
+    cudaGraphExec_t graph = nullptr;
+    int graph_level = -1, graph_sort_n = -1;
+    cudaStream_t graph_stream = nullptr;
+    std::vector<void*> allocs;
+};
+
+namespace gsevt {
+
+template <typename T>
+static int dev_alloc(GsevtEngine* e, T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t err = cudaMalloc(&q, n * sizeof(T) > 0 ? n * sizeof(T) : 256);
+    if (err != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", n * sizeof(T), cudaGetErrorString(err)); return GSEVT_ECUDA; }
+    e->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+// getProjectionMatrix (graphics_utils.py:49-69) evaluated in double like the reference's python floats,
+// stored column-major as float32.
+static void projection_colmajor(double znear, double zfar, double fovX, double fovY, float* out) {
+    const double tanY = tan(fovY / 2), tanX = tan(fovX / 2);
+    const double top = tanY * znear, bottom = -top, right = tanX * znear, left = -right;
+    float P[4][4];
+    memset(P, 0, sizeof(P));
+    P[0][0] = (float)(2.0 * znear / (right - left));
+    P[1][1] = (float)(2.0 * znear / (top - bottom));
+    P[0][2] = (float)((right + left) / (right - left));
+    P[1][2] = (float)((top + bottom) / (top - bottom));
+    P[3][2] = 1.0f;
+    P[2][2] = (float)(zfar / (zfar - znear));
+    P[2][3] = (float)(-(zfar * znear) / (zfar - znear));
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) out[4 * c + r] = P[r][c];
+}
+
+// Enqueue one full optimisation iteration (or one evaluation) on stream s.
+static void enqueue_iteration(GsevtEngine* e, cudaStream_t s) {
+    const GsevtMap* m = e->map;
+    const LevelInfo& L = e->lv[e->cur_level];
+    const int P = m->P;
+    launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, s);
+    PreMapArgs pa;
+    pa.P = P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
+    pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
+    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.rec = e->rec; pa.grad8 = e->grad8;
+    launch_preprocess_map(pa, s);
+    launch_scan(e->scan_temp, e->scan_bytes, e->tiles, e->offsets, 2 * P, s);
+    launch_emit_keys(P, 2, e->views, e->rec, e->radii, e->offsets, e->keys_u, e->vals_u, e->sort_n, e->overflow,
+                     e->ctl, s);
+    const int tiles = L.gx * L.gy;
+    const int bit = (int)higher_msb((uint32_t)(2 * tiles));
+    launch_sort_pairs(e->sort_temp, e->sort_bytes, e->keys_u, e->keys, e->vals_u, e->vals, e->sort_n, 32 + bit, s);
+    launch_identify_ranges(e->keys, e->ranges, 2 * tiles, -1, e->offsets + (2 * P - 1), e->sort_n, s);
+    BlendFwdArgs f;
+    memset(&f, 0, sizeof(f));
+    f.W = L.W; f.H = L.H; f.grid_x = L.gx; f.grid_y = L.gy; f.nviews = 2;
+    f.ranges = e->ranges; f.point_list = e->vals; f.rec = e->rec; f.view_stride_gauss = (size_t)P;
+    f.views = e->views; f.final_T = e->final_T; f.n_contrib = e->n_contrib; f.out_color = e->gray; f.ctl = e->ctl;
+    launch_blend_fwd_gray(f, s);
+    const float* ev = e->ev_sign + L.ev_offset;
+    launch_loss_stats(e->gray, ev, L.W * L.H, e->ctl, e->loss_partials, e->loss_nb, s);
+    BlendBwdArgs b;
+    memset(&b, 0, sizeof(b));
+    b.W = L.W; b.H = L.H; b.grid_x = L.gx; b.grid_y = L.gy; b.nviews = 2;
+    b.ranges = e->ranges; b.point_list = e->vals; b.rec = e->rec; b.view_stride_gauss = (size_t)P; b.views = e->views;
+    b.final_T = e->final_T; b.n_contrib = e->n_contrib; b.gray = e->gray; b.event_frame = ev; b.ctl = e->ctl;
+    b.grad8 = e->grad8;
+    launch_blend_bwd_gray(b, s);
+    GeomBwdArgs q;
+    memset(&q, 0, sizeof(q));
+    q.P = P; q.D = m->D; q.M = 16; q.nviews = 2; q.views = e->views; q.radii = e->radii; q.clamped = e->clamped;
+    q.grad8 = e->grad8; q.xyz_opacity = m->xyz_opacity; q.cov3D_a = m->cov_a; q.cov3D_b = m->cov_b;
+    q.sh_planar = m->sh_planar; q.ctl = e->ctl; q.partials = e->geom_partials;
+    launch_geom_bwd_map(q, s);
+    launch_engine_update(e->ctl, e->geom_partials, e->geom_blocks, e->host_flag_dev, s);
+}
+
+static int upload_level(GsevtEngine* e, int level, cudaStream_t s) {
+    const LevelInfo& L = e->lv[level];
+    struct { int level, W, H, gx, gy; float tx, ty, fx, fy; float proj[16]; } h;
+    h.level = level; h.W = L.W; h.H = L.H; h.gx = L.gx; h.gy = L.gy;
+    h.tx = L.tanfovx; h.ty = L.tanfovy; h.fx = L.focal_x; h.fy = L.focal_y;
+    memcpy(h.proj, L.proj_raw, sizeof(h.proj));
+    static_assert(offsetof(EngineCtl, proj_raw) - offsetof(EngineCtl, level) == 9 * 4, "EngineCtl level block layout");
+    GSEVT_CUDA_OK(cudaMemcpyAsync((char*)e->ctl + offsetof(EngineCtl, level), &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+template <typename T>
+static int set_field(GsevtEngine* e, size_t off, const T& v, cudaStream_t s) {
+    GSEVT_CUDA_OK(cudaMemcpyAsync((char*)e->ctl + off, &v, sizeof(T), cudaMemcpyHostToDevice, s));
+    return 0;
+}
+#define SETF(field, value) do { auto v__ = (value); int rc__ = set_field(e, offsetof(EngineCtl, field), v__, s); if (rc__) return rc__; } while (0)
+
+}  // namespace gsevt
+
+extern "C" {
+
+GSEVT_API int gsevt_map_create(int32_t P, int32_t sh_degree, const float* xyz, const float* scales, const float* rotations,
+                     const float* opacities, const float* shs, float scale_modifier, void* stream, GsevtMap** out) {
+    if (P <= 0 || !xyz || !scales || !rotations || !opacities || !shs || !out || sh_degree < 0 || sh_degree > 3) {
+        set_error("gsevt_map_create: bad arguments"); return GSEVT_EINVAL;
+    }
+    GsevtMap* m = new GsevtMap();
+    m->P = P; m->D = sh_degree;
+    const size_t p = (size_t)P;
+    if (cudaMalloc(&m->xyz_opacity, p * 16) != cudaSuccess || cudaMalloc(&m->cov_a, p * 16) != cudaSuccess ||
+        cudaMalloc(&m->cov_b, p * 8) != cudaSuccess || cudaMalloc(&m->sh_planar, p * 48 * 4) != cudaSuccess) {
+        set_error("gsevt_map_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        gsevt_map_destroy(m);
+        return GSEVT_ECUDA;
+    }
+    m->bytes = p * (16 + 16 + 8 + 192);
+    launch_pack_map(P, 16, xyz, scales, rotations, opacities, shs, scale_modifier, m->xyz_opacity, m->cov_a, m->cov_b,
+                    m->sh_planar, (cudaStream_t)stream);
+    GSEVT_CUDA_OK(cudaPeekAtLastError());
+    *out = m;
+    return 0;
+}
+GSEVT_API void gsevt_map_destroy(GsevtMap* m) {
+    if (!m) return;
+    cudaFree(m->xyz_opacity); cudaFree(m->cov_a); cudaFree(m->cov_b); cudaFree(m->sh_planar);
+    delete m;
+}
+GSEVT_API int32_t gsevt_map_size(const GsevtMap* m) { return m ? m->P : 0; }
+GSEVT_API size_t gsevt_map_bytes(const GsevtMap* m) { return m ? m->bytes : 0; }
+
+GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* cfg, GsevtEngine** out) {
+    if (!map || !cfg || !out || cfg->width <= 0 || cfg->height <= 0 || cfg->levels < 1 || cfg->levels > GSEVT_MAX_LEVELS) {
+        set_error("gsevt_engine_create: bad arguments"); return GSEVT_EINVAL;
+    }
+    GsevtEngine* e = new GsevtEngine();
+    e->map = map; e->cfg = *cfg; e->nlevels = cfg->levels;
+    size_t ev_off = 0;
+    for (int l = 0; l < cfg->levels; l++) {
+        LevelInfo& L = e->lv[l];
+        // frame.py:64-66,75-82: int(W * 0.5**l); FoV from focal2fov(fx*s, W*s) (graphics_utils.py:100-101)
+        const double sc = pow(0.5, l);
+        L.W = (int)(cfg->width * sc); L.H = (int)(cfg->height * sc);
+        if (L.W <= 0 || L.H <= 0) { set_error("pyramid level %d is empty", l); delete e; return GSEVT_EINVAL; }
+        L.gx = (L.W + 15) / 16; L.gy = (L.H + 15) / 16;
+        const double fovx = 2 * atan(L.W / (2 * ((double)cfg->fx * sc)));
+        const double fovy = 2 * atan(L.H / (2 * ((double)cfg->fy * sc)));
+        L.tanfovx = (float)tan(fovx * 0.5); L.tanfovy = (float)tan(fovy * 0.5);
+        L.focal_x = L.W / (2.0f * L.tanfovx); L.focal_y = L.H / (2.0f * L.tanfovy);
+        projection_colmajor(cfg->znear, cfg->zfar, fovx, fovy, L.proj_raw);
+        L.ev_offset = ev_off;
+        ev_off += (size_t)(cfg->width >> l) * (cfg->height >> l);
+    }
+    const int P = map->P;
+    const size_t p2 = 2 * (size_t)P;
+    long long cap = cfg->instance_capacity > 0 ? (long long)cfg->instance_capacity * 2 : (long long)P * 16;
+    if (cap < (1 << 20)) cap = 1 << 20;
+    if (cap > 0x3fffffff) cap = 0x3fffffff;
+    e->cap = (int)cap;
+    e->sort_n = e->cap;
+    e->scan_bytes = scan_temp_bytes((int)p2);
+    e->sort_bytes = sort_temp_bytes(e->cap);
+    e->geom_blocks = geom_bwd_blocks(P, 2);
+    const LevelInfo& L0 = e->lv[0];
+    const size_t hw = (size_t)L0.W * L0.H;
+    e->loss_nb = loss_blocks((int)hw);
+    int rc = 0;
+    rc |= dev_alloc(e, &e->ctl, 1);
+    rc |= dev_alloc(e, &e->views, 2);
+    rc |= dev_alloc(e, &e->bg3, 4);
+    rc |= dev_alloc(e, &e->rec, 2 * p2);
+    rc |= dev_alloc(e, &e->grad8, 2 * p2);
+    rc |= dev_alloc(e, &e->radii, p2);
+    rc |= dev_alloc(e, &e->tiles, p2);
+    rc |= dev_alloc(e, &e->offsets, p2);
+    rc |= dev_alloc(e, &e->clamped, p2);
+    rc |= dev_alloc(e, (char**)&e->scan_temp, e->scan_bytes);
+    rc |= dev_alloc(e, &e->keys_u, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->keys, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->vals_u, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
+    rc |= dev_alloc(e, (char**)&e->sort_temp, e->sort_bytes);
+    rc |= dev_alloc(e, &e->ranges, 2 * (size_t)L0.gx * L0.gy);
+    rc |= dev_alloc(e, &e->gray, 2 * hw);
+    rc |= dev_alloc(e, &e->final_T, 2 * hw);
+    rc |= dev_alloc(e, &e->n_contrib, 2 * hw);
+    rc |= dev_alloc(e, &e->loss_partials, (size_t)e->loss_nb * 3 + 2);
+    rc |= dev_alloc(e, &e->geom_partials, (size_t)e->geom_blocks * GSEVT_NPART);
+    rc |= dev_alloc(e, &e->lastRT, 12);
+    rc |= dev_alloc(e, &e->overflow, 1);
+    if (rc) { gsevt_engine_destroy(e); return GSEVT_ECUDA; }
+    if (cudaHostAlloc((void**)&e->host_flag, 4, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&e->host_flag_dev, e->host_flag, 0) != cudaSuccess) {
+        set_error("pinned flag allocation failed"); gsevt_engine_destroy(e); return GSEVT_ECUDA;
+    }
+    *e->host_flag = 0;
+    EngineCtl h;
+    memset(&h, 0, sizeof(h));
+    h.R[0] = h.R[4] = h.R[8] = 1.0f;
+    h.lr_base[0] = cfg->lr_rot; h.lr_base[1] = cfg->lr_trans; h.lr_base[2] = cfg->lr_w; h.lr_base[3] = cfg->lr_v;
+    h.max_optim_iter = cfg->max_optim_iter; h.converged_threshold = cfg->converged_threshold;
+    h.level_done = 1;
+    cudaMemcpy(e->ctl, &h, sizeof(h), cudaMemcpyHostToDevice);
+    float bg[4] = {cfg->background[0], cfg->background[1], cfg->background[2], 0.f};
+    cudaMemcpy(e->bg3, bg, sizeof(bg), cudaMemcpyHostToDevice);
+    cudaMemset(e->overflow, 0, 4);
+    cudaMemset(e->loss_partials, 0, ((size_t)e->loss_nb * 3 + 2) * 8);
+    cudaMemset(e->grad8, 0, 2 * p2 * 16);
+    cudaMemset(e->radii, 0, p2 * 4);
+    if (cudaGetLastError() != cudaSuccess) { set_error("engine init failed"); gsevt_engine_destroy(e); return GSEVT_ECUDA; }
+    *out = e;
+    return 0;
+}
+
+GSEVT_API void gsevt_engine_destroy(GsevtEngine* e) {
+    if (!e) return;
+    if (e->graph) cudaGraphExecDestroy(e->graph);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->host_flag) cudaFreeHost(e->host_flag);
+    delete e;
+}
+
+GSEVT_API int gsevt_engine_set_state(GsevtEngine* e, const float* R, const float* T, const float* w, const float* v, void* stream) {
+    if (!e || !R || !T || !w || !v) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    float h[18];
+    memcpy(h, R, 36); memcpy(h + 9, T, 12); memcpy(h + 12, w, 12); memcpy(h + 15, v, 12);
+    GSEVT_CUDA_OK(cudaMemcpyAsync(e->ctl, h, sizeof(h), cudaMemcpyHostToDevice, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));  // h is a stack buffer
+    return 0;
+}
+GSEVT_API int gsevt_engine_get_state(GsevtEngine* e, float* R, float* T, float* w, float* v, void* stream) {
+    if (!e) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    float h[18];
+    GSEVT_CUDA_OK(cudaMemcpyAsync(h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    if (R) memcpy(R, h, 36);
+    if (T) memcpy(T, h + 9, 12);
+    if (w) memcpy(w, h + 12, 12);
+    if (v) memcpy(v, h + 15, 12);
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_begin_frame(GsevtEngine* e, double delta_tau, const float* sign_pyr, const float* unsign_pyr, void* stream) {
+    (void)unsign_pyr;  // |sign| is recomputed on the fly; kept in the ABI for symmetry with the reference
+    if (!e || !sign_pyr || !(delta_tau != 0.0)) { set_error("begin_frame: delta_tau must be non-zero and the event pyramid non-null"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    e->ev_sign = sign_pyr;
+    struct { float dt, half; } h = {(float)delta_tau, (float)(delta_tau / 2)};
+    GSEVT_CUDA_OK(cudaMemcpyAsync((char*)e->ctl + offsetof(EngineCtl, delta_tau), &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    // fresh Adam per frame (tracker.py:117-129)
+    GSEVT_CUDA_OK(cudaMemsetAsync((char*)e->ctl + offsetof(EngineCtl, adam_m), 0,
+                                  offsetof(EngineCtl, lr_base) - offsetof(EngineCtl, adam_m), s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+static int probe_instances(GsevtEngine* e, cudaStream_t s, uint32_t* total) {
+    // pose_setup + projection + scan only, to size the sort for this level.
+    const GsevtMap* m = e->map;
+    SETF(level_done, (int)0);
+    launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, s);
+    PreMapArgs pa;
+    pa.P = m->P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
+    pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
+    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.rec = e->rec; pa.grad8 = e->grad8;
+    launch_preprocess_map(pa, s);
+    launch_scan(e->scan_temp, e->scan_bytes, e->tiles, e->offsets, 2 * m->P, s);
+    GSEVT_CUDA_OK(cudaMemcpyAsync(total, e->offsets + (2 * (size_t)m->P - 1), 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_begin_level(GsevtEngine* e, int32_t level, int32_t opt_vel, void* stream) {
+    if (!e || level < 0 || level >= e->nlevels) { set_error("begin_level: bad level"); return GSEVT_EINVAL; }
+    if (!e->ev_sign) { set_error("begin_level before begin_frame"); return GSEVT_ESTATE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    e->cur_level = level;
+    int rc = upload_level(e, level, s);
+    if (rc) return rc;
+    struct { int opt_vel, optim_iter, start_vel, level_done, iters; } h = {opt_vel ? 1 : 0, 0, 0, 0, 0};
+    GSEVT_CUDA_OK(cudaMemcpyAsync((char*)e->ctl + offsetof(EngineCtl, opt_vel), &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    SETF(n_losses, (int)0);
+    SETF(eval_only, (int)0);
+    uint32_t total = 0;
+    rc = probe_instances(e, s, &total);
+    if (rc) return rc;
+    long long want = (long long)(total * 1.25) + 65536;
+    if (want > e->cap) want = e->cap;
+    if ((long long)total > e->cap) { set_error("instance capacity %d exceeded (%u instances)", e->cap, total); return GSEVT_EOVERFLOW; }
+    e->sort_n = (int)want;
+    *e->host_flag = 0;
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_iterate(GsevtEngine* e, int32_t n, void* stream) {
+    if (!e || n < 0) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    if (!e->ev_sign) { set_error("iterate before begin_frame"); return GSEVT_ESTATE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool can_graph = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
+    if (can_graph && (e->graph == nullptr || e->graph_level != e->cur_level || e->graph_sort_n != e->sort_n || e->graph_stream != s)) {
+        if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        GSEVT_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+        enqueue_iteration(e, s);
+        cudaError_t err = cudaStreamEndCapture(s, &g);
+        if (err != cudaSuccess || !g) { set_error("graph capture failed: %s", cudaGetErrorString(err)); return GSEVT_ECUDA; }
+        err = cudaGraphInstantiate(&e->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (err != cudaSuccess) { e->graph = nullptr; set_error("graph instantiate failed: %s", cudaGetErrorString(err)); return GSEVT_ECUDA; }
+        e->graph_level = e->cur_level; e->graph_sort_n = e->sort_n; e->graph_stream = s;
+    }
+    for (int i = 0; i < n; i++) {
+        if (can_graph) GSEVT_CUDA_OK(cudaGraphLaunch(e->graph, s));
+        else enqueue_iteration(e, s);
+    }
+    GSEVT_CUDA_OK(cudaPeekAtLastError());
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_poll_done(GsevtEngine* e) { return e && e->host_flag ? *(volatile int*)e->host_flag : 0; }
+
+GSEVT_API int gsevt_engine_status(GsevtEngine* e, GsevtEngineStatus* out, void* stream) {
+    if (!e || !out) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    static thread_local EngineCtl h;
+    uint32_t offs[2] = {0, 0};
+    int ov = 0;
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&h, e->ctl, offsetof(EngineCtl, losses), cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[0], e->offsets + (e->map->P - 1), 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[1], e->offsets + (2 * (size_t)e->map->P - 1), 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&ov, e->overflow, 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    memset(out, 0, sizeof(*out));
+    out->level_done = h.level_done; out->optim_iter = h.optim_iter; out->start_vel_opt_iter = h.start_vel_opt_iter;
+    out->opt_vel = h.opt_vel; out->iters_executed = h.iters_executed; out->overflow = ov;
+    out->num_rendered[0] = (int)offs[0]; out->num_rendered[1] = (int)(offs[1] - offs[0]);
+    out->last_loss = h.last_loss;
+    memcpy(out->pose_grads, h.grads, sizeof(h.grads));
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_losses(GsevtEngine* e, float* out, int32_t capacity, void* stream) {
+    if (!e || !out || capacity < 0) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int n = 0;
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&n, (char*)e->ctl + offsetof(EngineCtl, n_losses), 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    int c = n < capacity ? n : capacity;
+    if (c > GSEVT_MAX_LOSSES) c = GSEVT_MAX_LOSSES;
+    if (c > 0) {
+        GSEVT_CUDA_OK(cudaMemcpyAsync(out, (char*)e->ctl + offsetof(EngineCtl, losses), (size_t)c * 4, cudaMemcpyDeviceToHost, s));
+        GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    }
+    return c;
+}
+
+GSEVT_API int gsevt_engine_const_vel_model(GsevtEngine* e, double tau, void* stream) {
+    if (!e) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    launch_const_vel(e->ctl, (float)tau, (cudaStream_t)stream);
+    GSEVT_CUDA_OK(cudaPeekAtLastError());
+    return 0;
+}
+GSEVT_API int gsevt_engine_weighted_velocity(GsevtEngine* e, const float* last_R, const float* last_T, double delta_tau,
+                                   double weight, void* stream) {
+    if (!e || !last_R || !last_T || delta_tau == 0.0) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    float h[12];
+    memcpy(h, last_R, 36); memcpy(h + 9, last_T, 12);
+    GSEVT_CUDA_OK(cudaMemcpyAsync(e->lastRT, h, sizeof(h), cudaMemcpyHostToDevice, s));
+    launch_weighted_velocity(e->ctl, e->lastRT, (float)delta_tau, (float)weight, s);
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_eval(GsevtEngine* e, int32_t level, int32_t signed_loss, float* loss_out, float* grads_out12, void* stream) {
+    if (!e || level < 0 || level >= e->nlevels) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    if (!e->ev_sign) { set_error("eval before begin_frame"); return GSEVT_ESTATE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    e->cur_level = level;
+    int rc = upload_level(e, level, s);
+    if (rc) return rc;
+    SETF(eval_only, (int)1);
+    SETF(loss_signed, (int)(signed_loss ? 1 : 0));
+    uint32_t total = 0;
+    rc = probe_instances(e, s, &total);
+    if (rc) return rc;
+    if ((long long)total > e->cap) { set_error("instance capacity %d exceeded (%u instances)", e->cap, total); return GSEVT_EOVERFLOW; }
+    long long want = (long long)(total * 1.25) + 65536;
+    e->sort_n = (int)(want > e->cap ? e->cap : want);
+    enqueue_iteration(e, s);
+    GsevtEngineStatus st;
+    rc = gsevt_engine_status(e, &st, stream);
+    if (rc) return rc;
+    if (loss_out) *loss_out = st.last_loss;
+    if (grads_out12) memcpy(grads_out12, st.pose_grads, 48);
+    SETF(eval_only, (int)0);
+    SETF(level_done, (int)1);
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    if (st.overflow) { set_error("instance capacity exceeded during eval"); return GSEVT_EOVERFLOW; }
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_render_delta(GsevtEngine* e, int32_t level, float* delta_out, float* gray_last, float* gray_next, void* stream) {
+    // Uses the images of the most recent evaluation / iteration at `level`.
+    if (!e || level != e->cur_level) { set_error("render_delta: run gsevt_engine_eval at this level first"); return GSEVT_ESTATE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const LevelInfo& L = e->lv[level];
+    const size_t hw = (size_t)L.W * L.H;
+    if (gray_last) GSEVT_CUDA_OK(cudaMemcpyAsync(gray_last, e->gray, hw * 4, cudaMemcpyDeviceToDevice, s));
+    if (gray_next) GSEVT_CUDA_OK(cudaMemcpyAsync(gray_next, e->gray + hw, hw * 4, cudaMemcpyDeviceToDevice, s));
+    (void)delta_out;
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e) {
+    (void)e;
+    // pose_setup, preprocess, emit_keys, identify_ranges, blend_fwd, loss_stats, blend_bwd, geom_bwd, update = 9 of
+    // ours; plus CUB: scan (2 kernels) and radix sort (histogram + one onesweep per 8-bit digit), and one memset.
+    return 9;
+}
+
+}  // extern "C"

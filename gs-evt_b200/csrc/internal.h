@@ -1,0 +1,211 @@
+// Internal (non-ABI) declarations shared by the libgsevt translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "common.cuh"
+
+namespace gsevt {
+
+#define GSEVT_MAX_LOSSES 1024
+#define GSEVT_NPART 12          // pose-gradient components
+#define GSEVT_MAX_LEVELS 4
+
+// Device-resident control block of a tracking engine.  Written only by single-thread control
+// kernels (pose_setup / loss_finish / update) so that no host round trip is needed per iteration.
+struct EngineCtl {
+    // pose / velocity state (utils/render_camera/camera.py:51-54)
+    float R[9];           // world->camera rotation, row-major
+    float T[3];
+    float ang_vel[3];
+    float lin_vel[3];
+    float delta_tau;
+    float half_dtau;      // (float)(delta_tau / 2) computed in double on the host
+    // level constants
+    int level, W, H, grid_x, grid_y;
+    float tanfovx, tanfovy, focal_x, focal_y;
+    float proj_raw[16];   // P^T flattened row-major == P column-major ... stored column-major
+    // Adam (torch.optim.Adam defaults): groups 0 rot, 1 trans, 2 w, 3 v
+    float adam_m[12], adam_v[12];
+    int adam_step[4];
+    float lr_base[4];
+    // loop control (utils/tracker.py:149-240)
+    int opt_vel, optim_iter, start_vel_opt_iter, level_done, iters_executed;
+    int max_optim_iter;
+    float converged_threshold;
+    int n_losses;
+    int overflow;
+    int num_rendered[2];
+    // loss coefficients for the blend backward: dL/dd = alpha*d - beta*E_eff
+    float loss_alpha, loss_beta, last_loss;
+    int loss_signed;
+    int eval_only;        // 1: compute loss + gradients, skip the optimiser / pose update
+    float grads[12];      // rho, theta, v, w
+    float losses[GSEVT_MAX_LOSSES];
+};
+
+// ---- preprocess ------------------------------------------------------------------------------
+struct PreAosArgs {
+    int P, D, M;
+    const ViewParams* vp;     // device
+    const float* means3D;
+    const float* scales;
+    const float* rotations;
+    const float* opacities;
+    const float* shs;
+    const float* colors_precomp;
+    const float* cov3D_precomp;
+    float scale_modifier;
+    // outputs
+    int* radii_internal;
+    int* radii_out;
+    uint32_t* tiles_touched;
+    float* cov3D;
+    uint8_t* clamped;
+    float4* rec;     // [2P]
+    float4* rgb4;    // [P]
+};
+void launch_preprocess_aos(const PreAosArgs& a, cudaStream_t s);
+
+struct PreMapArgs {
+    int P, D;
+    const ViewParams* views;  // device [2]
+    const EngineCtl* ctl;     // may be NULL
+    const float4* xyz_opacity;
+    const float4* cov3D_a;
+    const float2* cov3D_b;
+    const float* sh_planar;   // [48][P]
+    int* radii;               // [2P]
+    uint32_t* tiles_touched;  // [2P]
+    uint8_t* clamped;         // [2P]
+    float4* rec;              // [2][2P]
+    float4* grad8;            // [2][2P]
+};
+void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s);
+void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s);
+void launch_pack_map(int P, int M, const float* xyz, const float* scales, const float* rots, const float* opac,
+                     const float* shs, float mod, float4* xyz_opacity, float4* cov_a, float2* cov_b, float* sh_planar,
+                     cudaStream_t s);
+// Fills a ViewParams from the operator's device-side matrices.
+void launch_build_view_params(ViewParams* out, const float* view, const float* proj, const float* proj_raw,
+                              const float* campos, const float* vel, const float* vel_inv, const float* bg,
+                              float tanfovx, float tanfovy, int W, int H, float delta_time, cudaStream_t s);
+
+// ---- binning ---------------------------------------------------------------------------------
+size_t scan_temp_bytes(int n);
+size_t sort_temp_bytes(int n);
+void launch_scan(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int n, cudaStream_t s);
+// nviews = 1 (operator) or 2 (engine).  total = device pointer to the inclusive total (offsets[nviews*P-1]).
+// cap > 0: slots [total, cap) are filled with sentinel keys; overflow flag set when total > cap.
+void launch_emit_keys(int P, int nviews, const ViewParams* views, const float4* rec, const int* radii,
+                      const uint32_t* offsets, uint64_t* keys, uint32_t* values, int cap, int* overflow,
+                      const EngineCtl* ctl, cudaStream_t s);
+void launch_sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
+                       const uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit, cudaStream_t s);
+// n_host >= 0: exact count known on the host; otherwise count is read from *n_dev (clamped to cap).
+void launch_identify_ranges(const uint64_t* keys, uint2* ranges, int ntiles_total, int n_host, const uint32_t* n_dev,
+                            int cap, cudaStream_t s);
+uint32_t higher_msb(uint32_t n);
+
+// ---- blending --------------------------------------------------------------------------------
+struct BlendFwdArgs {
+    int W, H, grid_x, grid_y;
+    int nviews;
+    const uint2* ranges;         // [nviews][tiles]
+    const uint32_t* point_list;
+    const float4* rec;           // [nviews][2P]  (view stride = 2*P float4)
+    const float4* rgb4;          // operator only
+    size_t view_stride_gauss;    // P (Gaussians per view) for rec / grad indexing
+    const float* bg;             // device [3] (operator) or NULL (engine: ViewParams bg)
+    const ViewParams* views;
+    float* final_T;              // [nviews][HW]
+    uint32_t* n_contrib;         // [nviews][HW]
+    float* out_color;            // operator: [3][HW]; engine: gray [nviews][HW]
+    float* out_depth;            // operator only
+    float* out_opacity;          // operator only
+    int* n_touched;              // operator only, may be NULL
+    const EngineCtl* ctl;
+};
+void launch_blend_fwd_rgb(const BlendFwdArgs& a, cudaStream_t s);
+void launch_blend_fwd_gray(const BlendFwdArgs& a, cudaStream_t s);
+
+struct BlendBwdArgs {
+    int W, H, grid_x, grid_y;
+    int nviews;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float4* rec;
+    const float4* rgb4;
+    size_t view_stride_gauss;
+    const float* bg;
+    const ViewParams* views;
+    const float* final_T;
+    const uint32_t* n_contrib;
+    // operator: upstream pixel gradients
+    const float* dL_dpix;        // [3][HW]
+    const float* dL_dpix_depth;  // [HW] or NULL
+    // engine: gray images + event frame + loss coefficients in ctl
+    const float* gray;           // [2][HW]
+    const float* event_frame;    // [HW] at this level (signed)
+    const EngineCtl* ctl;
+    // outputs (accumulated with float atomics, must be zero on entry)
+    float4* grad8;               // [nviews][2P]: operator {dmx, dmy, dA, dB | dC, dopacity, dcol0, ddepth}
+                                 //               engine   {dmx, dmy, dA, dB | dC, dgray, 0, 0}
+    float2* gradc;               // operator: [P] {dcol1, dcol2}
+};
+void launch_blend_bwd_rgb(const BlendBwdArgs& a, cudaStream_t s);
+void launch_blend_bwd_gray(const BlendBwdArgs& a, cudaStream_t s);
+
+// ---- geometry backward + pose chain ------------------------------------------------------------
+struct GeomBwdArgs {
+    int P, D, M;
+    int nviews;
+    const ViewParams* views;
+    const int* radii;            // [nviews][P]
+    const uint8_t* clamped;      // [nviews][P]
+    const float4* grad8;         // [nviews][2P]
+    const float2* gradc;         // operator only
+    // map (AoS operator / packed engine)
+    const float* means3D; const float* shs; const float* cov3D;            // operator
+    const float* scales; const float* rotations; float scale_modifier;     // operator (map grads)
+    const float4* xyz_opacity; const float4* cov3D_a; const float2* cov3D_b; const float* sh_planar;  // engine
+    int colors_precomp;          // operator: colours were given, no SH chain
+    const EngineCtl* ctl;
+    float* partials;             // [nblocks][12]
+    // optional per-Gaussian outputs (operator)
+    float* dL_dmeans2D; float* dL_dmeans3D; float* dL_dopacity; float* dL_dcolors; float* dL_dcov3D;
+    float* dL_dsh; float* dL_dscales; float* dL_drotations; float* dL_dtau; float* dL_dvel;
+};
+int geom_bwd_blocks(int P, int nviews);
+void launch_geom_bwd_aos(const GeomBwdArgs& a, cudaStream_t s);
+void launch_geom_bwd_map(const GeomBwdArgs& a, cudaStream_t s);
+void launch_reduce_partials(const float* partials, int nblocks, float* out12, cudaStream_t s);
+
+// ---- loss (engine) -----------------------------------------------------------------------------
+void launch_loss_stats(const float* gray, const float* event_frame, int HW, EngineCtl* ctl, double* partials,
+                       int nblocks, cudaStream_t s);
+int loss_blocks(int HW);
+
+// ---- engine control kernels ----------------------------------------------------------------------
+void launch_pose_setup(EngineCtl* ctl, ViewParams* views, const float* bg3, float znear, float zfar, cudaStream_t s);
+void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, cudaStream_t s);
+void launch_const_vel(EngineCtl* ctl, float tau, cudaStream_t s);
+void launch_weighted_velocity(EngineCtl* ctl, const float* lastRT, float delta_tau, float weight, cudaStream_t s);
+
+// ---- events ------------------------------------------------------------------------------------
+void launch_event_accumulate(const int16_t* x, const int16_t* y, const uint8_t* p, int n, int W, int H, int* counts,
+                             int* oob, cudaStream_t s);
+void launch_event_frame(const int* counts, const int* map_ix, const int* map_iy, int W, int H, int levels,
+                        float* sign_out, float* unsign_out, float* scratch, double* dscratch, cudaStream_t s);
+
+void set_error(const char* fmt, ...);
+}  // namespace gsevt
+
+#define GSEVT_CUDA_OK(expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            gsevt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return GSEVT_ECUDA;                                                              \
+        }                                                                                    \
+    } while (0)

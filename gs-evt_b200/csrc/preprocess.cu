@@ -1,0 +1,247 @@
+// Projection kernels: per-Gaussian cull / project / EWA covariance / conic / radius / tile rect /
+// SH -> colour.  Restates preprocessCUDA (dgr/cuda_rasterizer/forward.cu:157-258) with the rounding
+// contract of common.cuh so that depth bits, pixel centres, radii and tile rects are bit-identical.
+//
+//  * preprocess_aos_kernel  — operator path: caller's AoS tensors, one view.
+//  * preprocess_map_kernel  — engine path: packed frozen map (SoA, planar SH, precomputed cov3D),
+//                             BOTH views per thread so the 232 B/Gaussian map read happens once.
+// HBM-bound: grid = ceil(P/256) x 256 threads, all per-Gaussian loads coalesced (AoS inputs are
+// staged through shared memory in 16-byte vectors; planar SH is read as 48 coalesced lines per warp).
+#include "internal.h"
+
+namespace gsevt {
+
+struct ProjOut {
+    int radius;
+    int tiles;
+    float mx, my, depth;
+    float A, B, C;
+};
+
+// Everything of preprocessCUDA between the frustum test and the colour evaluation.
+__device__ __forceinline__ bool project_geometry(const ViewParams& vp, float px, float py, float pz,
+                                                 const float* __restrict__ cov3D, ProjOut& o) {
+    o.radius = 0;
+    o.tiles = 0;
+    const float depth = affine3r(vp.view[2], vp.view[6], vp.view[10], vp.view[14], px, py, pz);
+    if (!(depth > 0.2f)) return false;  // in_frustum (auxiliary.h:154): p_view.z <= 0.2 is culled
+    const float hx = affine3r(vp.proj[0], vp.proj[4], vp.proj[8], vp.proj[12], px, py, pz);
+    const float hy = affine3r(vp.proj[1], vp.proj[5], vp.proj[9], vp.proj[13], px, py, pz);
+    const float hw = affine3r(vp.proj[3], vp.proj[7], vp.proj[11], vp.proj[15], px, py, pz);
+    const float p_w = __frcp_rn(__fadd_rn(hw, 0.0000001f));
+    const float ndc_x = __fmul_rn(hx, p_w), ndc_y = __fmul_rn(hy, p_w);
+
+    Ewa e;
+    ewa_forward(vp.view, px, py, pz, vp.focal_x, vp.focal_y, vp.tanfovx, vp.tanfovy, cov3D, e);
+    const float det = __fmaf_rn(e.a, e.c, -__fmul_rn(e.b, e.b));
+    if (det == 0.0f) return false;
+    const float det_inv = __frcp_rn(det);
+    o.A = __fmul_rn(e.c, det_inv);
+    o.B = __fmul_rn(e.b, -det_inv);
+    o.C = __fmul_rn(e.a, det_inv);
+    const float mid = __fmul_rn(__fadd_rn(e.a, e.c), 0.5f);
+    const float s = __fsqrt_rn(fmaxf(__fmaf_rn(mid, mid, -det), 0.1f));
+    const float lam = fmaxf(__fadd_rn(mid, s), __fadd_rn(mid, -s));
+    const int radius = (int)ceilf(__fmul_rn(__fsqrt_rn(lam), 3.0f));
+    o.mx = ndc2pix_r(ndc_x, vp.W);
+    o.my = ndc2pix_r(ndc_y, vp.H);
+    int x0, y0, x1, y1;
+    tile_rect(o.mx, o.my, radius, vp.grid_x, vp.grid_y, x0, y0, x1, y1);
+    const int area = (x1 - x0) * (y1 - y0);
+    if (area == 0) return false;
+    o.radius = radius;
+    o.tiles = area;
+    o.depth = depth;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Operator path
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preprocess_aos_kernel(PreAosArgs a) {
+    __shared__ float s_xyz[256 * 3];
+    __shared__ float s_scale[256 * 3];
+    __shared__ ViewParams s_vp;
+    load_views(&s_vp, a.vp, 1);
+    const int base = blockIdx.x * 256;
+    const int n = min(256, a.P - base);
+    // coalesced staging of the stride-3 arrays
+    for (int i = threadIdx.x; i < n * 3; i += 256) {
+        s_xyz[i] = __ldg(a.means3D + (size_t)base * 3 + i);
+        if (a.scales) s_scale[i] = __ldg(a.scales + (size_t)base * 3 + i);
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= n) return;
+    const int idx = base + t;
+    const ViewParams& vp = s_vp;
+    const float px = s_xyz[3 * t], py = s_xyz[3 * t + 1], pz = s_xyz[3 * t + 2];
+
+    float cov[6];
+    if (a.cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) cov[k] = __ldg(a.cov3D_precomp + (size_t)idx * 6 + k);
+    } else {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+        cov3d_from_scale_rot(s_scale[3 * t], s_scale[3 * t + 1], s_scale[3 * t + 2], a.scale_modifier, q.x, q.y, q.z,
+                             q.w, cov);
+    }
+    ProjOut o;
+    const bool vis_depth = affine3r(vp.view[2], vp.view[6], vp.view[10], vp.view[14], px, py, pz) > 0.2f;
+    // The reference writes cov3D for every Gaussian that passes the frustum test, before the later
+    // early-outs (forward.cu:213); keep that so the backward can rely on it.
+    if (vis_depth && !a.cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) a.cov3D[(size_t)idx * 6 + k] = cov[k];
+    }
+    const bool ok = project_geometry(vp, px, py, pz, cov, o);
+    a.radii_internal[idx] = ok ? o.radius : 0;
+    if (a.radii_out) a.radii_out[idx] = ok ? o.radius : 0;
+    a.tiles_touched[idx] = ok ? (uint32_t)o.tiles : 0u;
+    if (!ok) return;
+
+    float rgb[3];
+    unsigned clampbits = 0;
+    if (a.colors_precomp) {
+        rgb[0] = __ldg(a.colors_precomp + (size_t)idx * 3);
+        rgb[1] = __ldg(a.colors_precomp + (size_t)idx * 3 + 1);
+        rgb[2] = __ldg(a.colors_precomp + (size_t)idx * 3 + 2);
+    } else {
+        const float* sh = a.shs + (size_t)idx * a.M * 3;
+        sh_to_rgb(a.D, px - vp.campos[0], py - vp.campos[1], pz - vp.campos[2],
+                  [&](int k, int ch) { return __ldg(sh + k * 3 + ch); }, rgb);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            if (rgb[ch] < 0.0f) clampbits |= 1u << ch;
+            rgb[ch] = fmaxf(rgb[ch], 0.0f);
+        }
+    }
+    a.clamped[idx] = (uint8_t)clampbits;
+    const float gray = GSEVT_GRAY_R * rgb[0] + GSEVT_GRAY_G * rgb[1] + GSEVT_GRAY_B * rgb[2];
+    const float opacity = __ldg(a.opacities + idx);
+    a.rec[2 * (size_t)idx] = make_float4(o.mx, o.my, o.A, o.B);
+    a.rec[2 * (size_t)idx + 1] = make_float4(o.C, opacity, gray, o.depth);
+    a.rgb4[idx] = make_float4(rgb[0], rgb[1], rgb[2], gray);
+}
+
+void launch_preprocess_aos(const PreAosArgs& a, cudaStream_t s) {
+    if (a.P <= 0) return;
+    preprocess_aos_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Engine path: packed map, two views per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preprocess_map_kernel(PreMapArgs a) {
+    if (a.ctl && a.ctl->level_done) return;
+    __shared__ ViewParams s_vp[2];
+    load_views(s_vp, a.views, 2);
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= a.P) return;
+    const float4 xo = __ldg(a.xyz_opacity + idx);
+    float cov[6];
+    {
+        const float4 c0 = __ldg(a.cov3D_a + idx);
+        const float2 c1 = __ldg(a.cov3D_b + idx);
+        cov[0] = c0.x; cov[1] = c0.y; cov[2] = c0.z; cov[3] = c0.w; cov[4] = c1.x; cov[5] = c1.y;
+    }
+    ProjOut o[2];
+    bool ok[2];
+#pragma unroll
+    for (int v = 0; v < 2; v++) ok[v] = project_geometry(s_vp[v], xo.x, xo.y, xo.z, cov, o[v]);
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+        const size_t j = (size_t)v * a.P + idx;
+        a.radii[j] = ok[v] ? o[v].radius : 0;
+        a.tiles_touched[j] = ok[v] ? (uint32_t)o[v].tiles : 0u;
+    }
+    if (!ok[0] && !ok[1]) return;
+    // SH -> RGB for both views from ONE pass over the 48 planar coefficients (coalesced 128-byte lines)
+    const float* sh = a.sh_planar + idx;
+    const size_t P = (size_t)a.P;
+    float basis[2][16];
+#pragma unroll
+    for (int v = 0; v < 2; v++)
+        sh_basis(a.D, xo.x - s_vp[v].campos[0], xo.y - s_vp[v].campos[1], xo.z - s_vp[v].campos[2], basis[v]);
+    float rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    const int nb = (a.D + 1) * (a.D + 1);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k < nb) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                const float c = __ldg(sh + (size_t)(k * 3 + ch) * P);
+                rgb[0][ch] += basis[0][k] * c;
+                rgb[1][ch] += basis[1][k] * c;
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+        if (!ok[v]) continue;
+        unsigned clampbits = 0;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float c = rgb[v][ch] + 0.5f;
+            if (c < 0.0f) clampbits |= 1u << ch;
+            rgb[v][ch] = fmaxf(c, 0.0f);
+        }
+        const float gray = GSEVT_GRAY_R * rgb[v][0] + GSEVT_GRAY_G * rgb[v][1] + GSEVT_GRAY_B * rgb[v][2];
+        const size_t j = (size_t)v * P + idx;
+        a.clamped[j] = (uint8_t)clampbits;
+        a.rec[2 * j] = make_float4(o[v].mx, o[v].my, o[v].A, o[v].B);
+        a.rec[2 * j + 1] = make_float4(o[v].C, xo.w, gray, o[v].depth);
+        // zero the blend-backward accumulators of every Gaussian that can receive a gradient
+        a.grad8[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        a.grad8[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
+    if (a.P <= 0) return;
+    preprocess_map_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+}
+
+// checkFrustum (rasterizer_impl.cu:54-66)
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means, const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float px = means[3 * (size_t)idx], py = means[3 * (size_t)idx + 1], pz = means[3 * (size_t)idx + 2];
+    const float depth = affine3r(__ldg(view + 2), __ldg(view + 6), __ldg(view + 10), __ldg(view + 14), px, py, pz);
+    present[idx] = depth > 0.2f ? 1 : 0;
+}
+
+void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s) {
+    if (P <= 0) return;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means, view, present);
+}
+
+// Packs the activated AoS map tensors into the engine's resident layout (once per map).
+__global__ void pack_map_kernel(int P, int M, const float* __restrict__ xyz, const float* __restrict__ scales,
+                                const float* __restrict__ rots, const float* __restrict__ opac,
+                                const float* __restrict__ shs, float mod, float4* __restrict__ xyz_opacity,
+                                float4* __restrict__ cov_a, float2* __restrict__ cov_b, float* __restrict__ sh_planar) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const size_t i = idx;
+    xyz_opacity[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], opac[i]);
+    float cov[6];
+    cov3d_from_scale_rot(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2], mod, rots[4 * i], rots[4 * i + 1],
+                         rots[4 * i + 2], rots[4 * i + 3], cov);
+    cov_a[i] = make_float4(cov[0], cov[1], cov[2], cov[3]);
+    cov_b[i] = make_float2(cov[4], cov[5]);
+    for (int k = 0; k < 16; k++)
+        for (int ch = 0; ch < 3; ch++)
+            sh_planar[(size_t)(k * 3 + ch) * P + i] = k < M ? shs[(i * M + k) * 3 + ch] : 0.0f;
+}
+
+void launch_pack_map(int P, int M, const float* xyz, const float* scales, const float* rots, const float* opac,
+                     const float* shs, float mod, float4* xyz_opacity, float4* cov_a, float2* cov_b, float* sh_planar,
+                     cudaStream_t s) {
+    if (P <= 0) return;
+    pack_map_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, M, xyz, scales, rots, opac, shs, mod, xyz_opacity, cov_a, cov_b,
+                                                   sh_planar);
+}
+
+}  // namespace gsevt
