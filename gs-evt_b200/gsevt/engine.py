@@ -1,0 +1,261 @@
+"""Python handles for the native tracking engine, the packed map and the GPU event-frame builder.
+
+These are thin wrappers: every operation is one C-ABI call into libgsevt.so (include/gsevt.h §2, §3).
+They replace, for the hot loop only, the reference's per-iteration Python:
+  RenderFrame.get_delta_Ir      utils/render_camera/frame.py:61-94
+  render2 / build_rasterizer    gaussian_splatting/gaussian_renderer/__init__.py:234-339
+  Tracker.tracking_loss         utils/tracker.py:93-103
+  Adam step, update_pose/vwRT   utils/tracker.py:212-222, utils/render_camera/camera.py:129-155
+  EventFrame.integrate_events   utils/event_camera/event.py:116-128
+  Tracker.image_pyramid         utils/tracker.py:78-91
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+
+def _fp(arr):
+    return arr.ctypes.data_as(_lib.c_float_p)
+
+
+class PackedMap:
+    """Frozen, activated Gaussian map resident in HBM in the engine's SoA layout
+    (xyz+opacity float4, precomputed 3D covariance, planar SH): 232 B/Gaussian."""
+
+    def __init__(self, xyz, scales, rotations, opacities, shs, sh_degree=3, scale_modifier=1.0):
+        self._lib = _lib.load()
+        _lib.require_device()
+        dev = xyz.device
+        f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        xyz, scales, rotations, opacities, shs = f(xyz), f(scales), f(rotations), f(opacities), f(shs)
+        P = xyz.shape[0]
+        if shs.shape[1] != 16:
+            full = torch.zeros((P, 16, 3), dtype=torch.float32, device=dev)
+            full[:, :shs.shape[1]] = shs
+            shs = full
+        self.P, self.sh_degree, self.device = P, int(sh_degree), dev
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.gsevt_map_create(P, int(sh_degree), xyz.data_ptr(), scales.data_ptr(), rotations.data_ptr(),
+                                                  opacities.data_ptr(), shs.data_ptr(), float(scale_modifier),
+                                                  _lib.stream_ptr(), C.byref(h)), "gsevt_map_create")
+            torch.cuda.current_stream().synchronize()
+        self.handle = h
+
+    @classmethod
+    def from_gaussian_model(cls, gaussians, scale_modifier=1.0):
+        """Activations exactly as the reference applies them each iteration
+        (gaussian_splatting/scene/gaussian_model.py:75-95)."""
+        with torch.no_grad():
+            return cls(gaussians.get_xyz, gaussians.get_scaling, gaussians.get_rotation, gaussians.get_opacity,
+                       gaussians.get_features, gaussians.active_sh_degree, scale_modifier)
+
+    @property
+    def nbytes(self):
+        return int(self._lib.gsevt_map_bytes(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.gsevt_map_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TrackingEngine:
+    """One camera hypothesis tracked against a PackedMap; the whole optimisation iteration runs on the
+    device (CUDA graph per pyramid level) with no host synchronisation."""
+
+    def __init__(self, packed_map, width, height, fx, fy, background=(0.0, 0.0, 0.0), levels=3,
+                 lr_rot=0.004, lr_trans=0.004, lr_w=0.002, lr_v=0.002, converged_threshold=1e-4,
+                 max_optim_iter=200, znear=0.01, zfar=100.0, instance_capacity=0):
+        self._lib = _lib.load()
+        self.map = packed_map
+        self.device = packed_map.device
+        self.width, self.height, self.levels = int(width), int(height), int(levels)
+        cfg = _lib.GsevtEngineConfig()
+        cfg.width, cfg.height, cfg.levels = int(width), int(height), int(levels)
+        cfg.fx, cfg.fy, cfg.znear, cfg.zfar = float(fx), float(fy), float(znear), float(zfar)
+        for i in range(3):
+            cfg.background[i] = float(background[i])
+        cfg.lr_rot, cfg.lr_trans, cfg.lr_w, cfg.lr_v = float(lr_rot), float(lr_trans), float(lr_w), float(lr_v)
+        cfg.converged_threshold = float(converged_threshold)
+        cfg.max_optim_iter = int(max_optim_iter)
+        cfg.instance_capacity = int(instance_capacity)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_create(packed_map.handle, C.byref(cfg), C.byref(h)), "gsevt_engine_create")
+            # graph capture is illegal on the legacy default stream, so the engine runs on its own stream
+            self.stream = torch.cuda.Stream(device=self.device)
+        self.handle = h
+        self._pyr = None
+
+    # ---- state -------------------------------------------------------------------------------
+    def set_state(self, R, T, angular_vel, linear_vel):
+        a = [np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1)) for x in (R, T, angular_vel, linear_vel)]
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_set_state(self.handle, _fp(a[0]), _fp(a[1]), _fp(a[2]), _fp(a[3]),
+                                                        self.stream.cuda_stream), "gsevt_engine_set_state")
+
+    def get_state(self):
+        R, T, w, v = (np.zeros(9, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32))
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_get_state(self.handle, _fp(R), _fp(T), _fp(w), _fp(v), self.stream.cuda_stream),
+                       "gsevt_engine_get_state")
+        return R.reshape(3, 3), T, w, v
+
+    # ---- per frame / level -----------------------------------------------------------------------
+    def begin_frame(self, delta_tau, sign_pyramid, unsign_pyramid=None):
+        """sign_pyramid: flat float32 CUDA tensor in the layout of gsevt_event_frame."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        self._pyr = (sign_pyramid, unsign_pyramid)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_begin_frame(self.handle, float(delta_tau), sign_pyramid.data_ptr(),
+                                                          _lib.ptr(unsign_pyramid), self.stream.cuda_stream),
+                       "gsevt_engine_begin_frame")
+
+    def begin_level(self, level, opt_vel):
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_begin_level(self.handle, int(level), int(bool(opt_vel)),
+                                                          self.stream.cuda_stream), "gsevt_engine_begin_level")
+
+    def iterate(self, n=1):
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_iterate(self.handle, int(n), self.stream.cuda_stream), "gsevt_engine_iterate")
+
+    def poll_done(self):
+        return bool(self._lib.gsevt_engine_poll_done(self.handle))
+
+    def status(self):
+        st = _lib.GsevtEngineStatus()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_status(self.handle, C.byref(st), self.stream.cuda_stream), "gsevt_engine_status")
+        if st.overflow:
+            raise _lib.GsevtError("tile-instance capacity exceeded; recreate the engine with a larger instance_capacity")
+        return st
+
+    def losses(self):
+        buf = np.zeros(1024, np.float32)
+        with torch.cuda.device(self.device):
+            n = _lib.check(self._lib.gsevt_engine_losses(self.handle, _fp(buf), 1024, self.stream.cuda_stream),
+                           "gsevt_engine_losses")
+        return buf[:n].copy()
+
+    def run_level(self, level, opt_vel, chunk=8):
+        """Optimises one pyramid level to the reference's stopping rule; returns the status."""
+        self.begin_level(level, opt_vel)
+        while True:
+            self.iterate(chunk)
+            self.stream.synchronize()
+            if self.poll_done():
+                break
+        return self.status()
+
+    def const_vel_model(self, tau):
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_const_vel_model(self.handle, float(tau), self.stream.cuda_stream),
+                       "gsevt_engine_const_vel_model")
+
+    def weighted_velocity(self, last_R, last_T, delta_tau, weight):
+        a = np.ascontiguousarray(np.asarray(last_R, np.float32).reshape(-1))
+        b = np.ascontiguousarray(np.asarray(last_T, np.float32).reshape(-1))
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_weighted_velocity(self.handle, _fp(a), _fp(b), float(delta_tau), float(weight),
+                                                                self.stream.cuda_stream), "gsevt_engine_weighted_velocity")
+
+    def eval(self, level, signed=True):
+        """Loss and the 12 pose/velocity gradients [rho, theta, v, w] at the current state (no step)."""
+        loss = C.c_float(0)
+        g = np.zeros(12, np.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_eval(self.handle, int(level), int(bool(signed)), C.byref(loss), _fp(g),
+                                                   self.stream.cuda_stream), "gsevt_engine_eval")
+        return float(loss.value), g
+
+    def gray_images(self, level):
+        Wl, Hl = self.width >> level, self.height >> level
+        Wl, Hl = int(self.width * 0.5 ** level), int(self.height * 0.5 ** level)
+        last = torch.empty((Hl, Wl), dtype=torch.float32, device=self.device)
+        nxt = torch.empty((Hl, Wl), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_render_delta(self.handle, int(level), None, last.data_ptr(), nxt.data_ptr(),
+                                                           self.stream.cuda_stream), "gsevt_engine_render_delta")
+        self.stream.synchronize()
+        return last, nxt
+
+    @property
+    def launches_per_iteration(self):
+        return int(self._lib.gsevt_engine_launches_per_iteration(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.gsevt_engine_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class EventFrameBuilder:
+    """GPU event frames: polarity scatter-add, undistort, 9x9 blur, L2 normalise, abs, pyramid."""
+
+    def __init__(self, width, height, intrinsic, distortion, levels=3, device="cuda"):
+        self._lib = _lib.load()
+        _lib.require_device()
+        self.W, self.H, self.levels = int(width), int(height), int(levels)
+        self.device = torch.device(device)
+        K = np.ascontiguousarray(np.asarray(intrinsic, dtype=np.float64).reshape(9))
+        D = np.zeros(5, np.float64)
+        d = np.asarray(distortion, dtype=np.float64).ravel()
+        D[:min(5, d.size)] = d[:5]
+        ix = np.zeros((self.H, self.W), np.int32)
+        iy = np.zeros((self.H, self.W), np.int32)
+        _lib.check(self._lib.gsevt_event_undistort_map(K.ctypes.data_as(C.POINTER(C.c_double)),
+                                                       D.ctypes.data_as(C.POINTER(C.c_double)), self.W, self.H,
+                                                       ix.ctypes.data, iy.ctypes.data), "gsevt_event_undistort_map")
+        self.map_ix = torch.from_numpy(ix).to(self.device)
+        self.map_iy = torch.from_numpy(iy).to(self.device)
+        self.counts = torch.zeros((self.H, self.W), dtype=torch.int32, device=self.device)
+        self.oob = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        sb = self._lib.gsevt_event_frame_scratch_size(self.W, self.H)
+        self.scratch = torch.empty((sb,), dtype=torch.uint8, device=self.device)
+        self.level_shapes = [(self.H >> l, self.W >> l) for l in range(self.levels)]
+        self.total = sum(h * w for h, w in self.level_shapes)
+
+    def accumulate(self, x, y, p):
+        """x, y int16 and p uint8 CUDA tensors (or array-likes, copied)."""
+        to = lambda a, dt: a if isinstance(a, torch.Tensor) and a.device == self.device and a.dtype == dt \
+            else torch.as_tensor(np.asarray(a), dtype=dt).to(self.device, non_blocking=True)
+        x, y, p = to(x, torch.int16), to(y, torch.int16), to(p, torch.uint8)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_event_accumulate(x.data_ptr(), y.data_ptr(), p.data_ptr(), int(x.numel()), self.W, self.H,
+                                                        self.counts.data_ptr(), 1, self.oob.data_ptr(), _lib.stream_ptr()),
+                       "gsevt_event_accumulate")
+        return self.counts
+
+    def build(self, x, y, p):
+        """Returns (sign_pyramid, unsign_pyramid): flat float32 tensors, level l at offset sum_{k<l} H_k*W_k."""
+        self.accumulate(x, y, p)
+        sign = torch.empty((self.total,), dtype=torch.float32, device=self.device)
+        unsign = torch.empty((self.total,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_event_frame(self.counts.data_ptr(), self.map_ix.data_ptr(), self.map_iy.data_ptr(),
+                                                   self.W, self.H, self.levels, sign.data_ptr(), unsign.data_ptr(),
+                                                   self.scratch.data_ptr(), self.scratch.numel(), _lib.stream_ptr()),
+                       "gsevt_event_frame")
+        return sign, unsign
+
+    def level_view(self, flat, level):
+        off = sum(h * w for h, w in self.level_shapes[:level])
+        h, w = self.level_shapes[level]
+        return flat[off:off + h * w].view(1, h, w)
