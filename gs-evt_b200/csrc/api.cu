@@ -126,9 +126,10 @@ GSEVT_API int gsevt_abi_version(void) { return GSEVT_ABI_VERSION; }
 GSEVT_API int gsevt_device_arch(void) {
     int dev = 0;
     GSEVT_CUDA_OK(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    GSEVT_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
-    return prop.major * 10 + prop.minor;
+    int major = 0, minor = 0;
+    GSEVT_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    GSEVT_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return major * 10 + minor;
 }
 
 GSEVT_API int gsevt_raster_sizes(int32_t P, int32_t width, int32_t height, size_t* geom_bytes, size_t* img_bytes) {
@@ -453,46 +454,67 @@ static void projection_colmajor(double znear, double zfar, double fovX, double f
         for (int r = 0; r < 4; r++) out[4 * c + r] = P[r][c];
 }
 
-// Enqueue one full optimisation iteration (or one evaluation) on stream s.
-static void enqueue_iteration(GsevtEngine* e, cudaStream_t s) {
+// Enqueue one full optimisation iteration (or one evaluation) on stream s.  When `ev` is non-null an
+// event is recorded before every stage and after the last one (GSEVT_NSTAGES + 1 events): used by
+// gsevt_engine_profile for per-stage device times, never inside a captured graph.
+#define GSEVT_NSTAGES 11
+static const char* const kStageNames[GSEVT_NSTAGES] = {
+    "pose_setup", "preprocess_map", "scan(cub)", "emit_keys", "radix_sort(cub)", "identify_ranges",
+    "blend_fwd_gray", "loss_stats", "blend_bwd_gray", "geom_bwd_pose", "engine_update"};
+
+static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = nullptr) {
     const GsevtMap* m = e->map;
     const LevelInfo& L = e->lv[e->cur_level];
     const int P = m->P;
+    int stage = 0;
+    auto mark = [&]() { if (ev) cudaEventRecord(ev[stage], s); stage++; };
+    mark();
     launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, s);
+    mark();
     PreMapArgs pa;
     pa.P = P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
     pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
     pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.rec = e->rec; pa.grad8 = e->grad8;
     launch_preprocess_map(pa, s);
+    mark();
     launch_scan(e->scan_temp, e->scan_bytes, e->tiles, e->offsets, 2 * P, s);
+    mark();
     launch_emit_keys(P, 2, e->views, e->rec, e->radii, e->offsets, e->keys_u, e->vals_u, e->sort_n, e->overflow,
                      e->ctl, s);
+    mark();
     const int tiles = L.gx * L.gy;
     const int bit = (int)higher_msb((uint32_t)(2 * tiles));
     launch_sort_pairs(e->sort_temp, e->sort_bytes, e->keys_u, e->keys, e->vals_u, e->vals, e->sort_n, 32 + bit, s);
+    mark();
     launch_identify_ranges(e->keys, e->ranges, 2 * tiles, -1, e->offsets + (2 * P - 1), e->sort_n, s);
+    mark();
     BlendFwdArgs f;
     memset(&f, 0, sizeof(f));
     f.W = L.W; f.H = L.H; f.grid_x = L.gx; f.grid_y = L.gy; f.nviews = 2;
     f.ranges = e->ranges; f.point_list = e->vals; f.rec = e->rec; f.view_stride_gauss = (size_t)P;
     f.views = e->views; f.final_T = e->final_T; f.n_contrib = e->n_contrib; f.out_color = e->gray; f.ctl = e->ctl;
     launch_blend_fwd_gray(f, s);
-    const float* ev = e->ev_sign + L.ev_offset;
-    launch_loss_stats(e->gray, ev, L.W * L.H, e->ctl, e->loss_partials, e->loss_nb, s);
+    mark();
+    const float* evf = e->ev_sign + L.ev_offset;
+    launch_loss_stats(e->gray, evf, L.W * L.H, e->ctl, e->loss_partials, e->loss_nb, s);
+    mark();
     BlendBwdArgs b;
     memset(&b, 0, sizeof(b));
     b.W = L.W; b.H = L.H; b.grid_x = L.gx; b.grid_y = L.gy; b.nviews = 2;
     b.ranges = e->ranges; b.point_list = e->vals; b.rec = e->rec; b.view_stride_gauss = (size_t)P; b.views = e->views;
-    b.final_T = e->final_T; b.n_contrib = e->n_contrib; b.gray = e->gray; b.event_frame = ev; b.ctl = e->ctl;
+    b.final_T = e->final_T; b.n_contrib = e->n_contrib; b.gray = e->gray; b.event_frame = evf; b.ctl = e->ctl;
     b.grad8 = e->grad8;
     launch_blend_bwd_gray(b, s);
+    mark();
     GeomBwdArgs q;
     memset(&q, 0, sizeof(q));
     q.P = P; q.D = m->D; q.M = 16; q.nviews = 2; q.views = e->views; q.radii = e->radii; q.clamped = e->clamped;
     q.grad8 = e->grad8; q.xyz_opacity = m->xyz_opacity; q.cov3D_a = m->cov_a; q.cov3D_b = m->cov_b;
     q.sh_planar = m->sh_planar; q.ctl = e->ctl; q.partials = e->geom_partials;
     launch_geom_bwd_map(q, s);
+    mark();
     launch_engine_update(e->ctl, e->geom_partials, e->geom_blocks, e->host_flag_dev, s);
+    mark();
 }
 
 static int upload_level(GsevtEngine* e, int level, cudaStream_t s) {
@@ -828,6 +850,55 @@ GSEVT_API int gsevt_engine_render_delta(GsevtEngine* e, int32_t level, float* de
     if (gray_last) GSEVT_CUDA_OK(cudaMemcpyAsync(gray_last, e->gray, hw * 4, cudaMemcpyDeviceToDevice, s));
     if (gray_next) GSEVT_CUDA_OK(cudaMemcpyAsync(gray_next, e->gray + hw, hw * 4, cudaMemcpyDeviceToDevice, s));
     (void)delta_out;
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_stage_count(void) { return GSEVT_NSTAGES; }
+GSEVT_API const char* gsevt_engine_stage_name(int32_t i) { return i >= 0 && i < GSEVT_NSTAGES ? kStageNames[i] : ""; }
+
+GSEVT_API int gsevt_engine_profile(GsevtEngine* e, int32_t n_iters, float* stage_ms, void* stream) {
+    if (!e || n_iters <= 0 || !stage_ms) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    if (!e->ev_sign) { set_error("profile before begin_frame"); return GSEVT_ESTATE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t ev[GSEVT_NSTAGES + 1];
+    for (int i = 0; i <= GSEVT_NSTAGES; i++) GSEVT_CUDA_OK(cudaEventCreate(&ev[i]));
+    double acc[GSEVT_NSTAGES];
+    for (int i = 0; i < GSEVT_NSTAGES; i++) acc[i] = 0.0;
+    int rc = 0;
+    for (int it = 0; it < n_iters && !rc; it++) {
+        enqueue_iteration(e, s, ev);
+        if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("profile: %s", cudaGetErrorString(cudaGetLastError())); rc = GSEVT_ECUDA; break; }
+        for (int i = 0; i < GSEVT_NSTAGES; i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            acc[i] += ms;
+        }
+    }
+    for (int i = 0; i <= GSEVT_NSTAGES; i++) cudaEventDestroy(ev[i]);
+    for (int i = 0; i < GSEVT_NSTAGES; i++) stage_ms[i] = (float)(acc[i] / n_iters);
+    return rc;
+}
+
+GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream) {
+    if (!e || !out8) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const LevelInfo& L = e->lv[e->cur_level];
+    unsigned long long* d = nullptr;
+    GSEVT_CUDA_OK(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
+    GSEVT_CUDA_OK(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), s));
+    launch_workload_counters(e->map->P, e->radii, e->grad8, L.W * L.H, e->n_contrib, d, s);
+    unsigned long long h[8];
+    uint32_t offs[2] = {0, 0};
+    GSEVT_CUDA_OK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[0], e->offsets + (e->map->P - 1), 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[1], e->offsets + (2 * (size_t)e->map->P - 1), 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    cudaFree(d);
+    out8[0] = (int64_t)h[0]; out8[1] = (int64_t)h[1];              // visible Gaussians per view
+    out8[2] = (int64_t)offs[0]; out8[3] = (int64_t)(offs[1] - offs[0]);  // tile instances per view
+    out8[4] = (int64_t)h[2]; out8[5] = (int64_t)h[3];              // sum of n_contrib per view (pairs walked)
+    out8[6] = (int64_t)h[4];                                       // (view, Gaussian) pairs with a non-zero blend gradient
+    out8[7] = (int64_t)e->sort_n;                                  // slots sorted (instances + padding)
     return 0;
 }
 

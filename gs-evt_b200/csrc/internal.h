@@ -198,6 +198,9 @@ void launch_event_accumulate(const int16_t* x, const int16_t* y, const uint8_t* 
 void launch_event_frame(const int* counts, const int* map_ix, const int* map_iy, int W, int H, int levels,
                         float* sign_out, float* unsign_out, float* scratch, double* dscratch, cudaStream_t s);
 
+void launch_workload_counters(int P, const int* radii, const float4* grad8, int HW, const uint32_t* n_contrib,
+                              unsigned long long* out, cudaStream_t s);
+
 void set_error(const char* fmt, ...);
 }  // namespace gsevt
 

@@ -215,4 +215,34 @@ void launch_loss_stats(const float* gray, const float* event_frame, int HW, Engi
     loss_stats_kernel<<<nblocks, 256, 0, s>>>(gray, event_frame, HW, ctl, partials, nblocks);
 }
 
+// ---- workload counters (bench / profiling only) ---------------------------------------------------
+// out[0], out[1]: Gaussians with radius > 0 per view; out[2], out[3]: sum of n_contrib per view (the
+// number of (pixel, instance) pairs a pixel walks before it terminates); out[4]: (view, Gaussian) pairs
+// whose blend gradient is non-zero.
+__global__ void workload_counters_kernel(int P, const int* __restrict__ radii, const float4* __restrict__ grad8, int HW,
+                                         const uint32_t* __restrict__ n_contrib, unsigned long long* __restrict__ out) {
+    unsigned long long c[5] = {0, 0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2LL * P; i += stride) {
+        if (radii[i] > 0) {
+            c[i >= P ? 1 : 0]++;
+            const float4 a = grad8[2 * i], b = grad8[2 * i + 1];
+            if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f || b.x != 0.f || b.y != 0.f) c[4]++;
+        }
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2LL * HW; i += stride)
+        c[2 + (i >= HW ? 1 : 0)] += n_contrib[i];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        unsigned long long v = c[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + k, v);
+    }
+}
+void launch_workload_counters(int P, const int* radii, const float4* grad8, int HW, const uint32_t* n_contrib,
+                              unsigned long long* out, cudaStream_t s) {
+    workload_counters_kernel<<<296, 256, 0, s>>>(P, radii, grad8, HW, n_contrib, out);
+}
+
 }  // namespace gsevt

@@ -99,10 +99,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         sh_c, col_c = _f32(sh, dev), _f32(colors_precomp, dev)
         op_c, sc_c, rot_c, cov_c = _f32(opacities, dev), _f32(scales, dev), _f32(rotations, dev), _f32(cov3Ds_precomp, dev)
         P, H, W = means3D.shape[0], int(rs.image_height), int(rs.image_width)
-        if (sh_c is None) == (col_c is None):
-            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
-        if ((sc_c is None or rot_c is None) and cov_c is None) or ((sc_c is not None or rot_c is not None) and cov_c is not None):
-            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        if P != 0:  # with P == 0 every per-Gaussian tensor is empty and the reference returns zeros (rasterize_points.cu:85)
+            if (sh_c is None) == (col_c is None):
+                raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+            if ((sc_c is None or rot_c is None) and cov_c is None) or ((sc_c is not None or rot_c is not None) and cov_c is not None):
+                raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
 
         with torch.cuda.device(dev):
             f32 = dict(dtype=torch.float32, device=dev)

@@ -52,10 +52,12 @@ class GaussianModel:
         rest = np.stack([col(nm) for nm in rest_names], axis=1).reshape(n, 3, ncoef - 1) if rest_names else np.zeros((n, 3, 0), np.float32)
         sc = np.stack([col(nm) for nm in sorted([p for p in v.dtype.names if p.startswith("scale_")], key=lambda s: int(s.split("_")[-1]))], axis=1)
         rot = np.stack([col(nm) for nm in sorted([p for p in v.dtype.names if p.startswith("rot")], key=lambda s: int(s.split("_")[-1]))], axis=1)
-        mk = lambda a: nn.Parameter(torch.tensor(a, dtype=torch.float, device=self.device).contiguous().requires_grad_(False))
+        # frozen map: the reference wraps these in nn.Parameter(...) whose default requires_grad=True silently re-enables
+        # gradients for every map tensor (gaussian_model.py:298-323); nothing consumes them, so they are really frozen here
+        mk = lambda a: nn.Parameter(torch.tensor(a, dtype=torch.float, device=self.device).contiguous(), requires_grad=False)
         self._xyz = mk(xyz)
-        self._features_dc = nn.Parameter(torch.tensor(dc, dtype=torch.float, device=self.device).transpose(1, 2).contiguous().requires_grad_(False))
-        self._features_rest = nn.Parameter(torch.tensor(rest, dtype=torch.float, device=self.device).transpose(1, 2).contiguous().requires_grad_(False))
+        self._features_dc = nn.Parameter(torch.tensor(dc, dtype=torch.float, device=self.device).transpose(1, 2).contiguous(), requires_grad=False)
+        self._features_rest = nn.Parameter(torch.tensor(rest, dtype=torch.float, device=self.device).transpose(1, 2).contiguous(), requires_grad=False)
         self._opacity, self._scaling, self._rotation = mk(opac), mk(sc), mk(rot)
         self.active_sh_degree = self.max_sh_degree
         self._packed = None

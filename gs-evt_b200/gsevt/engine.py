@@ -190,6 +190,24 @@ class TrackingEngine:
         self.stream.synchronize()
         return last, nxt
 
+    def profile(self, n_iters=5):
+        """Mean device time (ms) of every stage of an iteration, measured with CUDA events on the engine
+        stream over n real (un-graphed) iterations: {stage name: ms}."""
+        n = int(self._lib.gsevt_engine_stage_count())
+        ms = np.zeros(n, np.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_profile(self.handle, int(n_iters), _fp(ms), self.stream.cuda_stream),
+                       "gsevt_engine_profile")
+        return {self._lib.gsevt_engine_stage_name(i).decode(): float(ms[i]) for i in range(n)}
+
+    def workload(self):
+        """Data-dependent work counters of the most recent iteration (see gsevt_engine_workload)."""
+        out = (C.c_int64 * 8)()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_workload(self.handle, out, self.stream.cuda_stream), "gsevt_engine_workload")
+        v = list(out)
+        return dict(visible=v[0:2], instances=v[2:4], pairs_walked=v[4:6], gaussians_with_grad=v[6], sorted_slots=v[7])
+
     @property
     def launches_per_iteration(self):
         return int(self._lib.gsevt_engine_launches_per_iteration(self.handle))
@@ -214,6 +232,8 @@ class EventFrameBuilder:
         _lib.require_device()
         self.W, self.H, self.levels = int(width), int(height), int(levels)
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         K = np.ascontiguousarray(np.asarray(intrinsic, dtype=np.float64).reshape(9))
         D = np.zeros(5, np.float64)
         d = np.asarray(distortion, dtype=np.float64).ravel()
@@ -229,18 +249,46 @@ class EventFrameBuilder:
         self.oob = torch.zeros((1,), dtype=torch.int32, device=self.device)
         sb = self._lib.gsevt_event_frame_scratch_size(self.W, self.H)
         self.scratch = torch.empty((sb,), dtype=torch.uint8, device=self.device)
+        self._pin = self._pin_np = self._dev = self._copied = self._keep = None
+        self.h2d_bytes_last = 0
         self.level_shapes = [(self.H >> l, self.W >> l) for l in range(self.levels)]
         self.total = sum(h * w for h, w in self.level_shapes)
 
+    def _stage(self, x, y, p):
+        """Packs host event columns into ONE pinned staging buffer and issues one async H2D copy
+        (x int16 | y int16 | p uint8 = 5 bytes/event); returns the three device pointers."""
+        n = int(x.shape[0])
+        if self._pin is None or self._pin.numel() < 5 * n:
+            cap = max(5 * n, 1 << 16)
+            self._pin = torch.empty((cap,), dtype=torch.uint8).pin_memory()
+            self._pin_np = self._pin.numpy()
+            self._dev = torch.empty((cap,), dtype=torch.uint8, device=self.device)
+            self._copied = torch.cuda.Event()
+        else:
+            self._copied.synchronize()   # the previous frame's DMA must have read the staging buffer
+        b = self._pin_np
+        b[0:2 * n].view(np.int16)[:] = x
+        b[2 * n:4 * n].view(np.int16)[:] = y
+        b[4 * n:5 * n] = p
+        self._dev[:5 * n].copy_(self._pin[:5 * n], non_blocking=True)
+        self._copied.record(torch.cuda.current_stream(self.device))
+        base = self._dev.data_ptr()
+        return base, base + 2 * n, base + 4 * n, n
+
     def accumulate(self, x, y, p):
-        """x, y int16 and p uint8 CUDA tensors (or array-likes, copied)."""
-        to = lambda a, dt: a if isinstance(a, torch.Tensor) and a.device == self.device and a.dtype == dt \
-            else torch.as_tensor(np.asarray(a), dtype=dt).to(self.device, non_blocking=True)
-        x, y, p = to(x, torch.int16), to(y, torch.int16), to(p, torch.uint8)
+        """x, y int16 and p uint8: CUDA tensors are used in place; host arrays go through the pinned
+        staging buffer."""
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.gsevt_event_accumulate(x.data_ptr(), y.data_ptr(), p.data_ptr(), int(x.numel()), self.W, self.H,
-                                                        self.counts.data_ptr(), 1, self.oob.data_ptr(), _lib.stream_ptr()),
-                       "gsevt_event_accumulate")
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                xs, ys, ps = (t.to(device=self.device, dtype=dt).contiguous() for t, dt in
+                              ((x, torch.int16), (y, torch.int16), (p, torch.uint8)))
+                px, py, pp, n = xs.data_ptr(), ys.data_ptr(), ps.data_ptr(), int(xs.numel())
+                self._keep = (xs, ys, ps)
+            else:
+                conv = lambda a, dt: (a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)).astype(dt, copy=False).ravel()
+                px, py, pp, n = self._stage(conv(x, np.int16), conv(y, np.int16), conv(p, np.uint8))
+            _lib.check(self._lib.gsevt_event_accumulate(px, py, pp, n, self.W, self.H, self.counts.data_ptr(), 1,
+                                                        self.oob.data_ptr(), _lib.stream_ptr()), "gsevt_event_accumulate")
         return self.counts
 
     def build(self, x, y, p):

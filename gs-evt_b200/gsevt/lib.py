@@ -101,9 +101,14 @@ PROTOTYPES = {
     "gsevt_engine_render_delta": (C.c_int, [c_void_p, C.c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gsevt_engine_eval": (C.c_int, [c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p, c_void_p]),
     "gsevt_engine_launches_per_iteration": (C.c_int, [c_void_p]),
+    "gsevt_engine_stage_count": (C.c_int, []),
+    "gsevt_engine_stage_name": (C.c_char_p, [C.c_int32]),
+    "gsevt_engine_profile": (C.c_int, [c_void_p, C.c_int32, c_float_p, c_void_p]),
+    "gsevt_engine_workload": (C.c_int, [c_void_p, C.POINTER(C.c_int64), c_void_p]),
 }
 
 _lib = None
+_ARCH = {}
 
 
 class GsevtError(RuntimeError):
@@ -141,7 +146,10 @@ def require_device():
     import torch
     if not torch.cuda.is_available():
         raise GsevtError("gsevt needs a CUDA device (sm_100a); no CPU fallback exists")
-    arch = check(load().gsevt_device_arch(), "gsevt_device_arch")
+    dev = torch.cuda.current_device()
+    arch = _ARCH.get(dev)
+    if arch is None:  # cudaGetDeviceProperties is slow (milliseconds): ask once per device
+        arch = _ARCH[dev] = check(load().gsevt_device_arch(), "gsevt_device_arch")
     if arch // 10 != 10:
         raise GsevtError(f"libgsevt.so only carries sm_100a code; current device is sm_{arch}")
     return arch

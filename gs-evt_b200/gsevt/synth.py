@@ -20,6 +20,12 @@ DESK = dict(
     converged_threshold=1e-4, max_optim_iter=200, max_events_per_frame=30000,
 )
 
+# configs/VECTOR/robot_normal1_config.yaml: same sensor, different initial pose / velocity (config 3).
+ROBOT = dict(DESK,
+             R=[0.98161380, -0.00045487, 0.19087728, -0.02444478, 0.99146338, 0.12807349, -0.18930609, -0.13038466, 0.97322302],
+             T=[-4.80009293, -0.70624608, 2.88821495],
+             angular_vel=[0.04814772, 0.04794633, 0.00379134], linear_vel=[0.11414605, 0.00285491, -0.19478575])
+
 
 def synth_map(P, seed=0, W=DESK["W"], H=DESK["H"], fx=DESK["fx"], fy=DESK["fy"], R=DESK["R"], T=DESK["T"],
               sh_degree=3):
@@ -82,7 +88,7 @@ def load_map_into(gaussians, m, device="cuda"):
     """Fills a GaussianModel from a synth_map dict without a PLY round trip."""
     import torch
     from torch import nn
-    mk = lambda a: nn.Parameter(torch.tensor(a, dtype=torch.float, device=device).contiguous().requires_grad_(False))
+    mk = lambda a: nn.Parameter(torch.tensor(a, dtype=torch.float, device=device).contiguous(), requires_grad=False)
     gaussians._xyz, gaussians._scaling, gaussians._rotation, gaussians._opacity = (
         mk(m["xyz"]), mk(m["scaling"]), mk(m["rotation"]), mk(m["opacity"]))
     gaussians._features_dc, gaussians._features_rest = mk(m["f_dc"]), mk(m["f_rest"])

@@ -259,6 +259,17 @@ GSEVT_API int gsevt_engine_render_delta(GsevtEngine* e, int32_t level, float* de
 /* One gradient evaluation without optimiser step (parity tests): loss and the 12 pose gradients. */
 GSEVT_API int gsevt_engine_eval(GsevtEngine* e, int32_t level, int32_t signed_loss, float* loss_out, float* grads_out12,
                       void* stream);
+/* Profiling (bench.py's roofline leg): runs n_iters iterations OUTSIDE the CUDA graph with a CUDA
+ * event between stages on `stream` and returns the mean device time of each stage in ms
+ * (gsevt_engine_stage_count() entries, names from gsevt_engine_stage_name).  The iterations are real
+ * (state advances).  Synchronises. */
+GSEVT_API int gsevt_engine_stage_count(void);
+GSEVT_API const char* gsevt_engine_stage_name(int32_t i);
+GSEVT_API int gsevt_engine_profile(GsevtEngine* e, int32_t n_iters, float* stage_ms, void* stream);
+/* Data-dependent work of the most recent iteration: out8 = {visible Gaussians view 0, view 1, tile
+ * instances view 0, view 1, sum of n_contrib view 0, view 1, (view, Gaussian) pairs with a non-zero blend
+ * gradient, slots sorted}.  Synchronises. */
+GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream);
 /* Number of kernels the engine launches per executed iteration (for bench.py's gpu_launches). */
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e);
 /* Non-blocking: 1 once the device has flagged the current level as finished (read from mapped

@@ -228,9 +228,12 @@ def loss_and_pixel_grad(gray_last, gray_next, E, signed=True):
     return float(L), dd.astype(np.float32)
 
 
-def tracking_eval(act, R, T, ang_vel, lin_vel, delta_tau, W, H, fx, fy, level, E, signed=True, bg=(0, 0, 0)):
+def tracking_eval(act, R, T, ang_vel, lin_vel, delta_tau, W, H, fx, fy, level, E, signed=True, bg=(0, 0, 0), gray_override=None):
     """One full evaluation of the tracking objective on the CPU: two forwards, loss, two backwards.
-    act: dict from gsevt.synth.activate().  Returns (loss, grads12 [rho,theta,v,w], aux)."""
+    act: dict from gsevt.synth.activate().  Returns (loss, grads12 [rho,theta,v,w], aux).
+    gray_override = (gray_last, gray_next): take the loss and its pixel gradient from these images instead of
+    the oracle's own renders (used for the unsigned objective, whose gradient flips sign with the rounding
+    noise of the render difference)."""
     views = view_setup(R, T, ang_vel, lin_vel, delta_tau, W, H, fx, fy, level)
     fws, scs, grays = [], [], []
     for v in views:
@@ -241,7 +244,8 @@ def tracking_eval(act, R, T, ang_vel, lin_vel, delta_tau, W, H, fx, fy, level, E
         scs.append(sc)
         fws.append(fw)
         grays.append(np.tensordot(GRAY, fw["color"], axes=(0, 0)).astype(np.float32))
-    L, dd = loss_and_pixel_grad(grays[0], grays[1], np.asarray(E, np.float32).reshape(grays[0].shape), signed)
+    lg = grays if gray_override is None else [np.asarray(x, np.float32).reshape(grays[0].shape) for x in gray_override]
+    L, dd = loss_and_pixel_grad(lg[0], lg[1], np.asarray(E, np.float32).reshape(grays[0].shape), signed)
     total = np.zeros(12, np.float64)
     for sgn, sc, fw in ((-1.0, scs[0], fws[0]), (1.0, scs[1], fws[1])):
         dcol = (GRAY[:, None, None] * (np.float32(sgn) * dd)[None]).astype(np.float32)
