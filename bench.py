@@ -316,11 +316,14 @@ def roofline(stages, wl, P, HW, clocks):
     slots = wl["sorted_slots"]
     bytes_alg = {
         # map read once for both views (40 B) + SH for Gaussians visible in >= 1 view (192 B) + per-view records out
-        "preprocess_map": 40 * P + 192 * max(wl["visible"]) + 2 * P * 8 + Pv * (32 + 32 + 1),
-        "scan(cub)": 2 * P * 8,
-        "emit_keys": 2 * P * 8 + Pv * 36 + slots * 12,
-        "radix_sort(cub)": slots * 8 + 6 * 24 * slots,
-        "identify_ranges": N * 8,
+        "preprocess_map": 40 * P + 192 * max(wl["visible"]) + 2 * P * 12 + Pv * (32 + 32 + 1),
+        # 2P (depth key, id) pairs: histogram read + 4 digit passes of (8 B in + 8 B out)
+        "depth_sort(cub)": 2 * P * (4 + 4 * 16),
+        "scan(cub)": 2 * P * 12,
+        "emit_tiles": 2 * P * 16 + Pv * 32 + slots * 6,
+        # (u16 tile key, u32 id) pairs: histogram read + 2 digit passes of (6 B in + 6 B out)
+        "tile_sort(cub)": slots * 2 + 2 * 12 * slots,
+        "identify_ranges": N * 2,
         "geom_bwd_pose": 2 * P * 4 + Pv * 32 + Pg * (40 + 192 + 1),
         "loss_stats": 3 * 4 * HW,
     }

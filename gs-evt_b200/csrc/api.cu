@@ -376,6 +376,7 @@ struct GsevtMap {
     float4* cov_a = nullptr;
     float2* cov_b = nullptr;
     float* sh_planar = nullptr;
+    float* sh_aos = nullptr;
     size_t bytes = 0;
 };
 
@@ -403,7 +404,9 @@ struct GsevtEngine {
     uint32_t* offsets = nullptr;
     uint8_t* clamped = nullptr;
     void* scan_temp = nullptr; size_t scan_bytes = 0;
-    uint64_t *keys_u = nullptr, *keys = nullptr;
+    uint32_t *depth_key = nullptr, *depth_sorted = nullptr, *iota = nullptr, *order = nullptr, *rect = nullptr;
+    void* sortA_temp = nullptr; size_t sortA_bytes = 0;
+    uint16_t *keys_u = nullptr, *keys = nullptr;
     uint32_t *vals_u = nullptr, *vals = nullptr;
     void* sort_temp = nullptr; size_t sort_bytes = 0;
     uint2* ranges = nullptr;
@@ -436,6 +439,42 @@ static int dev_alloc(GsevtEngine* e, T** p, size_t n) {
     return 0;
 }
 
+static void dev_free(GsevtEngine* e, void* p) {
+    if (!p) return;
+    for (size_t i = 0; i < e->allocs.size(); i++)
+        if (e->allocs[i] == p) { e->allocs.erase(e->allocs.begin() + i); break; }
+    cudaFree(p);
+}
+
+// Slots sorted per iteration for `total` live tile instances: a little slack so that the pose may move inside a
+// level without re-sizing (an overflow is detected on the device, the iteration is voided and the host re-sizes:
+// gsevt_engine_resume), rounded so that small changes do not re-capture the CUDA graph.
+static long long slots_for(long long total) {
+    long long want = total + total / 16 + 16384;
+    return (want + 4095) / 4096 * 4096;
+}
+
+// Grows the instance buffers (never inside a captured graph).
+static int ensure_capacity(GsevtEngine* e, long long slots) {
+    if (slots <= e->cap) return 0;
+    long long cap = slots + slots / 2;
+    if (cap > 0x3fffffff) cap = 0x3fffffff;
+    if (slots > cap) { set_error("instance count %lld exceeds the supported maximum", slots); return GSEVT_EOVERFLOW; }
+    cudaDeviceSynchronize();
+    if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+    dev_free(e, e->keys_u); dev_free(e, e->keys); dev_free(e, e->vals_u); dev_free(e, e->vals); dev_free(e, e->sort_temp);
+    e->keys_u = e->keys = nullptr; e->vals_u = e->vals = nullptr; e->sort_temp = nullptr;
+    e->cap = (int)cap;
+    e->sort_bytes = sort16_temp_bytes(e->cap);
+    int rc = 0;
+    rc |= dev_alloc(e, &e->keys_u, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->keys, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->vals_u, (size_t)e->cap);
+    rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
+    rc |= dev_alloc(e, (char**)&e->sort_temp, e->sort_bytes);
+    return rc ? GSEVT_ECUDA : 0;
+}
+
 // getProjectionMatrix (graphics_utils.py:49-69) evaluated in double like the reference's python floats,
 // stored column-major as float32.
 static void projection_colmajor(double znear, double zfar, double fovX, double fovY, float* out) {
@@ -457,9 +496,9 @@ static void projection_colmajor(double znear, double zfar, double fovX, double f
 // Enqueue one full optimisation iteration (or one evaluation) on stream s.  When `ev` is non-null an
 // event is recorded before every stage and after the last one (GSEVT_NSTAGES + 1 events): used by
 // gsevt_engine_profile for per-stage device times, never inside a captured graph.
-#define GSEVT_NSTAGES 11
+#define GSEVT_NSTAGES 12
 static const char* const kStageNames[GSEVT_NSTAGES] = {
-    "pose_setup", "preprocess_map", "scan(cub)", "emit_keys", "radix_sort(cub)", "identify_ranges",
+    "pose_setup", "preprocess_map", "depth_sort(cub)", "scan(cub)", "emit_tiles", "tile_sort(cub)", "identify_ranges",
     "blend_fwd_gray", "loss_stats", "blend_bwd_gray", "geom_bwd_pose", "engine_update"};
 
 static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = nullptr) {
@@ -474,19 +513,21 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     PreMapArgs pa;
     pa.P = P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
     pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
-    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.rec = e->rec; pa.grad8 = e->grad8;
+    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.rect = e->rect;
+    pa.rec = e->rec; pa.grad8 = e->grad8;
     launch_preprocess_map(pa, s);
     mark();
-    launch_scan(e->scan_temp, e->scan_bytes, e->tiles, e->offsets, 2 * P, s);
+    launch_sort_pairs32(e->sortA_temp, e->sortA_bytes, e->depth_key, e->depth_sorted, e->iota, e->order, 2 * P, s);
     mark();
-    launch_emit_keys(P, 2, e->views, e->rec, e->radii, e->offsets, e->keys_u, e->vals_u, e->sort_n, e->overflow,
-                     e->ctl, s);
+    launch_scan_gather(e->scan_temp, e->scan_bytes, e->rect, e->order, e->offsets, 2 * P, s);
     mark();
     const int tiles = L.gx * L.gy;
-    const int bit = (int)higher_msb((uint32_t)(2 * tiles));
-    launch_sort_pairs(e->sort_temp, e->sort_bytes, e->keys_u, e->keys, e->vals_u, e->vals, e->sort_n, 32 + bit, s);
+    launch_emit_tiles(P, L.gx, tiles, e->rect, e->order, e->offsets, e->keys_u, e->vals_u, e->sort_n, e->overflow, e->ctl, s);
     mark();
-    launch_identify_ranges(e->keys, e->ranges, 2 * tiles, -1, e->offsets + (2 * P - 1), e->sort_n, s);
+    const int bit = (int)higher_msb((uint32_t)(2 * tiles));
+    launch_sort_pairs16(e->sort_temp, e->sort_bytes, e->keys_u, e->keys, e->vals_u, e->vals, e->sort_n, bit, s);
+    mark();
+    launch_identify_ranges16(e->keys, e->ranges, 2 * tiles, e->offsets + (2 * P - 1), e->sort_n, s);
     mark();
     BlendFwdArgs f;
     memset(&f, 0, sizeof(f));
@@ -510,10 +551,10 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     memset(&q, 0, sizeof(q));
     q.P = P; q.D = m->D; q.M = 16; q.nviews = 2; q.views = e->views; q.radii = e->radii; q.clamped = e->clamped;
     q.grad8 = e->grad8; q.xyz_opacity = m->xyz_opacity; q.cov3D_a = m->cov_a; q.cov3D_b = m->cov_b;
-    q.sh_planar = m->sh_planar; q.ctl = e->ctl; q.partials = e->geom_partials;
+    q.sh_planar = m->sh_planar; q.sh_aos = m->sh_aos; q.ctl = e->ctl; q.partials = e->geom_partials;
     launch_geom_bwd_map(q, s);
     mark();
-    launch_engine_update(e->ctl, e->geom_partials, e->geom_blocks, e->host_flag_dev, s);
+    launch_engine_update(e->ctl, e->geom_partials, e->geom_blocks, e->host_flag_dev, e->overflow, s);
     mark();
 }
 
@@ -548,21 +589,22 @@ GSEVT_API int gsevt_map_create(int32_t P, int32_t sh_degree, const float* xyz, c
     m->P = P; m->D = sh_degree;
     const size_t p = (size_t)P;
     if (cudaMalloc(&m->xyz_opacity, p * 16) != cudaSuccess || cudaMalloc(&m->cov_a, p * 16) != cudaSuccess ||
-        cudaMalloc(&m->cov_b, p * 8) != cudaSuccess || cudaMalloc(&m->sh_planar, p * 48 * 4) != cudaSuccess) {
+        cudaMalloc(&m->cov_b, p * 8) != cudaSuccess || cudaMalloc(&m->sh_planar, p * 48 * 4) != cudaSuccess ||
+        cudaMalloc(&m->sh_aos, p * 48 * 4) != cudaSuccess) {
         set_error("gsevt_map_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         gsevt_map_destroy(m);
         return GSEVT_ECUDA;
     }
-    m->bytes = p * (16 + 16 + 8 + 192);
+    m->bytes = p * (16 + 16 + 8 + 192 + 192);
     launch_pack_map(P, 16, xyz, scales, rotations, opacities, shs, scale_modifier, m->xyz_opacity, m->cov_a, m->cov_b,
-                    m->sh_planar, (cudaStream_t)stream);
+                    m->sh_planar, m->sh_aos, (cudaStream_t)stream);
     GSEVT_CUDA_OK(cudaPeekAtLastError());
     *out = m;
     return 0;
 }
 GSEVT_API void gsevt_map_destroy(GsevtMap* m) {
     if (!m) return;
-    cudaFree(m->xyz_opacity); cudaFree(m->cov_a); cudaFree(m->cov_b); cudaFree(m->sh_planar);
+    cudaFree(m->xyz_opacity); cudaFree(m->cov_a); cudaFree(m->cov_b); cudaFree(m->sh_planar); cudaFree(m->sh_aos);
     delete m;
 }
 GSEVT_API int32_t gsevt_map_size(const GsevtMap* m) { return m ? m->P : 0; }
@@ -581,6 +623,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
         const double sc = pow(0.5, l);
         L.W = (int)(cfg->width * sc); L.H = (int)(cfg->height * sc);
         if (L.W <= 0 || L.H <= 0) { set_error("pyramid level %d is empty", l); delete e; return GSEVT_EINVAL; }
+        if (L.W > 255 * 16 || L.H > 255 * 16) { set_error("image larger than 4080 px is not supported by the packed tile rects"); delete e; return GSEVT_EINVAL; }
         L.gx = (L.W + 15) / 16; L.gy = (L.H + 15) / 16;
         const double fovx = 2 * atan(L.W / (2 * ((double)cfg->fx * sc)));
         const double fovy = 2 * atan(L.H / (2 * ((double)cfg->fy * sc)));
@@ -592,13 +635,15 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     }
     const int P = map->P;
     const size_t p2 = 2 * (size_t)P;
-    long long cap = cfg->instance_capacity > 0 ? (long long)cfg->instance_capacity * 2 : (long long)P * 16;
+    long long cap = cfg->instance_capacity > 0 ? (long long)cfg->instance_capacity * 2 : (long long)P * 16;   // grows on demand
     if (cap < (1 << 20)) cap = 1 << 20;
     if (cap > 0x3fffffff) cap = 0x3fffffff;
     e->cap = (int)cap;
     e->sort_n = e->cap;
     e->scan_bytes = scan_temp_bytes((int)p2);
-    e->sort_bytes = sort_temp_bytes(e->cap);
+    { const size_t g = scan_gather_temp_bytes((int)p2); if (g > e->scan_bytes) e->scan_bytes = g; }
+    e->sortA_bytes = sort32_temp_bytes((int)p2);
+    e->sort_bytes = sort16_temp_bytes(e->cap);
     e->geom_blocks = geom_bwd_blocks(P, 2);
     const LevelInfo& L0 = e->lv[0];
     const size_t hw = (size_t)L0.W * L0.H;
@@ -614,6 +659,12 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->offsets, p2);
     rc |= dev_alloc(e, &e->clamped, p2);
     rc |= dev_alloc(e, (char**)&e->scan_temp, e->scan_bytes);
+    rc |= dev_alloc(e, &e->depth_key, p2);
+    rc |= dev_alloc(e, &e->depth_sorted, p2);
+    rc |= dev_alloc(e, &e->iota, p2);
+    rc |= dev_alloc(e, &e->order, p2);
+    rc |= dev_alloc(e, &e->rect, p2);
+    rc |= dev_alloc(e, (char**)&e->sortA_temp, e->sortA_bytes);
     rc |= dev_alloc(e, &e->keys_u, (size_t)e->cap);
     rc |= dev_alloc(e, &e->keys, (size_t)e->cap);
     rc |= dev_alloc(e, &e->vals_u, (size_t)e->cap);
@@ -646,6 +697,8 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     cudaMemset(e->loss_partials, 0, ((size_t)e->loss_nb * 3 + 2) * 8);
     cudaMemset(e->grad8, 0, 2 * p2 * 16);
     cudaMemset(e->radii, 0, p2 * 4);
+    launch_iota(e->iota, (int)p2, nullptr);
+    cudaDeviceSynchronize();
     if (cudaGetLastError() != cudaSuccess) { set_error("engine init failed"); gsevt_engine_destroy(e); return GSEVT_ECUDA; }
     *out = e;
     return 0;
@@ -703,9 +756,10 @@ static int probe_instances(GsevtEngine* e, cudaStream_t s, uint32_t* total) {
     PreMapArgs pa;
     pa.P = m->P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
     pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
-    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.rec = e->rec; pa.grad8 = e->grad8;
+    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.rect = e->rect;
+    pa.rec = e->rec; pa.grad8 = e->grad8;
     launch_preprocess_map(pa, s);
-    launch_scan(e->scan_temp, e->scan_bytes, e->tiles, e->offsets, 2 * m->P, s);
+    launch_scan_gather(e->scan_temp, e->scan_bytes, e->rect, nullptr, e->offsets, 2 * m->P, s);   // plain order: only the total matters here
     GSEVT_CUDA_OK(cudaMemcpyAsync(total, e->offsets + (2 * (size_t)m->P - 1), 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     return 0;
@@ -725,10 +779,30 @@ GSEVT_API int gsevt_engine_begin_level(GsevtEngine* e, int32_t level, int32_t op
     uint32_t total = 0;
     rc = probe_instances(e, s, &total);
     if (rc) return rc;
-    long long want = (long long)(total * 1.25) + 65536;
-    if (want > e->cap) want = e->cap;
-    if ((long long)total > e->cap) { set_error("instance capacity %d exceeded (%u instances)", e->cap, total); return GSEVT_EOVERFLOW; }
+    const long long want = slots_for(total);
+    rc = ensure_capacity(e, want);
+    if (rc) return rc;
     e->sort_n = (int)want;
+    GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
+    *e->host_flag = 0;
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_resume(GsevtEngine* e, void* stream) {
+    // After the device paused a level because the instance list outgrew the sorted slots (poll_done() == 2):
+    // re-count at the current pose, grow, clear the pause.  The voided iteration left no trace in the state.
+    if (!e) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    uint32_t total = 0;
+    int rc = probe_instances(e, s, &total);   // clears level_done
+    if (rc) return rc;
+    const long long want = slots_for((long long)total + total / 8);
+    rc = ensure_capacity(e, want);
+    if (rc) return rc;
+    e->sort_n = (int)want;
+    GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     *e->host_flag = 0;
     return 0;
 }
@@ -767,10 +841,20 @@ GSEVT_API int gsevt_engine_status(GsevtEngine* e, GsevtEngineStatus* out, void* 
     uint32_t offs[2] = {0, 0};
     int ov = 0;
     GSEVT_CUDA_OK(cudaMemcpyAsync(&h, e->ctl, offsetof(EngineCtl, losses), cudaMemcpyDeviceToHost, s));
-    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[0], e->offsets + (e->map->P - 1), 4, cudaMemcpyDeviceToHost, s));
+    // instances of view 0 = start of the first non-empty range of view 1 = number of sorted keys below `tiles`;
+    // read it from the ranges: the first touched tile of view 1 starts where view 0 ends.
     GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[1], e->offsets + (2 * (size_t)e->map->P - 1), 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaMemcpyAsync(&ov, e->overflow, 4, cudaMemcpyDeviceToHost, s));
-    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    {
+        const LevelInfo& L = e->lv[e->cur_level];
+        const int tiles = L.gx * L.gy;
+        std::vector<uint2> r((size_t)2 * tiles);
+        GSEVT_CUDA_OK(cudaMemcpyAsync(r.data(), e->ranges, r.size() * sizeof(uint2), cudaMemcpyDeviceToHost, s));
+        GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+        uint32_t v0 = 0;
+        for (int t = 0; t < tiles; t++) v0 += r[t].y - r[t].x;
+        offs[0] = v0;
+    }
     memset(out, 0, sizeof(*out));
     out->level_done = h.level_done; out->optim_iter = h.optim_iter; out->start_vel_opt_iter = h.start_vel_opt_iter;
     out->opt_vel = h.opt_vel; out->iters_executed = h.iters_executed; out->overflow = ov;
@@ -825,9 +909,13 @@ GSEVT_API int gsevt_engine_eval(GsevtEngine* e, int32_t level, int32_t signed_lo
     uint32_t total = 0;
     rc = probe_instances(e, s, &total);
     if (rc) return rc;
-    if ((long long)total > e->cap) { set_error("instance capacity %d exceeded (%u instances)", e->cap, total); return GSEVT_EOVERFLOW; }
-    long long want = (long long)(total * 1.25) + 65536;
-    e->sort_n = (int)(want > e->cap ? e->cap : want);
+    {
+        const long long want = slots_for(total);
+        rc = ensure_capacity(e, want);
+        if (rc) return rc;
+        e->sort_n = (int)want;
+        GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
+    }
     enqueue_iteration(e, s);
     GsevtEngineStatus st;
     rc = gsevt_engine_status(e, &st, stream);
@@ -851,6 +939,32 @@ GSEVT_API int gsevt_engine_render_delta(GsevtEngine* e, int32_t level, float* de
     if (gray_next) GSEVT_CUDA_OK(cudaMemcpyAsync(gray_next, e->gray + hw, hw * 4, cudaMemcpyDeviceToDevice, s));
     (void)delta_out;
     return 0;
+}
+
+GSEVT_API int gsevt_engine_binning(GsevtEngine* e, int32_t view, uint64_t* keys_out, uint32_t* list_out, uint32_t* ranges_out,
+                         int32_t capacity, void* stream) {
+    if (!e || view < 0 || view > 1 || !keys_out || !list_out || !ranges_out) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const LevelInfo& L = e->lv[e->cur_level];
+    const int tiles = L.gx * L.gy;
+    std::vector<uint2> r((size_t)2 * tiles);
+    GSEVT_CUDA_OK(cudaMemcpyAsync(r.data(), e->ranges, r.size() * sizeof(uint2), cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    uint32_t n0 = 0, n1 = 0;
+    for (int t = 0; t < tiles; t++) { n0 += r[t].y - r[t].x; n1 += r[tiles + t].y - r[tiles + t].x; }
+    const uint32_t first = view == 0 ? 0u : n0, count = view == 0 ? n0 : n1;
+    if ((int64_t)count > (int64_t)capacity) { set_error("capacity %d < %u instances", capacity, count); return GSEVT_ENOMEM; }
+    launch_rebuild_keys(e->keys, e->vals, e->rec + 2 * (size_t)view * e->map->P, (uint32_t)(view * tiles), first, count, keys_out,
+                        list_out, s);
+    // ranges of this view, rebased to its own list (untouched tiles stay (0,0) like the reference's)
+    std::vector<uint32_t> rr((size_t)2 * tiles, 0u);
+    for (int t = 0; t < tiles; t++) {
+        const uint2 q = r[(size_t)view * tiles + t];
+        if (q.y > q.x) { rr[2 * t] = q.x - first; rr[2 * t + 1] = q.y - first; }
+    }
+    GSEVT_CUDA_OK(cudaMemcpyAsync(ranges_out, rr.data(), rr.size() * 4, cudaMemcpyHostToDevice, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    return (int)count;
 }
 
 GSEVT_API int gsevt_engine_stage_count(void) { return GSEVT_NSTAGES; }
@@ -890,9 +1004,14 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
     unsigned long long h[8];
     uint32_t offs[2] = {0, 0};
     GSEVT_CUDA_OK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
-    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[0], e->offsets + (e->map->P - 1), 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[1], e->offsets + (2 * (size_t)e->map->P - 1), 4, cudaMemcpyDeviceToHost, s));
-    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    {
+        const int tiles = L.gx * L.gy;
+        std::vector<uint2> r((size_t)2 * tiles);
+        GSEVT_CUDA_OK(cudaMemcpyAsync(r.data(), e->ranges, r.size() * sizeof(uint2), cudaMemcpyDeviceToHost, s));
+        GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+        for (int t = 0; t < tiles; t++) offs[0] += r[t].y - r[t].x;
+    }
     cudaFree(d);
     out8[0] = (int64_t)h[0]; out8[1] = (int64_t)h[1];              // visible Gaussians per view
     out8[2] = (int64_t)offs[0]; out8[3] = (int64_t)(offs[1] - offs[0]);  // tile instances per view
@@ -904,8 +1023,8 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
 
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e) {
     (void)e;
-    // pose_setup, preprocess, emit_keys, identify_ranges, blend_fwd, loss_stats, blend_bwd, geom_bwd, update = 9 of
-    // ours; plus CUB: scan (2 kernels) and radix sort (histogram + one onesweep per 8-bit digit), and one memset.
+    // pose_setup, preprocess, emit_tiles, identify_ranges, blend_fwd, loss_stats, blend_bwd, geom_bwd, update = 9 of
+    // ours; plus CUB: two radix sorts (histogram + exclusive sum + one onesweep per 8-bit digit) and a scan, one memset.
     return 9;
 }
 

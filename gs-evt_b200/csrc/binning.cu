@@ -7,6 +7,8 @@
 // library the reference calls); everything else is ours.  HBM-bound.
 #include "internal.h"
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 namespace gsevt {
 
@@ -163,6 +165,156 @@ void launch_build_view_params(ViewParams* out, const float* view, const float* p
                               float tanfovx, float tanfovy, int W, int H, float delta_time, cudaStream_t s) {
     build_view_params_kernel<<<1, 32, 0, s>>>(out, view, proj, proj_raw, campos, vel, vel_inv, bg, tanfovx, tanfovy, W,
                                               H, delta_time);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Engine path: two-level binning.
+//
+// The reference's order inside a tile is (depth bits, Gaussian index) — the second by stability of the
+// radix sort over the emission order (rasterizer_impl.cu:85-109,306-311).  The same total order is
+// produced with far less traffic by
+//   1. sorting the 2P (view, Gaussian) pairs ONCE by their 32-bit depth key (stable: ties keep index order;
+//      culled pairs carry key 0xFFFFFFFF and sink to the end),
+//   2. emitting tile instances in that order with a 16-bit key = tile id (+ tiles per view for view 1),
+//   3. a stable sort on the tile id alone (<= 13 bits: two 8-bit passes instead of six over 64-bit keys).
+// Within a tile the stable tile sort preserves emission order = (depth, index) order, so point lists and
+// tile ranges are identical to the reference's; gsevt_engine_binning() rebuilds the 64-bit keys for the tests.
+// ------------------------------------------------------------------------------------------------
+size_t sort32_temp_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n > 0 ? n : 1);
+    return bytes;
+}
+size_t sort16_temp_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint16_t*)nullptr, (uint16_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n > 0 ? n : 1);
+    return bytes;
+}
+void launch_sort_pairs32(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
+                         const uint32_t* vals_in, uint32_t* vals_out, int n, cudaStream_t s) {
+    if (n <= 0) return;
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 32, s);
+}
+void launch_sort_pairs16(void* temp, size_t temp_bytes, const uint16_t* keys_in, uint16_t* keys_out,
+                         const uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit, cudaStream_t s) {
+    if (n <= 0) return;
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, end_bit, s);
+}
+
+namespace {
+__host__ __device__ __forceinline__ uint32_t rect_area(uint32_t r) {
+    return ((r >> 16 & 255u) - (r & 255u)) * ((r >> 24) - (r >> 8 & 255u));
+}
+struct GatherArea {
+    const uint32_t* rects;
+    const uint32_t* order;
+    __host__ __device__ __forceinline__ uint32_t operator()(int i) const { return rect_area(rects[order ? order[i] : (uint32_t)i]); }
+};
+}  // namespace
+size_t scan_gather_temp_bytes(int n) {
+    size_t bytes = 0;
+    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), GatherArea{nullptr, nullptr});
+    cub::DeviceScan::InclusiveSum(nullptr, bytes, it, (uint32_t*)nullptr, n > 0 ? n : 1);
+    return bytes;
+}
+void launch_scan_gather(void* temp, size_t temp_bytes, const uint32_t* rects, const uint32_t* order, uint32_t* offsets, int n,
+                        cudaStream_t s) {
+    if (n <= 0) return;
+    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), GatherArea{rects, order});
+    cub::DeviceScan::InclusiveSum(temp, temp_bytes, it, offsets, n, s);
+}
+
+// One thread per sorted position: one dependent gather (the packed rect) and a run of (tile, id) stores.
+// Also fills the unused capacity [total, cap) with sentinel keys.
+__global__ void __launch_bounds__(256) emit_tiles_kernel(int P, int gx, int tiles_per_view, const uint32_t* __restrict__ rects,
+                                                         const uint32_t* __restrict__ order,
+                                                         const uint32_t* __restrict__ offsets, uint16_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ values, int cap, int* __restrict__ overflow,
+                                                         const EngineCtl* __restrict__ ctl) {
+    if (ctl && ctl->level_done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = 2 * P;
+    const uint32_t total = offsets[n - 1];
+    if (i == 0 && total > (uint32_t)cap) *overflow = 1;
+    if (i < cap && (uint32_t)i >= total) {
+        keys[i] = 0xFFFFu;
+        values[i] = 0u;
+    }
+    if (i >= n) return;
+    const uint32_t gid = order[i];
+    const uint32_t r = __ldg(rects + gid);
+    if (r == 0u) return;
+    const int x0 = r & 255u, y0 = r >> 8 & 255u, x1 = r >> 16 & 255u, y1 = r >> 24;
+    const int v = gid >= (uint32_t)P ? 1 : 0;
+    uint32_t off = i == 0 ? 0u : offsets[i - 1];
+    const uint32_t tile_base = (uint32_t)(v * tiles_per_view);
+    const uint32_t idx = gid - (uint32_t)v * (uint32_t)P;
+    for (int y = y0; y < y1; y++) {
+        for (int x = x0; x < x1; x++) {
+            if (off >= (uint32_t)cap) return;
+            keys[off] = (uint16_t)(tile_base + (uint32_t)(y * gx + x));
+            values[off] = idx;
+            off++;
+        }
+    }
+}
+void launch_emit_tiles(int P, int grid_x, int tiles_per_view, const uint32_t* rects, const uint32_t* order,
+                       const uint32_t* offsets, uint16_t* keys, uint32_t* values, int cap, int* overflow,
+                       const EngineCtl* ctl, cudaStream_t s) {
+    const int threads = 2 * P > cap ? 2 * P : cap;
+    if (threads <= 0) return;
+    emit_tiles_kernel<<<(threads + 255) / 256, 256, 0, s>>>(P, grid_x, tiles_per_view, rects, order, offsets, keys, values, cap,
+                                                           overflow, ctl);
+}
+
+__global__ void __launch_bounds__(256) identify_ranges16_kernel(const uint16_t* __restrict__ keys, uint2* __restrict__ ranges,
+                                                                const uint32_t* __restrict__ n_dev, int cap) {
+    const uint32_t L = min(*n_dev, (uint32_t)cap);
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L) return;
+    const uint32_t cur = keys[idx];
+    if (idx == 0)
+        ranges[cur].x = 0;
+    else {
+        const uint32_t prev = keys[idx - 1];
+        if (cur != prev) {
+            ranges[prev].y = idx;
+            ranges[cur].x = idx;
+        }
+    }
+    if (idx == L - 1) ranges[cur].y = L;
+}
+void launch_identify_ranges16(const uint16_t* keys, uint2* ranges, int ntiles_total, const uint32_t* n_dev, int cap,
+                              cudaStream_t s) {
+    cudaMemsetAsync(ranges, 0, (size_t)ntiles_total * sizeof(uint2), s);
+    if (cap <= 0) return;
+    identify_ranges16_kernel<<<(cap + 255) / 256, 256, 0, s>>>(keys, ranges, n_dev, cap);
+}
+
+__global__ void iota_kernel(uint32_t* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+void launch_iota(uint32_t* out, int n, cudaStream_t s) {
+    if (n > 0) iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(out, n);
+}
+
+// Parity-test helper: rebuild the reference's 64-bit keys of one view from the engine's sorted lists.
+__global__ void rebuild_keys_kernel(const uint16_t* __restrict__ tile_keys, const uint32_t* __restrict__ vals,
+                                    const float4* __restrict__ rec_view, uint32_t tile_base, uint32_t first, uint32_t count,
+                                    uint64_t* __restrict__ keys_out, uint32_t* __restrict__ list_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t id = vals[first + i];
+    const uint32_t tile = (uint32_t)tile_keys[first + i] - tile_base;
+    keys_out[i] = ((uint64_t)tile << 32) | __float_as_uint(rec_view[2 * (size_t)id + 1].w);
+    list_out[i] = id;
+}
+void launch_rebuild_keys(const uint16_t* tile_keys, const uint32_t* vals, const float4* rec_view, uint32_t tile_base,
+                         uint32_t first, uint32_t count, uint64_t* keys_out, uint32_t* list_out, cudaStream_t s) {
+    if (count) rebuild_keys_kernel<<<(count + 255) / 256, 256, 0, s>>>(tile_keys, vals, rec_view, tile_base, first, count, keys_out, list_out);
 }
 
 }  // namespace gsevt

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     if (a.ctl && a.ctl->level_done) return;
     __shared__ float4 s_r0[256];
     __shared__ float4 s_r1[256];
-    __shared__ float2 s_ext[256];
+    __shared__ float4 s_cull[256];   // {x, y, half extent x, half extent y} of the alpha >= 1/255 ellipse's box
     __shared__ float4 s_rgb[OPERATOR ? 256 : 1];
     __shared__ int s_id[OPERATOR ? 256 : 1];
 
@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
             const float4 r1 = __ldg(rec + 2 * (size_t)id + 1);
             s_r0[threadIdx.x] = r0;
             s_r1[threadIdx.x] = r1;
-            s_ext[threadIdx.x] = cull_extent(r0.z, r0.w, r1.x, r1.y);
+            const float2 ext = cull_extent(r0.z, r0.w, r1.x, r1.y);
+            s_cull[threadIdx.x] = make_float4(r0.x, r0.y, ext.x, ext.y);
             if constexpr (OPERATOR) {
                 s_rgb[threadIdx.x] = __ldg(a.rgb4 + id);
                 s_id[threadIdx.x] = (int)id;
@@ -98,35 +99,45 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
         }
         __syncthreads();
         const int cnt = min(256, todo - base);
-        for (int j = 0; j < cnt; j++) {
-            if ((j & 31) == 0 && __all_sync(0xffffffffu, done)) break;
-            const float4 r0 = s_r0[j];
-            const float2 ext = s_ext[j];
-            if (fabsf(r0.x - cxw) > ext.x || fabsf(r0.y - cyw) > ext.y) continue;  // warp-uniform
-            if (done) continue;
-            const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
-            const float4 r1 = s_r1[j];
-            const float power = eval_power(dx, dy, r0.z, r0.w, r1.x);
-            if (power > 0.0f) continue;
-            const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
-            if (alpha < kAlphaMin) continue;
-            const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
-            if (test_T < 0.0001f) {
-                done = true;
-                continue;
+        // 32 staged instances at a time: lane l tests instance j0+l against this warp's 8x4 pixel block, the
+        // ballot is the ordered hit list, and only hits are evaluated per pixel (list order is preserved).
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            if (__all_sync(0xffffffffu, done)) break;
+            bool hit = false;
+            if (j0 + lane < cnt) {
+                const float4 c = s_cull[j0 + lane];
+                hit = fabsf(c.x - cxw) <= c.z && fabsf(c.y - cyw) <= c.w;
             }
-            if constexpr (OPERATOR) {
-                const float4 col = s_rgb[j];
-                acc[0] = __fmaf_rn(T, __fmul_rn(alpha, col.x), acc[0]);
-                acc[1] = __fmaf_rn(T, __fmul_rn(alpha, col.y), acc[1]);
-                acc[2] = __fmaf_rn(T, __fmul_rn(alpha, col.z), acc[2]);
-                D = __fmaf_rn(T, __fmul_rn(alpha, r1.w), D);
-                if (a.n_touched && test_T > 0.5f) atomicAdd(a.n_touched + s_id[j], 1);
-            } else {
-                acc[0] = __fmaf_rn(T, __fmul_rn(alpha, r1.z), acc[0]);
+            unsigned hits = __ballot_sync(0xffffffffu, hit);
+            while (hits) {
+                const int j = j0 + __ffs(hits) - 1;
+                hits &= hits - 1;
+                if (done) continue;
+                const float4 r0 = s_r0[j];
+                const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
+                const float4 r1 = s_r1[j];
+                const float power = eval_power(dx, dy, r0.z, r0.w, r1.x);
+                if (power > 0.0f) continue;
+                const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
+                if (alpha < kAlphaMin) continue;
+                const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
+                if (test_T < 0.0001f) {
+                    done = true;
+                    continue;
+                }
+                if constexpr (OPERATOR) {
+                    const float4 col = s_rgb[j];
+                    acc[0] = __fmaf_rn(T, __fmul_rn(alpha, col.x), acc[0]);
+                    acc[1] = __fmaf_rn(T, __fmul_rn(alpha, col.y), acc[1]);
+                    acc[2] = __fmaf_rn(T, __fmul_rn(alpha, col.z), acc[2]);
+                    D = __fmaf_rn(T, __fmul_rn(alpha, r1.w), D);
+                    if (a.n_touched && test_T > 0.5f) atomicAdd(a.n_touched + s_id[j], 1);
+                } else {
+                    acc[0] = __fmaf_rn(T, __fmul_rn(alpha, r1.z), acc[0]);
+                }
+                T = test_T;
+                last_contributor = (uint32_t)(base + j + 1);
             }
-            T = test_T;
-            last_contributor = (uint32_t)(base + j + 1);
         }
     }
 
@@ -162,16 +173,40 @@ void launch_blend_fwd_gray(const BlendFwdArgs& a, cudaStream_t s) {
 // Values reduced per instance.  Engine: dmx dmy dA dB dC dgray (6).  Operator: dmx dmy dA dB dC dop
 // dc0 ddepth dc1 dc2 (10).  Row stride padded to an odd word count (bank-conflict-free flush).
 template <bool OPERATOR> struct BwdCfg;
-template <> struct BwdCfg<false> { static constexpr int K = 6, KP = 7, BATCH = 128; };
-template <> struct BwdCfg<true> { static constexpr int K = 10, KP = 11, BATCH = 64; };
+template <> struct BwdCfg<false> { static constexpr int K = 6, KR = 8, KP = 7, BATCH = 128; };
+template <> struct BwdCfg<true> { static constexpr int K = 10, KR = 16, KP = 11, BATCH = 64; };
+
+// Sum of each of N (power of two <= 32) per-lane values over the warp.  Returns, on every lane, the total of
+// component lane / (32 / N).  Halving exchange: at each step a lane keeps one half of its values and trades
+// the other half with its partner, so N values cost N - 1 + log2(32 / N) shuffles instead of 5 N.
+template <int N>
+__device__ __forceinline__ float warp_reduce_scatter(float (&v)[N], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1) {
+        const int half = n >> 1;
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; i++) {
+            const float send = hi ? v[i] : v[half + i];
+            const float keep = hi ? v[half + i] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        off >>= 1;
+    }
+    float r = v[0];
+#pragma unroll
+    for (; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+    return r;
+}
 
 template <int C, bool OPERATOR>
 __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     if (a.ctl && a.ctl->level_done) return;
-    constexpr int K = BwdCfg<OPERATOR>::K, KP = BwdCfg<OPERATOR>::KP, BATCH = BwdCfg<OPERATOR>::BATCH;
+    constexpr int K = BwdCfg<OPERATOR>::K, KR = BwdCfg<OPERATOR>::KR, KP = BwdCfg<OPERATOR>::KP, BATCH = BwdCfg<OPERATOR>::BATCH;
     __shared__ float4 s_r0[BATCH];
     __shared__ float4 s_r1[BATCH];
-    __shared__ float2 s_ext[BATCH];
+    __shared__ float4 s_cull[BATCH];
     __shared__ float4 s_rgb[OPERATOR ? BATCH : 1];
     __shared__ uint32_t s_id[BATCH];
     __shared__ uint32_t s_mask[BATCH];
@@ -248,17 +283,25 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
             const float4 r1 = __ldg(rec + 2 * (size_t)id + 1);
             s_r0[threadIdx.x] = r0;
             s_r1[threadIdx.x] = r1;
-            s_ext[threadIdx.x] = cull_extent(r0.z, r0.w, r1.x, r1.y);
+            const float2 ext = cull_extent(r0.z, r0.w, r1.x, r1.y);
+            s_cull[threadIdx.x] = make_float4(r0.x, r0.y, ext.x, ext.y);
             s_id[threadIdx.x] = id;
             s_mask[threadIdx.x] = 0u;
             if constexpr (OPERATOR) s_rgb[threadIdx.x] = __ldg(a.rgb4 + id);
         }
         __syncthreads();
 
-        for (int j = 0; j < cnt; j++) {
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            bool hit = false;
+            if (j0 + lane < cnt) {
+                const float4 c = s_cull[j0 + lane];
+                hit = fabsf(c.x - cxw) <= c.z && fabsf(c.y - cyw) <= c.w;
+            }
+            unsigned hits = __ballot_sync(0xffffffffu, hit);
+            while (hits) {
+            const int j = j0 + __ffs(hits) - 1;
+            hits &= hits - 1;
             const float4 r0 = s_r0[j];
-            const float2 ext = s_ext[j];
-            if (fabsf(r0.x - cxw) > ext.x || fabsf(r0.y - cyw) > ext.y) continue;  // warp-uniform
             const uint32_t pos = (uint32_t)(hi - j);
             const float4 r1 = s_r1[j];
             const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
@@ -268,9 +311,9 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
             const bool skip = !inside || pos >= last_contributor || power > 0.0f || alpha < kAlphaMin;
             if (__all_sync(0xffffffffu, skip)) continue;
 
-            float v[K];
+            float v[KR];
 #pragma unroll
-            for (int k = 0; k < K; k++) v[k] = 0.0f;
+            for (int k = 0; k < KR; k++) v[k] = 0.0f;
             if (!skip) {
                 T = T / (1.0f - alpha);
                 const float w = alpha * T;
@@ -311,14 +354,12 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
                 v[4] = -0.5f * gdy * dy * dL_dG;
                 if constexpr (OPERATOR) v[5] = G * dL_dalpha;
             }
-#pragma unroll
-            for (int k = 0; k < K; k++) v[k] = warp_sum(v[k]);
-            // lane k parks component k
-            float mine = v[0];
-#pragma unroll
-            for (int k = 1; k < K; k++) mine = lane == k ? v[k] : mine;
-            if (lane < K) my_acc[j * KP + lane] = mine;
+            // reduce-scatter over the warp: after log2(KR) halving exchanges each lane owns ONE component
+            // (index = lane / (32/KR)), finished with plain butterflies — 9 shuffles for 8 values instead of 40
+            const float mine = warp_reduce_scatter<KR>(v, lane);
+            if ((lane & (32 / KR - 1)) == 0 && lane / (32 / KR) < K) my_acc[j * KP + lane / (32 / KR)] = mine;
             if (lane == 0) atomicOr(&s_mask[j], 1u << warp);
+            }
         }
         __syncthreads();
 

@@ -168,8 +168,20 @@ __device__ void adam_group(EngineCtl* c, int group, const float* grad, double lr
 
 __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineCtl* ctl,
                                                                           const float* __restrict__ partials,
-                                                                          int nblocks, int* host_flag) {
+                                                                          int nblocks, int* host_flag,
+                                                                          const int* __restrict__ overflow) {
     if (ctl->level_done) return;
+    if (overflow && *overflow) {
+        // The instance list outgrew the slots sorted this iteration: void the iteration (state untouched), pause
+        // the level (2) and tell the host, which re-sizes and resumes (gsevt_engine_resume).
+        if (threadIdx.x == 0) {
+            ctl->level_done = 2;
+            ctl->overflow = 1;
+            if (host_flag) *host_flag = 2;
+            __threadfence_system();
+        }
+        return;
+    }
     __shared__ float s_g[GSEVT_NPART];
     {
         const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -252,8 +264,9 @@ __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineC
         c->optim_iter += 1;
     }
 }
-void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, cudaStream_t s) {
-    engine_update_kernel<<<1, 32 * GSEVT_NPART, 0, s>>>(ctl, partials, nblocks, host_flag);
+void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, const int* overflow,
+                          cudaStream_t s) {
+    engine_update_kernel<<<1, 32 * GSEVT_NPART, 0, s>>>(ctl, partials, nblocks, host_flag, overflow);
 }
 
 // ---- per-frame helpers ----------------------------------------------------------------------------

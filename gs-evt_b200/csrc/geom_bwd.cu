@@ -51,11 +51,21 @@ __device__ __forceinline__ void build_cur(SharedCam& c) {
 
 }  // namespace
 
+// Work distribution.  Only a small fraction of the (view, Gaussian) pairs carries a gradient (a few per cent on
+// the benchmark map: most Gaussians are culled, occluded or below the alpha threshold), and the per-pair
+// work is heavy and divergent.  Each CTA therefore scans a chunk of GEOM_CHUNK consecutive pairs with fully
+// coalesced loads, compacts the active ones into shared memory (deterministic order: ballot + block prefix)
+// and then runs the chain densely over the compacted list — full warps instead of one live lane per warp.
+#define GEOM_CHUNK 2048
+
 template <bool ENGINE>
 __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
     if (a.ctl && a.ctl->level_done) return;
     __shared__ SharedCam s_cam[2];
     __shared__ float s_red[8][GSEVT_NPART];
+    __shared__ uint32_t s_list[GEOM_CHUNK];
+    __shared__ int s_wcount[8];
+    __shared__ int s_count;
     for (int v = 0; v < a.nviews; v++) {
         load_views(&s_cam[v].vp, a.views + v, 1);
     }
@@ -64,12 +74,39 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
 
     const int P = a.P;
     const long long n = (long long)a.nviews * P;
+    const int warp_id = threadIdx.x >> 5, lane_id = threadIdx.x & 31;
     float acc[GSEVT_NPART];
 #pragma unroll
     for (int k = 0; k < GSEVT_NPART; k++) acc[k] = 0.0f;
 
-    for (long long gid = (long long)blockIdx.x * 256 + threadIdx.x; gid < n; gid += (long long)gridDim.x * 256) {
-        if (a.radii[gid] <= 0) continue;
+    for (long long chunk = (long long)blockIdx.x * GEOM_CHUNK; chunk < n; chunk += (long long)gridDim.x * GEOM_CHUNK) {
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        for (int k = 0; k < GEOM_CHUNK / 256; k++) {
+            const long long gid = chunk + k * 256 + threadIdx.x;
+            bool active = gid < n && a.radii[gid] > 0;
+            if (ENGINE && active) {
+                const float4 g0 = __ldg(a.grad8 + 2 * gid);
+                const float2 g1 = __ldg(reinterpret_cast<const float2*>(a.grad8 + 2 * gid + 1));
+                active = g0.x != 0.f || g0.y != 0.f || g0.z != 0.f || g0.w != 0.f || g1.x != 0.f || g1.y != 0.f;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, active);
+            if (lane_id == 0) s_wcount[warp_id] = __popc(bal);
+            __syncthreads();
+            int base = s_count;
+            for (int w = 0; w < warp_id; w++) base += s_wcount[w];
+            if (active) s_list[base + __popc(bal & ((1u << lane_id) - 1u))] = (uint32_t)(gid - chunk);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int t = 0;
+                for (int w = 0; w < 8; w++) t += s_wcount[w];
+                s_count += t;
+            }
+            __syncthreads();
+        }
+        const int count = s_count;
+    for (int li = threadIdx.x; li < count; li += 256) {
+        const long long gid = chunk + s_list[li];
         const float4 g0 = __ldg(a.grad8 + 2 * gid);
         const float4 g1 = __ldg(a.grad8 + 2 * gid + 1);
         const int view = (int)(gid / P);
@@ -79,7 +116,6 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
         const unsigned clampbits = a.clamped[gid];
         if constexpr (ENGINE) {
             const float dgray = g1.y;
-            if (dmx == 0.f && dmy == 0.f && dA == 0.f && dB == 0.f && dC == 0.f && dgray == 0.f) continue;
             dcol[0] = GSEVT_GRAY_R * dgray; dcol[1] = GSEVT_GRAY_G * dgray; dcol[2] = GSEVT_GRAY_B * dgray;
         } else {
             const float2 gc = __ldg(a.gradc + idx);
@@ -202,10 +238,16 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
             for (int ch = 0; ch < 3; ch++) dRGB[ch] = (clampbits >> ch) & 1u ? 0.0f : dcol[ch];
             const float ox = mx - vp.campos[0], oy = my - vp.campos[1], oz = mz - vp.campos[2];
             if constexpr (ENGINE) {
-                const float* sh = a.sh_planar + idx;
-                const size_t PP = (size_t)P;
-                sh_dir_grad(a.D, ox, oy, oz, [&](int k, int ch) { return __ldg(sh + (size_t)(k * 3 + ch) * PP); }, dRGB,
-                            gsh);
+                // sparse access: the AoS copy costs 6 sectors per Gaussian, the planar one (built for the dense
+                // forward pass) would cost 48
+                const float4* sh4 = reinterpret_cast<const float4*>(a.sh_aos) + 12 * (size_t)idx;
+                float shv[48];
+#pragma unroll
+                for (int q = 0; q < 12; q++) {
+                    const float4 t = __ldg(sh4 + q);
+                    shv[4 * q] = t.x; shv[4 * q + 1] = t.y; shv[4 * q + 2] = t.z; shv[4 * q + 3] = t.w;
+                }
+                sh_dir_grad(a.D, ox, oy, oz, [&](int k, int ch) { return shv[k * 3 + ch]; }, dRGB, gsh);
             } else {
                 const float* sh = a.shs + (size_t)idx * a.M * 3;
                 sh_dir_grad(a.D, ox, oy, oz, [&](int k, int ch) { return __ldg(sh + k * 3 + ch); }, dRGB, gsh);
@@ -315,6 +357,8 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
             }
         }
     }
+        __syncthreads();
+    }
 
     // block reduction of the 12 pose components -> partials[blockIdx.x][12] (fixed order, no atomics)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -334,7 +378,7 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
 
 int geom_bwd_blocks(int P, int nviews) {
     const long long n = (long long)P * nviews;
-    long long b = (n + 255) / 256;
+    long long b = (n + GEOM_CHUNK - 1) / GEOM_CHUNK;
     const long long cap = 148 * 8;  // one wave of 8 resident CTAs per SM
     if (b > cap) b = cap;
     if (b < 1) b = 1;

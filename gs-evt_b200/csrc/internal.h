@@ -78,6 +78,8 @@ struct PreMapArgs {
     int* radii;               // [2P]
     uint32_t* tiles_touched;  // [2P]
     uint8_t* clamped;         // [2P]
+    uint32_t* depth_key;      // [2P] float bits of the view depth, 0xFFFFFFFF when culled
+    uint32_t* rect;           // [2P] packed tile rect (x0 | y0<<8 | x1<<16 | y1<<24), 0 when culled
     float4* rec;              // [2][2P]
     float4* grad8;            // [2][2P]
 };
@@ -85,7 +87,7 @@ void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s);
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s);
 void launch_pack_map(int P, int M, const float* xyz, const float* scales, const float* rots, const float* opac,
                      const float* shs, float mod, float4* xyz_opacity, float4* cov_a, float2* cov_b, float* sh_planar,
-                     cudaStream_t s);
+                     float* sh_aos, cudaStream_t s);
 // Fills a ViewParams from the operator's device-side matrices.
 void launch_build_view_params(ViewParams* out, const float* view, const float* proj, const float* proj_raw,
                               const float* campos, const float* vel, const float* vel_inv, const float* bg,
@@ -106,6 +108,25 @@ void launch_sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, u
 void launch_identify_ranges(const uint64_t* keys, uint2* ranges, int ntiles_total, int n_host, const uint32_t* n_dev,
                             int cap, cudaStream_t s);
 uint32_t higher_msb(uint32_t n);
+// engine: two-level binning (depth sort of (view, Gaussian) pairs, then a stable 16-bit tile sort)
+size_t sort32_temp_bytes(int n);
+size_t sort16_temp_bytes(int n);
+size_t scan_gather_temp_bytes(int n);
+void launch_sort_pairs32(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
+                         const uint32_t* vals_in, uint32_t* vals_out, int n, cudaStream_t s);
+void launch_sort_pairs16(void* temp, size_t temp_bytes, const uint16_t* keys_in, uint16_t* keys_out,
+                         const uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit, cudaStream_t s);
+// offsets = inclusive sum of the tile-rect areas, visited in `order` (identity when order == NULL)
+void launch_scan_gather(void* temp, size_t temp_bytes, const uint32_t* rects, const uint32_t* order, uint32_t* offsets, int n,
+                        cudaStream_t s);
+void launch_emit_tiles(int P, int grid_x, int tiles_per_view, const uint32_t* rects, const uint32_t* order,
+                       const uint32_t* offsets, uint16_t* keys, uint32_t* values, int cap, int* overflow,
+                       const EngineCtl* ctl, cudaStream_t s);
+void launch_identify_ranges16(const uint16_t* keys, uint2* ranges, int ntiles_total, const uint32_t* n_dev, int cap,
+                              cudaStream_t s);
+void launch_iota(uint32_t* out, int n, cudaStream_t s);
+void launch_rebuild_keys(const uint16_t* tile_keys, const uint32_t* vals, const float4* rec_view, uint32_t tile_base,
+                         uint32_t first, uint32_t count, uint64_t* keys_out, uint32_t* list_out, cudaStream_t s);
 
 // ---- blending --------------------------------------------------------------------------------
 struct BlendFwdArgs {
@@ -168,7 +189,7 @@ struct GeomBwdArgs {
     // map (AoS operator / packed engine)
     const float* means3D; const float* shs; const float* cov3D;            // operator
     const float* scales; const float* rotations; float scale_modifier;     // operator (map grads)
-    const float4* xyz_opacity; const float4* cov3D_a; const float2* cov3D_b; const float* sh_planar;  // engine
+    const float4* xyz_opacity; const float4* cov3D_a; const float2* cov3D_b; const float* sh_planar; const float* sh_aos;  // engine
     int colors_precomp;          // operator: colours were given, no SH chain
     const EngineCtl* ctl;
     float* partials;             // [nblocks][12]
@@ -188,7 +209,8 @@ int loss_blocks(int HW);
 
 // ---- engine control kernels ----------------------------------------------------------------------
 void launch_pose_setup(EngineCtl* ctl, ViewParams* views, const float* bg3, float znear, float zfar, cudaStream_t s);
-void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, cudaStream_t s);
+void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, const int* overflow,
+                          cudaStream_t s);
 void launch_const_vel(EngineCtl* ctl, float tau, cudaStream_t s);
 void launch_weighted_velocity(EngineCtl* ctl, const float* lastRT, float delta_tau, float weight, cudaStream_t s);
 

@@ -14,6 +14,7 @@ namespace gsevt {
 struct ProjOut {
     int radius;
     int tiles;
+    uint32_t rect;   // x0 | y0 << 8 | x1 << 16 | y1 << 24 (tile units; grids up to 255 x 255)
     float mx, my, depth;
     float A, B, C;
 };
@@ -51,6 +52,7 @@ __device__ __forceinline__ bool project_geometry(const ViewParams& vp, float px,
     if (area == 0) return false;
     o.radius = radius;
     o.tiles = area;
+    o.rect = (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
     o.depth = depth;
     return true;
 }
@@ -153,7 +155,8 @@ __global__ void __launch_bounds__(256) preprocess_map_kernel(PreMapArgs a) {
     for (int v = 0; v < 2; v++) {
         const size_t j = (size_t)v * a.P + idx;
         a.radii[j] = ok[v] ? o[v].radius : 0;
-        a.tiles_touched[j] = ok[v] ? (uint32_t)o[v].tiles : 0u;
+        a.depth_key[j] = ok[v] ? __float_as_uint(o[v].depth) : 0xFFFFFFFFu;
+        a.rect[j] = ok[v] ? o[v].rect : 0u;
     }
     if (!ok[0] && !ok[1]) return;
     // SH -> RGB for both views from ONE pass over the 48 planar coefficients (coalesced 128-byte lines)
@@ -221,7 +224,8 @@ void launch_mark_visible(int P, const float* means, const float* view, uint8_t* 
 __global__ void pack_map_kernel(int P, int M, const float* __restrict__ xyz, const float* __restrict__ scales,
                                 const float* __restrict__ rots, const float* __restrict__ opac,
                                 const float* __restrict__ shs, float mod, float4* __restrict__ xyz_opacity,
-                                float4* __restrict__ cov_a, float2* __restrict__ cov_b, float* __restrict__ sh_planar) {
+                                float4* __restrict__ cov_a, float2* __restrict__ cov_b, float* __restrict__ sh_planar,
+                                float* __restrict__ sh_aos) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const size_t i = idx;
@@ -232,16 +236,19 @@ __global__ void pack_map_kernel(int P, int M, const float* __restrict__ xyz, con
     cov_a[i] = make_float4(cov[0], cov[1], cov[2], cov[3]);
     cov_b[i] = make_float2(cov[4], cov[5]);
     for (int k = 0; k < 16; k++)
-        for (int ch = 0; ch < 3; ch++)
-            sh_planar[(size_t)(k * 3 + ch) * P + i] = k < M ? shs[(i * M + k) * 3 + ch] : 0.0f;
+        for (int ch = 0; ch < 3; ch++) {
+            const float c = k < M ? shs[(i * M + k) * 3 + ch] : 0.0f;
+            sh_planar[(size_t)(k * 3 + ch) * P + i] = c;    // dense access (forward projection)
+            sh_aos[i * 48 + k * 3 + ch] = c;                 // sparse access (backward, few Gaussians carry a gradient)
+        }
 }
 
 void launch_pack_map(int P, int M, const float* xyz, const float* scales, const float* rots, const float* opac,
                      const float* shs, float mod, float4* xyz_opacity, float4* cov_a, float2* cov_b, float* sh_planar,
-                     cudaStream_t s) {
+                     float* sh_aos, cudaStream_t s) {
     if (P <= 0) return;
     pack_map_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, M, xyz, scales, rots, opac, shs, mod, xyz_opacity, cov_a, cov_b,
-                                                   sh_planar);
+                                                   sh_planar, sh_aos);
 }
 
 }  // namespace gsevt

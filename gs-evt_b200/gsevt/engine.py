@@ -131,14 +131,17 @@ class TrackingEngine:
             _lib.check(self._lib.gsevt_engine_iterate(self.handle, int(n), self.stream.cuda_stream), "gsevt_engine_iterate")
 
     def poll_done(self):
-        return bool(self._lib.gsevt_engine_poll_done(self.handle))
+        """0 running, 1 level finished, 2 paused (instance list outgrew the sorted slots: call resume())."""
+        return int(self._lib.gsevt_engine_poll_done(self.handle))
+
+    def resume(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_resume(self.handle, self.stream.cuda_stream), "gsevt_engine_resume")
 
     def status(self):
         st = _lib.GsevtEngineStatus()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.gsevt_engine_status(self.handle, C.byref(st), self.stream.cuda_stream), "gsevt_engine_status")
-        if st.overflow:
-            raise _lib.GsevtError("tile-instance capacity exceeded; recreate the engine with a larger instance_capacity")
         return st
 
     def losses(self):
@@ -154,7 +157,10 @@ class TrackingEngine:
         while True:
             self.iterate(chunk)
             self.stream.synchronize()
-            if self.poll_done():
+            flag = self.poll_done()
+            if flag == 2:
+                self.resume()
+            elif flag:
                 break
         return self.status()
 
@@ -189,6 +195,20 @@ class TrackingEngine:
                                                            self.stream.cuda_stream), "gsevt_engine_render_delta")
         self.stream.synchronize()
         return last, nxt
+
+    def binning(self, view, level):
+        """Sorted (keys, Gaussian ids, tile ranges) of `view` from the most recent evaluation, in the reference's
+        representation (parity tests)."""
+        Wl, Hl = int(self.width * 0.5 ** level), int(self.height * 0.5 ** level)
+        tiles = ((Wl + 15) // 16) * ((Hl + 15) // 16)
+        cap = max(1, sum(self.status().num_rendered))
+        keys = torch.empty((cap,), dtype=torch.int64, device=self.device)
+        ids = torch.empty((cap,), dtype=torch.int32, device=self.device)
+        ranges = torch.empty((tiles, 2), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            n = _lib.check(self._lib.gsevt_engine_binning(self.handle, int(view), keys.data_ptr(), ids.data_ptr(), ranges.data_ptr(),
+                                                          cap, self.stream.cuda_stream), "gsevt_engine_binning")
+        return (keys[:n].cpu().numpy().view(np.uint64), ids[:n].cpu().numpy().view(np.uint32), ranges.cpu().numpy().view(np.uint32))
 
     def profile(self, n_iters=5):
         """Mean device time (ms) of every stage of an iteration, measured with CUDA events on the engine

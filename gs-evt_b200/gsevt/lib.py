@@ -94,6 +94,7 @@ PROTOTYPES = {
     "gsevt_engine_begin_level": (C.c_int, [c_void_p, C.c_int32, C.c_int32, c_void_p]),
     "gsevt_engine_iterate": (C.c_int, [c_void_p, C.c_int32, c_void_p]),
     "gsevt_engine_poll_done": (C.c_int, [c_void_p]),
+    "gsevt_engine_resume": (C.c_int, [c_void_p, c_void_p]),
     "gsevt_engine_status": (C.c_int, [c_void_p, C.POINTER(GsevtEngineStatus), c_void_p]),
     "gsevt_engine_losses": (C.c_int, [c_void_p, c_float_p, C.c_int32, c_void_p]),
     "gsevt_engine_const_vel_model": (C.c_int, [c_void_p, C.c_double, c_void_p]),
@@ -101,6 +102,7 @@ PROTOTYPES = {
     "gsevt_engine_render_delta": (C.c_int, [c_void_p, C.c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gsevt_engine_eval": (C.c_int, [c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p, c_void_p]),
     "gsevt_engine_launches_per_iteration": (C.c_int, [c_void_p]),
+    "gsevt_engine_binning": (C.c_int, [c_void_p, C.c_int32, c_void_p, c_void_p, c_void_p, C.c_int32, c_void_p]),
     "gsevt_engine_stage_count": (C.c_int, []),
     "gsevt_engine_stage_name": (C.c_char_p, [C.c_int32]),
     "gsevt_engine_profile": (C.c_int, [c_void_p, C.c_int32, c_float_p, c_void_p]),

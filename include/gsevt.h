@@ -259,6 +259,12 @@ GSEVT_API int gsevt_engine_render_delta(GsevtEngine* e, int32_t level, float* de
 /* One gradient evaluation without optimiser step (parity tests): loss and the 12 pose gradients. */
 GSEVT_API int gsevt_engine_eval(GsevtEngine* e, int32_t level, int32_t signed_loss, float* loss_out, float* grads_out12,
                       void* stream);
+/* Parity access to the engine's binning of the most recent evaluation / iteration: the sorted instance list
+ * of `view` in the reference's representation — 64-bit keys (tile << 32 | depth bits), Gaussian ids, and the
+ * tile ranges into that list (rasterizer_impl.cu:70-138).  Device output pointers: keys_out[capacity],
+ * list_out[capacity], ranges_out[2 * tiles].  Returns the number of instances.  Synchronises. */
+GSEVT_API int gsevt_engine_binning(GsevtEngine* e, int32_t view, uint64_t* keys_out, uint32_t* list_out, uint32_t* ranges_out,
+                         int32_t capacity, void* stream);
 /* Profiling (bench.py's roofline leg): runs n_iters iterations OUTSIDE the CUDA graph with a CUDA
  * event between stages on `stream` and returns the mean device time of each stage in ms
  * (gsevt_engine_stage_count() entries, names from gsevt_engine_stage_name).  The iterations are real
@@ -272,8 +278,12 @@ GSEVT_API int gsevt_engine_profile(GsevtEngine* e, int32_t n_iters, float* stage
 GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream);
 /* Number of kernels the engine launches per executed iteration (for bench.py's gpu_launches). */
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e);
-/* Non-blocking: 1 once the device has flagged the current level as finished (read from mapped
- * pinned memory, no stream synchronisation). */
+/* After gsevt_engine_poll_done() returned 2: the tile-instance list outgrew the slots sorted per iteration
+ * (the pose moved a lot inside one level).  The device voided that iteration (state untouched) and paused the
+ * level; this call re-counts at the current pose, grows the buffers and clears the pause.  Synchronises. */
+GSEVT_API int gsevt_engine_resume(GsevtEngine* e, void* stream);
+/* Non-blocking: 1 once the device has flagged the current level as finished, 2 when it paused for
+ * gsevt_engine_resume (read from mapped pinned memory, no stream synchronisation). */
 GSEVT_API int gsevt_engine_poll_done(GsevtEngine* e);
 
 #ifdef __cplusplus

@@ -309,6 +309,11 @@ def test_engine_eval_matches_oracle(built, cuda_dev, level, signed):
     Lo, go, aux = orc.tracking_eval(*args)
     assert abs(L - Lo) < 1e-5 * abs(Lo)
     assert H.rel_max(gl, aux["gray"][0]) < TOL_IMG and H.rel_max(gn, aux["gray"][1]) < TOL_IMG
+    # the engine bins with a depth sort + 16-bit tile sort; the resulting lists must be the reference's, bit for bit
+    for view in (0, 1):
+        keys, ids, ranges = eng.binning(view, level)
+        fw = aux["fw"][view]
+        assert np.array_equal(keys, fw["keys"]) and np.array_equal(ids, fw["point_list"]) and np.array_equal(ranges, fw["ranges"])
     if signed:
         assert H.rel_max(g, go) < TOL_GRAD
     else:
@@ -372,6 +377,37 @@ def test_engine_optimisation_loop_control(built, cuda_dev):
     eng2, *_ = _engine(sc, cuda_dev, max_optim_iter=200, converged_threshold=1e9)
     st = eng2.run_level(2, opt_vel=False, chunk=4)
     assert st.start_vel_opt_iter == 10 and st.optim_iter == 11 and st.iters_executed == 12 and st.opt_vel == 1
+
+
+def test_engine_pauses_and_resumes_when_the_instance_list_outgrows_its_slots(built, cuda_dev):
+    """The per-iteration sort runs over a fixed number of slots (CUDA graph).  When the pose moves so far inside
+    a level that the live instances no longer fit, the device must void that iteration, pause, and continue after
+    gsevt_engine_resume with the same results as an engine that was sized for the pose from the start."""
+    sc = H.small_scene(20000, 320, 240, seed=4)
+    # reference run: sized at the real pose
+    eng, b, sign, unsign = _engine(sc, cuda_dev, converged_threshold=0.0, max_optim_iter=50)
+    eng.begin_level(0, True)
+    eng.iterate(4)
+    eng.stream.synchronize()
+    want_losses, want_state = eng.losses(), eng.get_state()
+    # second engine: level begun while looking away from the map (almost no instances), then moved to the real pose
+    eng2, b2, sign2, unsign2 = _engine(sc, cuda_dev, converged_threshold=0.0, max_optim_iter=50)
+    away = np.array([[-1, 0, 0], [0, 1, 0], [0, 0, -1]], np.float32) @ sc["R"]      # 180 deg about the camera y axis
+    eng2.set_state(away, sc["T"], sc["w"], sc["v"])
+    eng2.begin_level(0, True)
+    small = eng2.workload()["sorted_slots"]
+    eng2.set_state(sc["R"], sc["T"], sc["w"], sc["v"])
+    eng2.iterate(4)
+    eng2.stream.synchronize()
+    assert eng2.poll_done() == 2 and eng2.status().iters_executed == 0            # paused, nothing applied
+    assert all(np.array_equal(x, y) for x, y in zip(eng2.get_state(), (sc["R"], sc["T"], sc["w"], sc["v"])))
+    eng2.resume()
+    assert eng2.poll_done() == 0 and eng2.workload()["sorted_slots"] > small
+    eng2.iterate(4)
+    eng2.stream.synchronize()
+    got_losses, got_state = eng2.losses(), eng2.get_state()
+    assert np.abs(got_losses - want_losses).max() < 1e-5
+    assert all(np.abs(x - y).max() < 1e-5 for x, y in zip(got_state, want_state))
 
 
 def test_engine_iterations_match_reference_pipeline(built, cuda_dev, tmp_path):
