@@ -293,8 +293,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": round(ev_bytes * frames_run / args.steps, 1),
                     "d2h_bytes_per_step": round(status_bytes * frames_run / args.steps, 1),
                     "frames": frames_run, "note": "per frame: events pinned-host->device, GPU event frame, iterations, loss+pose read-back"},
-            "gpu_launches": 9 * args.steps,
-            "gpu_launches_note": "9 of our kernels per iteration (x steps); plus CUB scan (2) + radix sort (8) library kernels and 1 memset per iteration, all inside one CUDA graph",
+            "gpu_launches": eng.launches_per_iteration * args.steps,
+            "gpu_launches_note": "our own kernels per iteration (preprocess_map, emit_tiles, identify_ranges16, blend_fwd, loss_stats, "
+                                 "blend_bwd, geom_bwd, engine_update) x steps; plus CUB library kernels (two radix sorts, one scan) and "
+                                 "one memset per iteration, all inside one CUDA graph launch",
             "roofline": roof,
             "stages_ms": stage_table,
             "workload_counters": wl,

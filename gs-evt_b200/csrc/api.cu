@@ -496,9 +496,9 @@ static void projection_colmajor(double znear, double zfar, double fovX, double f
 // Enqueue one full optimisation iteration (or one evaluation) on stream s.  When `ev` is non-null an
 // event is recorded before every stage and after the last one (GSEVT_NSTAGES + 1 events): used by
 // gsevt_engine_profile for per-stage device times, never inside a captured graph.
-#define GSEVT_NSTAGES 12
+#define GSEVT_NSTAGES 11
 static const char* const kStageNames[GSEVT_NSTAGES] = {
-    "pose_setup", "preprocess_map", "depth_sort(cub)", "scan(cub)", "emit_tiles", "tile_sort(cub)", "identify_ranges",
+    "preprocess_map", "depth_sort(cub)", "scan(cub)", "emit_tiles", "tile_sort(cub)", "identify_ranges",
     "blend_fwd_gray", "loss_stats", "blend_bwd_gray", "geom_bwd_pose", "engine_update"};
 
 static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = nullptr) {
@@ -507,8 +507,8 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     const int P = m->P;
     int stage = 0;
     auto mark = [&]() { if (ev) cudaEventRecord(ev[stage], s); stage++; };
-    mark();
-    launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, s);
+    // the two ViewParams blocks are current on entry: written by the previous iteration's update kernel, or by
+    // the stand-alone pose kernel after any host-side change of state / level (probe_instances, set_state, ...)
     mark();
     PreMapArgs pa;
     pa.P = P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
@@ -554,7 +554,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     q.sh_planar = m->sh_planar; q.sh_aos = m->sh_aos; q.ctl = e->ctl; q.partials = e->geom_partials;
     launch_geom_bwd_map(q, s);
     mark();
-    launch_engine_update(e->ctl, e->geom_partials, e->geom_blocks, e->host_flag_dev, e->overflow, s);
+    launch_engine_update(e->ctl, e->geom_partials, e->geom_blocks, e->host_flag_dev, e->overflow, e->views, e->bg3, s);
     mark();
 }
 
@@ -718,6 +718,7 @@ GSEVT_API int gsevt_engine_set_state(GsevtEngine* e, const float* R, const float
     float h[18];
     memcpy(h, R, 36); memcpy(h + 9, T, 12); memcpy(h + 12, w, 12); memcpy(h + 15, v, 12);
     GSEVT_CUDA_OK(cudaMemcpyAsync(e->ctl, h, sizeof(h), cudaMemcpyHostToDevice, s));
+    launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, s);
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));  // h is a stack buffer
     return 0;
 }
@@ -882,6 +883,7 @@ GSEVT_API int gsevt_engine_losses(GsevtEngine* e, float* out, int32_t capacity, 
 GSEVT_API int gsevt_engine_const_vel_model(GsevtEngine* e, double tau, void* stream) {
     if (!e) { set_error("bad arguments"); return GSEVT_EINVAL; }
     launch_const_vel(e->ctl, (float)tau, (cudaStream_t)stream);
+    launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, (cudaStream_t)stream);
     GSEVT_CUDA_OK(cudaPeekAtLastError());
     return 0;
 }
@@ -893,6 +895,7 @@ GSEVT_API int gsevt_engine_weighted_velocity(GsevtEngine* e, const float* last_R
     memcpy(h, last_R, 36); memcpy(h + 9, last_T, 12);
     GSEVT_CUDA_OK(cudaMemcpyAsync(e->lastRT, h, sizeof(h), cudaMemcpyHostToDevice, s));
     launch_weighted_velocity(e->ctl, e->lastRT, (float)delta_tau, (float)weight, s);
+    launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, s);
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -1023,9 +1026,9 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
 
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e) {
     (void)e;
-    // pose_setup, preprocess, emit_tiles, identify_ranges, blend_fwd, loss_stats, blend_bwd, geom_bwd, update = 9 of
+    // preprocess, emit_tiles, identify_ranges, blend_fwd, loss_stats, blend_bwd, geom_bwd, update = 8 of
     // ours; plus CUB: two radix sorts (histogram + exclusive sum + one onesweep per 8-bit digit) and a scan, one memset.
-    return 9;
+    return 8;
 }
 
 }  // extern "C"

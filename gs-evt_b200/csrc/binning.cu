@@ -269,28 +269,36 @@ void launch_emit_tiles(int P, int grid_x, int tiles_per_view, const uint32_t* re
                                                            overflow, ctl);
 }
 
+// Eight keys per thread (one 16-byte load + the key before them).
 __global__ void __launch_bounds__(256) identify_ranges16_kernel(const uint16_t* __restrict__ keys, uint2* __restrict__ ranges,
                                                                 const uint32_t* __restrict__ n_dev, int cap) {
     const uint32_t L = min(*n_dev, (uint32_t)cap);
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L) return;
-    const uint32_t cur = keys[idx];
-    if (idx == 0)
-        ranges[cur].x = 0;
-    else {
-        const uint32_t prev = keys[idx - 1];
-        if (cur != prev) {
+    const uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) * 8u;
+    if (first >= L) return;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(keys + first));   // buffers are allocated in multiples of 256 B
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t prev = first == 0 ? 0xFFFFFFFFu : (uint32_t)__ldg(keys + first - 1);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t idx = first + k;
+        if (idx >= L) break;
+        const uint32_t cur = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+        if (idx == 0) {
+            ranges[cur].x = 0;
+        } else if (cur != prev) {
             ranges[prev].y = idx;
             ranges[cur].x = idx;
         }
+        if (idx == L - 1) ranges[cur].y = L;
+        prev = cur;
     }
-    if (idx == L - 1) ranges[cur].y = L;
 }
 void launch_identify_ranges16(const uint16_t* keys, uint2* ranges, int ntiles_total, const uint32_t* n_dev, int cap,
                               cudaStream_t s) {
     cudaMemsetAsync(ranges, 0, (size_t)ntiles_total * sizeof(uint2), s);
     if (cap <= 0) return;
-    identify_ranges16_kernel<<<(cap + 255) / 256, 256, 0, s>>>(keys, ranges, n_dev, cap);
+    const int threads = (cap + 7) / 8;
+    identify_ranges16_kernel<<<(threads + 255) / 256, 256, 0, s>>>(keys, ranges, n_dev, cap);
 }
 
 __global__ void iota_kernel(uint32_t* out, int n) {

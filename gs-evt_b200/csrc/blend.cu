@@ -51,11 +51,11 @@ __device__ __forceinline__ float eval_power(float dx, float dy, float A, float B
 template <int C, bool OPERATOR>
 __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     if (a.ctl && a.ctl->level_done) return;
-    __shared__ float4 s_r0[256];
-    __shared__ float4 s_r1[256];
-    __shared__ float4 s_cull[256];   // {x, y, half extent x, half extent y} of the alpha >= 1/255 ellipse's box
-    __shared__ float4 s_rgb[OPERATOR ? 256 : 1];
-    __shared__ int s_id[OPERATOR ? 256 : 1];
+    __shared__ float4 s_r0[2][256];
+    __shared__ float4 s_r1[2][256];
+    __shared__ float4 s_cull[2][256];   // {x, y, half extent x, half extent y} of the alpha >= 1/255 ellipse's box
+    __shared__ float4 s_rgb[OPERATOR ? 2 : 1][OPERATOR ? 256 : 1];
+    __shared__ int s_id[OPERATOR ? 2 : 1][OPERATOR ? 256 : 1];
 
     const int view = blockIdx.z;
     const int tiles = a.grid_x * a.grid_y;
@@ -80,24 +80,29 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     for (int ch = 0; ch < C; ch++) acc[ch] = 0.0f;
     float D = 0.0f;
 
-    for (int i = 0; i < rounds; i++) {
-        if (__syncthreads_count(done) == 256) break;
-        const int base = i * 256;
-        const int prog = base + threadIdx.x;
+    // double-buffered staging: ONE block barrier per round (it also counts the finished pixels)
+    auto stage = [&](int i, int buf) {
+        const int prog = i * 256 + threadIdx.x;
         if (prog < todo) {
             const uint32_t id = __ldg(a.point_list + range.x + prog);
             const float4 r0 = __ldg(rec + 2 * (size_t)id);
             const float4 r1 = __ldg(rec + 2 * (size_t)id + 1);
-            s_r0[threadIdx.x] = r0;
-            s_r1[threadIdx.x] = r1;
+            s_r0[buf][threadIdx.x] = r0;
+            s_r1[buf][threadIdx.x] = r1;
             const float2 ext = cull_extent(r0.z, r0.w, r1.x, r1.y);
-            s_cull[threadIdx.x] = make_float4(r0.x, r0.y, ext.x, ext.y);
+            s_cull[buf][threadIdx.x] = make_float4(r0.x, r0.y, ext.x, ext.y);
             if constexpr (OPERATOR) {
-                s_rgb[threadIdx.x] = __ldg(a.rgb4 + id);
-                s_id[threadIdx.x] = (int)id;
+                s_rgb[buf][threadIdx.x] = __ldg(a.rgb4 + id);
+                s_id[buf][threadIdx.x] = (int)id;
             }
         }
-        __syncthreads();
+    };
+    if (rounds > 0) stage(0, 0);
+    for (int i = 0; i < rounds; i++) {
+        const int buf = i & 1;
+        if (__syncthreads_count(done) == 256) break;
+        if (i + 1 < rounds) stage(i + 1, buf ^ 1);
+        const int base = i * 256;
         const int cnt = min(256, todo - base);
         // 32 staged instances at a time: lane l tests instance j0+l against this warp's 8x4 pixel block, the
         // ballot is the ordered hit list, and only hits are evaluated per pixel (list order is preserved).
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
             if (__all_sync(0xffffffffu, done)) break;
             bool hit = false;
             if (j0 + lane < cnt) {
-                const float4 c = s_cull[j0 + lane];
+                const float4 c = s_cull[buf][j0 + lane];
                 hit = fabsf(c.x - cxw) <= c.z && fabsf(c.y - cyw) <= c.w;
             }
             unsigned hits = __ballot_sync(0xffffffffu, hit);
@@ -113,9 +118,9 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
                 const int j = j0 + __ffs(hits) - 1;
                 hits &= hits - 1;
                 if (done) continue;
-                const float4 r0 = s_r0[j];
+                const float4 r0 = s_r0[buf][j];
                 const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
-                const float4 r1 = s_r1[j];
+                const float4 r1 = s_r1[buf][j];
                 const float power = eval_power(dx, dy, r0.z, r0.w, r1.x);
                 if (power > 0.0f) continue;
                 const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
@@ -126,12 +131,12 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
                     continue;
                 }
                 if constexpr (OPERATOR) {
-                    const float4 col = s_rgb[j];
+                    const float4 col = s_rgb[buf][j];
                     acc[0] = __fmaf_rn(T, __fmul_rn(alpha, col.x), acc[0]);
                     acc[1] = __fmaf_rn(T, __fmul_rn(alpha, col.y), acc[1]);
                     acc[2] = __fmaf_rn(T, __fmul_rn(alpha, col.z), acc[2]);
                     D = __fmaf_rn(T, __fmul_rn(alpha, r1.w), D);
-                    if (a.n_touched && test_T > 0.5f) atomicAdd(a.n_touched + s_id[j], 1);
+                    if (a.n_touched && test_T > 0.5f) atomicAdd(a.n_touched + s_id[buf][j], 1);
                 } else {
                     acc[0] = __fmaf_rn(T, __fmul_rn(alpha, r1.z), acc[0]);
                 }
@@ -170,11 +175,11 @@ void launch_blend_fwd_gray(const BlendFwdArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Backward
 // ------------------------------------------------------------------------------------------------
-// Values reduced per instance.  Engine: dmx dmy dA dB dC dgray (6).  Operator: dmx dmy dA dB dC dop
-// dc0 ddepth dc1 dc2 (10).  Row stride padded to an odd word count (bank-conflict-free flush).
+// Values reduced per instance.  Engine: dmx dmy dA dB dC dgray (6, padded to 8 for the reduction).
+// Operator: dmx dmy dA dB dC dop dc0 ddepth | dc1 dc2 (10, padded to 16).
 template <bool OPERATOR> struct BwdCfg;
-template <> struct BwdCfg<false> { static constexpr int K = 6, KR = 8, KP = 7, BATCH = 128; };
-template <> struct BwdCfg<true> { static constexpr int K = 10, KR = 16, KP = 11, BATCH = 64; };
+template <> struct BwdCfg<false> { static constexpr int K = 6, KR = 8, BATCH = 256; };
+template <> struct BwdCfg<true> { static constexpr int K = 10, KR = 16, BATCH = 256; };
 
 // Sum of each of N (power of two <= 32) per-lane values over the warp.  Returns, on every lane, the total of
 // component lane / (32 / N).  Halving exchange: at each step a lane keeps one half of its values and trades
@@ -200,17 +205,24 @@ __device__ __forceinline__ float warp_reduce_scatter(float (&v)[N], int lane) {
     return r;
 }
 
+// Back-to-front traversal.  Per staged batch (double-buffered: one block barrier per batch):
+//   * lane l tests instance j0+l against the warp's 8x4 pixel block and against the deepest position any of the
+//     warp's pixels blended; the ballot is the ordered hit list;
+//   * per hit: recompute alpha, rebuild T and the colour behind, per-lane gradient terms;
+//   * reduce-scatter over the warp and ONE red.add instruction per warp and hit: the lanes that own a component
+//     add it straight into the Gaussian's 32-byte accumulator record (same sector, one L2 request).
+// No shared-memory parking, no per-instance barrier; the reference has ~12 barriers and a 256-thread tree
+// reduction per Gaussian-tile instance (backward.cu:783-900).
 template <int C, bool OPERATOR>
 __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     if (a.ctl && a.ctl->level_done) return;
-    constexpr int K = BwdCfg<OPERATOR>::K, KR = BwdCfg<OPERATOR>::KR, KP = BwdCfg<OPERATOR>::KP, BATCH = BwdCfg<OPERATOR>::BATCH;
-    __shared__ float4 s_r0[BATCH];
-    __shared__ float4 s_r1[BATCH];
-    __shared__ float4 s_cull[BATCH];
-    __shared__ float4 s_rgb[OPERATOR ? BATCH : 1];
-    __shared__ uint32_t s_id[BATCH];
-    __shared__ uint32_t s_mask[BATCH];
-    __shared__ float s_acc[8 * BATCH * KP];
+    constexpr int K = BwdCfg<OPERATOR>::K, KR = BwdCfg<OPERATOR>::KR, BATCH = BwdCfg<OPERATOR>::BATCH;
+    static_assert(BATCH == 256, "one staged instance per thread");
+    __shared__ float4 s_r0[2][BATCH];
+    __shared__ float4 s_r1[2][BATCH];
+    __shared__ float4 s_cull[2][BATCH];
+    __shared__ float4 s_rgb[OPERATOR ? 2 : 1][OPERATOR ? BATCH : 1];
+    __shared__ uint32_t s_id[2][BATCH];
     __shared__ uint32_t s_max[8];
 
     const int view = blockIdx.z;
@@ -253,8 +265,8 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
         }
     }
 
-    // Deepest list position any pixel of this tile blended.
-    uint32_t wmax = __reduce_max_sync(0xffffffffu, last_contributor);
+    // Deepest list position any pixel of this warp / this tile blended.
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, last_contributor);
     if (lane == 0) s_max[warp] = wmax;
     __syncthreads();
     uint32_t max_lc = 0;
@@ -263,7 +275,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     if (max_lc == 0) return;
 
     const float4* __restrict__ rec = a.rec + 2 * (size_t)view * a.view_stride_gauss;
-    float4* __restrict__ grad8 = a.grad8 + 2 * (size_t)view * a.view_stride_gauss;
+    float* __restrict__ grad_f = reinterpret_cast<float*>(a.grad8 + 2 * (size_t)view * a.view_stride_gauss);
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
 
     float T = T_final;
@@ -272,123 +284,113 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     for (int ch = 0; ch < C; ch++) accum_rec[ch] = last_color[ch] = 0.0f;
     float accum_rec_depth = 0.0f, last_depth = 0.0f, last_alpha = 0.0f;
 
-    float* my_acc = s_acc + (size_t)warp * BATCH * KP;
-    const int nbatches = ((int)max_lc + BATCH - 1) / BATCH;
-    for (int b = 0; b < nbatches; b++) {
-        const int hi = (int)max_lc - 1 - b * BATCH;  // list position of batch entry 0
-        const int cnt = min(BATCH, hi + 1);
-        if (threadIdx.x < cnt) {
+    // which component this lane owns after the reduce-scatter, and whether it adds it to memory
+    constexpr int LPC = 32 / KR;                       // lanes per component
+    const int comp = lane / LPC;
+    const bool owner = (lane % LPC) == 0 && comp < K;
+
+    auto stage = [&](int b, int buf) {
+        const int hi = (int)max_lc - 1 - b * BATCH;    // list position of batch entry 0
+        if ((int)threadIdx.x <= hi) {
             const uint32_t id = __ldg(a.point_list + range.x + (uint32_t)(hi - (int)threadIdx.x));
             const float4 r0 = __ldg(rec + 2 * (size_t)id);
             const float4 r1 = __ldg(rec + 2 * (size_t)id + 1);
-            s_r0[threadIdx.x] = r0;
-            s_r1[threadIdx.x] = r1;
+            s_r0[buf][threadIdx.x] = r0;
+            s_r1[buf][threadIdx.x] = r1;
             const float2 ext = cull_extent(r0.z, r0.w, r1.x, r1.y);
-            s_cull[threadIdx.x] = make_float4(r0.x, r0.y, ext.x, ext.y);
-            s_id[threadIdx.x] = id;
-            s_mask[threadIdx.x] = 0u;
-            if constexpr (OPERATOR) s_rgb[threadIdx.x] = __ldg(a.rgb4 + id);
+            s_cull[buf][threadIdx.x] = make_float4(r0.x, r0.y, ext.x, ext.y);
+            s_id[buf][threadIdx.x] = id;
+            if constexpr (OPERATOR) s_rgb[buf][threadIdx.x] = __ldg(a.rgb4 + id);
         }
-        __syncthreads();
+    };
 
-        for (int j0 = 0; j0 < cnt; j0 += 32) {
+    const int nbatches = ((int)max_lc + BATCH - 1) / BATCH;
+    stage(0, 0);
+    for (int b = 0; b < nbatches; b++) {
+        const int buf = b & 1;
+        __syncthreads();                                   // batch b staged; everyone is done with buffer buf^1
+        if (b + 1 < nbatches) stage(b + 1, buf ^ 1);
+        const int hi = (int)max_lc - 1 - b * BATCH;
+        const int cnt = min(BATCH, hi + 1);
+        // entries of this batch with list position >= wmax cannot touch any pixel of this warp
+        const int jskip = max(0, hi + 1 - (int)wmax);      // first batch entry with pos < wmax
+        for (int j0 = jskip & ~31; j0 < cnt; j0 += 32) {
             bool hit = false;
-            if (j0 + lane < cnt) {
-                const float4 c = s_cull[j0 + lane];
+            const int jl = j0 + lane;
+            if (jl < cnt && jl >= jskip) {
+                const float4 c = s_cull[buf][jl];
                 hit = fabsf(c.x - cxw) <= c.z && fabsf(c.y - cyw) <= c.w;
             }
             unsigned hits = __ballot_sync(0xffffffffu, hit);
             while (hits) {
-            const int j = j0 + __ffs(hits) - 1;
-            hits &= hits - 1;
-            const float4 r0 = s_r0[j];
-            const uint32_t pos = (uint32_t)(hi - j);
-            const float4 r1 = s_r1[j];
-            const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
-            const float power = eval_power(dx, dy, r0.z, r0.w, r1.x);
-            const float G = expf(power);
-            const float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
-            const bool skip = !inside || pos >= last_contributor || power > 0.0f || alpha < kAlphaMin;
-            if (__all_sync(0xffffffffu, skip)) continue;
+                const int j = j0 + __ffs(hits) - 1;
+                hits &= hits - 1;
+                const float4 r0 = s_r0[buf][j];
+                const uint32_t pos = (uint32_t)(hi - j);
+                const float4 r1 = s_r1[buf][j];
+                const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
+                const float power = eval_power(dx, dy, r0.z, r0.w, r1.x);
+                const float G = expf(power);
+                const float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
+                const bool skip = pos >= last_contributor || power > 0.0f || alpha < kAlphaMin;   // !inside => last_contributor == 0
+                if (__all_sync(0xffffffffu, skip)) continue;
 
-            float v[KR];
+                float v[KR];
 #pragma unroll
-            for (int k = 0; k < KR; k++) v[k] = 0.0f;
-            if (!skip) {
-                T = T / (1.0f - alpha);
-                const float w = alpha * T;
-                float dL_dalpha = 0.0f;
-                if constexpr (OPERATOR) {
-                    const float4 col = s_rgb[j];
-                    const float c3[3] = {col.x, col.y, col.z};
+                for (int k = 0; k < KR; k++) v[k] = 0.0f;
+                if (!skip) {
+                    const float inv = __frcp_rn(1.0f - alpha);
+                    T = T * inv;
+                    const float w = alpha * T;
+                    float dL_dalpha = 0.0f;
+                    if constexpr (OPERATOR) {
+                        const float4 col = s_rgb[buf][j];
+                        const float c3[3] = {col.x, col.y, col.z};
 #pragma unroll
-                    for (int ch = 0; ch < C; ch++) {
-                        accum_rec[ch] = last_alpha * last_color[ch] + (1.0f - last_alpha) * accum_rec[ch];
-                        last_color[ch] = c3[ch];
-                        dL_dalpha += (c3[ch] - accum_rec[ch]) * dpix[ch];
+                        for (int ch = 0; ch < C; ch++) {
+                            accum_rec[ch] = last_alpha * last_color[ch] + (1.0f - last_alpha) * accum_rec[ch];
+                            last_color[ch] = c3[ch];
+                            dL_dalpha += (c3[ch] - accum_rec[ch]) * dpix[ch];
+                        }
+                        v[6] = w * dpix[0];
+                        v[8] = w * dpix[1];
+                        v[9] = w * dpix[2];
+                        accum_rec_depth = last_alpha * last_depth + (1.0f - last_alpha) * accum_rec_depth;
+                        last_depth = r1.w;
+                        dL_dalpha += (r1.w - accum_rec_depth) * dpix_depth;
+                        v[7] = w * dpix_depth;
+                    } else {
+                        accum_rec[0] = last_alpha * last_color[0] + (1.0f - last_alpha) * accum_rec[0];
+                        last_color[0] = r1.z;
+                        dL_dalpha += (r1.z - accum_rec[0]) * dpix[0];
+                        v[5] = w * dpix[0];
                     }
-                    v[6] = w * dpix[0];
-                    v[8] = w * dpix[1];
-                    v[9] = w * dpix[2];
-                    accum_rec_depth = last_alpha * last_depth + (1.0f - last_alpha) * accum_rec_depth;
-                    last_depth = r1.w;
-                    dL_dalpha += (r1.w - accum_rec_depth) * dpix_depth;
-                    v[7] = w * dpix_depth;
-                } else {
-                    accum_rec[0] = last_alpha * last_color[0] + (1.0f - last_alpha) * accum_rec[0];
-                    last_color[0] = r1.z;
-                    dL_dalpha += (r1.z - accum_rec[0]) * dpix[0];
-                    v[5] = w * dpix[0];
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final * inv) * bg_dot;
+                    const float dL_dG = r1.y * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
+                    const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+                    v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    v[1] = dL_dG * dG_ddely * ddely_dy;
+                    v[2] = -0.5f * gdx * dx * dL_dG;
+                    v[3] = -0.5f * gdx * dy * dL_dG;
+                    v[4] = -0.5f * gdy * dy * dL_dG;
+                    if constexpr (OPERATOR) v[5] = G * dL_dalpha;
                 }
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
-                const float dL_dG = r1.y * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-                const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -0.5f * gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                if constexpr (OPERATOR) v[5] = G * dL_dalpha;
-            }
-            // reduce-scatter over the warp: after log2(KR) halving exchanges each lane owns ONE component
-            // (index = lane / (32/KR)), finished with plain butterflies — 9 shuffles for 8 values instead of 40
-            const float mine = warp_reduce_scatter<KR>(v, lane);
-            if ((lane & (32 / KR - 1)) == 0 && lane / (32 / KR) < K) my_acc[j * KP + lane / (32 / KR)] = mine;
-            if (lane == 0) atomicOr(&s_mask[j], 1u << warp);
-            }
-        }
-        __syncthreads();
-
-        // flush: one thread per instance sums the warps that touched it and issues the global atomics
-        if (threadIdx.x < cnt) {
-            const uint32_t mask = s_mask[threadIdx.x];
-            if (mask) {
-                float sum[K];
-#pragma unroll
-                for (int k = 0; k < K; k++) sum[k] = 0.0f;
-                for (int w = 0; w < 8; w++) {
-                    if (mask & (1u << w)) {
-                        const float* row = s_acc + ((size_t)w * BATCH + threadIdx.x) * KP;
-#pragma unroll
-                        for (int k = 0; k < K; k++) sum[k] += row[k];
+                const float mine = warp_reduce_scatter<KR>(v, lane);
+                if (owner) {
+                    const uint32_t id = s_id[buf][j];
+                    if constexpr (OPERATOR) {
+                        float* dst = comp < 8 ? grad_f + 8 * (size_t)id + comp : reinterpret_cast<float*>(a.gradc + id) + (comp - 8);
+                        atomicAdd(dst, mine);
+                    } else {
+                        atomicAdd(grad_f + 8 * (size_t)id + comp, mine);
                     }
-                }
-                const uint32_t id = s_id[threadIdx.x];
-                float4* g = grad8 + 2 * (size_t)id;
-                atomicAdd(g, make_float4(sum[0], sum[1], sum[2], sum[3]));
-                if constexpr (OPERATOR) {
-                    atomicAdd(g + 1, make_float4(sum[4], sum[5], sum[6], sum[7]));
-                    atomicAdd(a.gradc + id, make_float2(sum[8], sum[9]));
-                } else {
-                    atomicAdd(reinterpret_cast<float2*>(g + 1), make_float2(sum[4], sum[5]));
                 }
             }
         }
-        __syncthreads();
     }
 }
 

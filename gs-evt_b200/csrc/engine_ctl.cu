@@ -100,8 +100,8 @@ __device__ void store_pose(EngineCtl* c, const SE3f& T) {
 
 }  // namespace
 
-__global__ void pose_setup_kernel(EngineCtl* ctl, ViewParams* views, const float* bg3) {
-    if (threadIdx.x != 0 || ctl->level_done) return;
+// Builds both ViewParams blocks from the current state (single thread).
+__device__ void pose_setup_device(EngineCtl* ctl, ViewParams* views, const float* bg3) {
     if (!ctl->eval_only) ctl->loss_signed = ctl->opt_vel;
     const float s = ctl->half_dtau;
     float rot[3], tr[3];
@@ -140,6 +140,14 @@ __global__ void pose_setup_kernel(EngineCtl* ctl, ViewParams* views, const float
         vp.pad_ = 0.0f;
     }
 }
+
+// Stand-alone form: run whenever the state or the level changed from the host (set_state, begin_level, eval,
+// resume, const_vel_model, weighted_velocity).  Inside the iteration loop the update kernel refreshes the views
+// itself, so an iteration has no separate pose launch.
+__global__ void pose_setup_kernel(EngineCtl* ctl, ViewParams* views, const float* bg3) {
+    if (threadIdx.x != 0) return;
+    pose_setup_device(ctl, views, bg3);
+}
 void launch_pose_setup(EngineCtl* ctl, ViewParams* views, const float* bg3, float, float, cudaStream_t s) {
     pose_setup_kernel<<<1, 32, 0, s>>>(ctl, views, bg3);
 }
@@ -169,7 +177,8 @@ __device__ void adam_group(EngineCtl* c, int group, const float* grad, double lr
 __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineCtl* ctl,
                                                                           const float* __restrict__ partials,
                                                                           int nblocks, int* host_flag,
-                                                                          const int* __restrict__ overflow) {
+                                                                          const int* __restrict__ overflow,
+                                                                          ViewParams* views, const float* bg3) {
     if (ctl->level_done) return;
     if (overflow && *overflow) {
         // The instance list outgrew the slots sorted this iteration: void the iteration (state untouched), pause
@@ -186,7 +195,7 @@ __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineC
     {
         const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
         double s = 0.0;
-        for (int b = lane; b < nblocks; b += 32) s += (double)partials[(size_t)b * GSEVT_NPART + k];
+        for (int b = lane; b < nblocks; b += 32) s += (double)partials[(size_t)k * nblocks + b];   // [12][nblocks]: coalesced
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) s_g[k] = (float)s;
@@ -262,11 +271,12 @@ __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineC
         __threadfence_system();
     } else {
         c->optim_iter += 1;
+        pose_setup_device(c, views, bg3);   // the next iteration's two views
     }
 }
 void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, const int* overflow,
-                          cudaStream_t s) {
-    engine_update_kernel<<<1, 32 * GSEVT_NPART, 0, s>>>(ctl, partials, nblocks, host_flag, overflow);
+                          ViewParams* views, const float* bg3, cudaStream_t s) {
+    engine_update_kernel<<<1, 32 * GSEVT_NPART, 0, s>>>(ctl, partials, nblocks, host_flag, overflow, views, bg3);
 }
 
 // ---- per-frame helpers ----------------------------------------------------------------------------

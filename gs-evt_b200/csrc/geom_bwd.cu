@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
         float s = 0.0f;
 #pragma unroll
         for (int w = 0; w < 8; w++) s += s_red[w][threadIdx.x];
-        a.partials[(size_t)blockIdx.x * GSEVT_NPART + threadIdx.x] = s;
+        a.partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;   // [12][nblocks]
     }
 }
 
@@ -392,12 +392,12 @@ void launch_geom_bwd_map(const GeomBwdArgs& a, cudaStream_t s) {
     geom_bwd_kernel<true><<<geom_bwd_blocks(a.P, a.nviews), 256, 0, s>>>(a);
 }
 
-// partials[nblocks][12] -> out12, fixed summation order, double accumulation.
+// partials[12][nblocks] -> out12, fixed summation order, double accumulation.
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nblocks, float* __restrict__ out12) {
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (k >= GSEVT_NPART) return;
     double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += (double)partials[(size_t)b * GSEVT_NPART + k];
+    for (int b = lane; b < nblocks; b += 32) s += (double)partials[(size_t)k * nblocks + b];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) out12[k] = (float)s;

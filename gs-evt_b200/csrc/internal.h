@@ -210,7 +210,7 @@ int loss_blocks(int HW);
 // ---- engine control kernels ----------------------------------------------------------------------
 void launch_pose_setup(EngineCtl* ctl, ViewParams* views, const float* bg3, float znear, float zfar, cudaStream_t s);
 void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, const int* overflow,
-                          cudaStream_t s);
+                          ViewParams* views, const float* bg3, cudaStream_t s);
 void launch_const_vel(EngineCtl* ctl, float tau, cudaStream_t s);
 void launch_weighted_velocity(EngineCtl* ctl, const float* lastRT, float delta_tau, float weight, cudaStream_t s);
 

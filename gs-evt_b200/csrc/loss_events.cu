@@ -147,7 +147,7 @@ void launch_event_frame(const int* counts, const int* map_ix, const int* map_iy,
 // ---- loss ----------------------------------------------------------------------------------------
 int loss_blocks(int HW) {
     int b = (HW + 1023) / 1024;
-    if (b > 128) b = 128;
+    if (b > 296) b = 296;   // two CTAs per SM
     if (b < 1) b = 1;
     return b;
 }
@@ -188,12 +188,20 @@ __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict
         s_last = atomicAdd(ticket, 1u) == (unsigned)(gridDim.x - 1);
     }
     __syncthreads();
-    if (!s_last || threadIdx.x != 0) return;
+    if (!s_last || threadIdx.x >= 32) return;
     __threadfence();
+    // last CTA: warp 0 sums the block partials in a fixed order (lane-strided, then a butterfly): deterministic
     double t0 = 0, t1 = 0, t2 = 0;
-    for (int b = 0; b < nblocks; b++) {  // fixed order: deterministic
+    for (int b = threadIdx.x; b < nblocks; b += 32) {
         t0 += partials[b * 3 + 0]; t1 += partials[b * 3 + 1]; t2 += partials[b * 3 + 2];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    if (threadIdx.x != 0) return;
     *ticket = 0u;
     const double n = sqrt(t0);
     double L2 = 1.0 - 2.0 * t1 / n + t2;
