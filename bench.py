@@ -317,16 +317,19 @@ def roofline(stages, wl, P, HW, clocks):
     Pg = wl["gaussians_with_grad"]
     slots = wl["sorted_slots"]
     bytes_alg = {
-        # map read once for both views (40 B) + SH for Gaussians visible in >= 1 view (192 B) + per-view records out
-        "preprocess_map": 40 * P + 192 * max(wl["visible"]) + 2 * P * 12 + Pv * (32 + 32 + 1),
-        # 2P (depth key, id) pairs: histogram read + 4 digit passes of (8 B in + 8 B out)
-        "depth_sort(cub)": 2 * P * (4 + 4 * 16),
+        # map read once for both views (40 B) + SH for Gaussians visible in >= 1 view (192 B); per pair: radius, depth key,
+        # {rect | id}; per visible pair: 32-B record, 32-B zeroed gradient accumulator, clamp byte
+        "preprocess_map": 40 * P + 192 * max(wl["visible"]) + 2 * P * 16 + Pv * (32 + 32 + 1),
+        # 2P (u32 depth key, u64 {rect | id}) pairs: histogram read + 4 digit passes of (12 B in + 12 B out)
+        "depth_sort(cub)": 2 * P * (4 + 4 * 24),
         "scan(cub)": 2 * P * 12,
-        "emit_tiles": 2 * P * 16 + Pv * 32 + slots * 6,
+        "emit_tiles": 2 * P * 12 + slots * 6,
         # (u16 tile key, u32 id) pairs: histogram read + 2 digit passes of (6 B in + 6 B out)
         "tile_sort(cub)": slots * 2 + 2 * 12 * slots,
         "identify_ranges": N * 2,
-        "geom_bwd_pose": 2 * P * 4 + Pv * 32 + Pg * (40 + 192 + 1),
+        # compaction scan (radius + 24 B of the accumulator per visible pair) + per active pair: list entry out/in,
+        # accumulator, xyz/opacity + covariance, SH (AoS copy), clamp byte
+        "geom_bwd_pose": 2 * P * 4 + Pv * 24 + Pg * (8 + 32 + 40 + 192 + 1),
         "loss_stats": 3 * 4 * HW,
     }
     flops_alg = {"blend_fwd_gray": 30.0 * S, "blend_bwd_gray": 100.0 * S}

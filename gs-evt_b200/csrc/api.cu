@@ -403,8 +403,11 @@ struct GsevtEngine {
     uint32_t* tiles = nullptr;
     uint32_t* offsets = nullptr;
     uint8_t* clamped = nullptr;
+    uint32_t* active_list = nullptr;   // [2P] compacted pairs with a gradient
+    uint32_t* active_count = nullptr;
     void* scan_temp = nullptr; size_t scan_bytes = 0;
-    uint32_t *depth_key = nullptr, *depth_sorted = nullptr, *iota = nullptr, *order = nullptr, *rect = nullptr;
+    uint32_t *depth_key = nullptr, *depth_sorted = nullptr;
+    uint64_t *pairs = nullptr, *pairs_sorted = nullptr;   // {tile rect | pair id}: projection order / depth order
     void* sortA_temp = nullptr; size_t sortA_bytes = 0;
     uint16_t *keys_u = nullptr, *keys = nullptr;
     uint32_t *vals_u = nullptr, *vals = nullptr;
@@ -513,16 +516,16 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     PreMapArgs pa;
     pa.P = P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
     pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
-    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.rect = e->rect;
+    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.pairs = e->pairs;
     pa.rec = e->rec; pa.grad8 = e->grad8;
     launch_preprocess_map(pa, s);
     mark();
-    launch_sort_pairs32(e->sortA_temp, e->sortA_bytes, e->depth_key, e->depth_sorted, e->iota, e->order, 2 * P, s);
+    launch_sort_pairs32(e->sortA_temp, e->sortA_bytes, e->depth_key, e->depth_sorted, e->pairs, e->pairs_sorted, 2 * P, s);
     mark();
-    launch_scan_gather(e->scan_temp, e->scan_bytes, e->rect, e->order, e->offsets, 2 * P, s);
+    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs_sorted, e->offsets, 2 * P, s);
     mark();
     const int tiles = L.gx * L.gy;
-    launch_emit_tiles(P, L.gx, tiles, e->rect, e->order, e->offsets, e->keys_u, e->vals_u, e->sort_n, e->overflow, e->ctl, s);
+    launch_emit_tiles(P, L.gx, tiles, e->pairs_sorted, e->offsets, e->keys_u, e->vals_u, e->sort_n, e->overflow, e->ctl, s);
     mark();
     const int bit = (int)higher_msb((uint32_t)(2 * tiles));
     launch_sort_pairs16(e->sort_temp, e->sort_bytes, e->keys_u, e->keys, e->vals_u, e->vals, e->sort_n, bit, s);
@@ -537,7 +540,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     launch_blend_fwd_gray(f, s);
     mark();
     const float* evf = e->ev_sign + L.ev_offset;
-    launch_loss_stats(e->gray, evf, L.W * L.H, e->ctl, e->loss_partials, e->loss_nb, s);
+    launch_loss_stats(e->gray, evf, L.W * L.H, e->ctl, e->loss_partials, e->loss_nb, e->active_count, s);
     mark();
     BlendBwdArgs b;
     memset(&b, 0, sizeof(b));
@@ -550,8 +553,9 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     GeomBwdArgs q;
     memset(&q, 0, sizeof(q));
     q.P = P; q.D = m->D; q.M = 16; q.nviews = 2; q.views = e->views; q.radii = e->radii; q.clamped = e->clamped;
-    q.grad8 = e->grad8; q.xyz_opacity = m->xyz_opacity; q.cov3D_a = m->cov_a; q.cov3D_b = m->cov_b;
+    q.grad8 = e->grad8; q.active_list = e->active_list; q.active_count = e->active_count; q.xyz_opacity = m->xyz_opacity; q.cov3D_a = m->cov_a; q.cov3D_b = m->cov_b;
     q.sh_planar = m->sh_planar; q.sh_aos = m->sh_aos; q.ctl = e->ctl; q.partials = e->geom_partials;
+    launch_geom_compact(2 * P, e->radii, e->grad8, e->active_list, e->active_count, e->ctl, s);
     launch_geom_bwd_map(q, s);
     mark();
     launch_engine_update(e->ctl, e->geom_partials, e->geom_blocks, e->host_flag_dev, e->overflow, e->views, e->bg3, s);
@@ -658,12 +662,13 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->tiles, p2);
     rc |= dev_alloc(e, &e->offsets, p2);
     rc |= dev_alloc(e, &e->clamped, p2);
+    rc |= dev_alloc(e, &e->active_list, p2);
+    rc |= dev_alloc(e, &e->active_count, 1);
     rc |= dev_alloc(e, (char**)&e->scan_temp, e->scan_bytes);
     rc |= dev_alloc(e, &e->depth_key, p2);
     rc |= dev_alloc(e, &e->depth_sorted, p2);
-    rc |= dev_alloc(e, &e->iota, p2);
-    rc |= dev_alloc(e, &e->order, p2);
-    rc |= dev_alloc(e, &e->rect, p2);
+    rc |= dev_alloc(e, &e->pairs, p2);
+    rc |= dev_alloc(e, &e->pairs_sorted, p2);
     rc |= dev_alloc(e, (char**)&e->sortA_temp, e->sortA_bytes);
     rc |= dev_alloc(e, &e->keys_u, (size_t)e->cap);
     rc |= dev_alloc(e, &e->keys, (size_t)e->cap);
@@ -697,7 +702,6 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     cudaMemset(e->loss_partials, 0, ((size_t)e->loss_nb * 3 + 2) * 8);
     cudaMemset(e->grad8, 0, 2 * p2 * 16);
     cudaMemset(e->radii, 0, p2 * 4);
-    launch_iota(e->iota, (int)p2, nullptr);
     cudaDeviceSynchronize();
     if (cudaGetLastError() != cudaSuccess) { set_error("engine init failed"); gsevt_engine_destroy(e); return GSEVT_ECUDA; }
     *out = e;
@@ -757,10 +761,10 @@ static int probe_instances(GsevtEngine* e, cudaStream_t s, uint32_t* total) {
     PreMapArgs pa;
     pa.P = m->P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
     pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
-    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.rect = e->rect;
+    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.pairs = e->pairs;
     pa.rec = e->rec; pa.grad8 = e->grad8;
     launch_preprocess_map(pa, s);
-    launch_scan_gather(e->scan_temp, e->scan_bytes, e->rect, nullptr, e->offsets, 2 * m->P, s);   // plain order: only the total matters here
+    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs, e->offsets, 2 * m->P, s);   // projection order: only the total matters here
     GSEVT_CUDA_OK(cudaMemcpyAsync(total, e->offsets + (2 * (size_t)m->P - 1), 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     return 0;
@@ -1026,9 +1030,9 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
 
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e) {
     (void)e;
-    // preprocess, emit_tiles, identify_ranges, blend_fwd, loss_stats, blend_bwd, geom_bwd, update = 8 of
+    // preprocess, emit_tiles, identify_ranges, blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, update = 9 of
     // ours; plus CUB: two radix sorts (histogram + exclusive sum + one onesweep per 8-bit digit) and a scan, one memset.
-    return 8;
+    return 9;
 }
 
 }  // extern "C"

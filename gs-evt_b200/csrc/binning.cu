@@ -183,7 +183,7 @@ void launch_build_view_params(ViewParams* out, const float* view, const float* p
 size_t sort32_temp_bytes(int n) {
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n > 0 ? n : 1);
+                                    (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n > 0 ? n : 1);
     return bytes;
 }
 size_t sort16_temp_bytes(int n) {
@@ -192,10 +192,13 @@ size_t sort16_temp_bytes(int n) {
                                     (const uint32_t*)nullptr, (uint32_t*)nullptr, n > 0 ? n : 1);
     return bytes;
 }
+// depth sort: key = depth bits, value = packed {tile rect (high 32) | pair id (low 32)} so that everything the
+// emission needs travels with the sort and is read back coalesced
 void launch_sort_pairs32(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
-                         const uint32_t* vals_in, uint32_t* vals_out, int n, cudaStream_t s) {
+                         const uint64_t* vals_in, uint64_t* vals_out, int n, cudaStream_t s) {
     if (n <= 0) return;
-    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 32, s);
+    cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, (const unsigned long long*)vals_in,
+                                    (unsigned long long*)vals_out, n, 0, 32, s);
 }
 void launch_sort_pairs16(void* temp, size_t temp_bytes, const uint16_t* keys_in, uint16_t* keys_out,
                          const uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit, cudaStream_t s) {
@@ -207,66 +210,90 @@ namespace {
 __host__ __device__ __forceinline__ uint32_t rect_area(uint32_t r) {
     return ((r >> 16 & 255u) - (r & 255u)) * ((r >> 24) - (r >> 8 & 255u));
 }
-struct GatherArea {
-    const uint32_t* rects;
-    const uint32_t* order;
-    __host__ __device__ __forceinline__ uint32_t operator()(int i) const { return rect_area(rects[order ? order[i] : (uint32_t)i]); }
+struct PairArea {
+    const uint64_t* pairs;
+    __host__ __device__ __forceinline__ uint32_t operator()(int i) const { return rect_area((uint32_t)(pairs[i] >> 32)); }
 };
 }  // namespace
 size_t scan_gather_temp_bytes(int n) {
     size_t bytes = 0;
-    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), GatherArea{nullptr, nullptr});
+    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), PairArea{nullptr});
     cub::DeviceScan::InclusiveSum(nullptr, bytes, it, (uint32_t*)nullptr, n > 0 ? n : 1);
     return bytes;
 }
-void launch_scan_gather(void* temp, size_t temp_bytes, const uint32_t* rects, const uint32_t* order, uint32_t* offsets, int n,
-                        cudaStream_t s) {
+// offsets[i] = inclusive sum of the tile-rect areas of pairs[0..i] (pairs in emission order)
+void launch_scan_gather(void* temp, size_t temp_bytes, const uint64_t* pairs, uint32_t* offsets, int n, cudaStream_t s) {
     if (n <= 0) return;
-    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), GatherArea{rects, order});
+    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), PairArea{pairs});
     cub::DeviceScan::InclusiveSum(temp, temp_bytes, it, offsets, n, s);
 }
 
-// One thread per sorted position: one dependent gather (the packed rect) and a run of (tile, id) stores.
-// Also fills the unused capacity [total, cap) with sentinel keys.
-__global__ void __launch_bounds__(256) emit_tiles_kernel(int P, int gx, int tiles_per_view, const uint32_t* __restrict__ rects,
-                                                         const uint32_t* __restrict__ order,
+// Tile-instance emission, output-centric.  A CTA takes 256 consecutive pairs of the depth-sorted list (coalesced
+// 8-byte loads, nothing gathered), whose instances occupy ONE contiguous output range; its threads then walk that
+// range with unit stride — each output slot finds its pair by binary search over the 256 offsets in shared memory
+// — so the (tile, id) stores are fully coalesced and the work is balanced whatever the rect sizes are.
+// (The reference emits one serial, divergent loop per Gaussian: rasterizer_impl.cu:85-109.)
+// Threads past the pair list fill the unused capacity [total, cap) with sentinel keys.
+__global__ void __launch_bounds__(256) emit_tiles_kernel(int P, int gx, int tiles_per_view, const uint64_t* __restrict__ pairs,
                                                          const uint32_t* __restrict__ offsets, uint16_t* __restrict__ keys,
                                                          uint32_t* __restrict__ values, int cap, int* __restrict__ overflow,
                                                          const EngineCtl* __restrict__ ctl) {
     if (ctl && ctl->level_done) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_off[257];     // exclusive offsets of the CTA's pairs, [256] = end
+    __shared__ uint32_t s_rect[256];
+    __shared__ uint32_t s_gid[256];
+    __shared__ float s_rcpw[256];
     const int n = 2 * P;
+    const int i = blockIdx.x * 256 + threadIdx.x;
     const uint32_t total = offsets[n - 1];
     if (i == 0 && total > (uint32_t)cap) *overflow = 1;
     if (i < cap && (uint32_t)i >= total) {
         keys[i] = 0xFFFFu;
         values[i] = 0u;
     }
-    if (i >= n) return;
-    const uint32_t gid = order[i];
-    const uint32_t r = __ldg(rects + gid);
-    if (r == 0u) return;
-    const int x0 = r & 255u, y0 = r >> 8 & 255u, x1 = r >> 16 & 255u, y1 = r >> 24;
-    const int v = gid >= (uint32_t)P ? 1 : 0;
-    uint32_t off = i == 0 ? 0u : offsets[i - 1];
-    const uint32_t tile_base = (uint32_t)(v * tiles_per_view);
-    const uint32_t idx = gid - (uint32_t)v * (uint32_t)P;
-    for (int y = y0; y < y1; y++) {
-        for (int x = x0; x < x1; x++) {
-            if (off >= (uint32_t)cap) return;
-            keys[off] = (uint16_t)(tile_base + (uint32_t)(y * gx + x));
-            values[off] = idx;
-            off++;
+    if (blockIdx.x * 256 >= n) return;
+    uint32_t rect = 0, gid = 0, incl = total;
+    if (i < n) {
+        const uint64_t pr = pairs[i];
+        rect = (uint32_t)(pr >> 32);
+        gid = (uint32_t)pr;
+        incl = offsets[i];
+    }
+    const uint32_t area = rect_area(rect);
+    s_off[threadIdx.x] = incl - area;
+    s_rect[threadIdx.x] = rect;
+    s_gid[threadIdx.x] = gid;
+    const uint32_t w = (rect >> 16 & 255u) - (rect & 255u);
+    s_rcpw[threadIdx.x] = w ? 1.0f / (float)w : 0.0f;
+    if (threadIdx.x == 255) s_off[256] = incl;
+    __syncthreads();
+    const uint32_t begin = s_off[0];
+    const uint32_t end = min(s_off[256], (uint32_t)cap);
+    for (uint32_t o = begin + threadIdx.x; o < end; o += 256) {
+        // last pair g with s_off[g] <= o (zero-area pairs share their successor's offset and are skipped by this)
+        int lo = 0, hi = 255;
+#pragma unroll
+        for (int step = 0; step < 8; step++) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_off[mid] <= o) lo = mid; else hi = mid - 1;
         }
+        const uint32_t r = s_rect[lo];
+        const uint32_t g = s_gid[lo];
+        const uint32_t t = o - s_off[lo];
+        const uint32_t x0 = r & 255u, y0 = r >> 8 & 255u, wd = (r >> 16 & 255u) - x0;
+        const uint32_t ty = (uint32_t)(((float)t + 0.5f) * s_rcpw[lo]);   // exact: t < 65536, wd <= 255
+        const uint32_t tx = t - ty * wd;
+        const uint32_t v = g >= (uint32_t)P ? 1u : 0u;
+        keys[o] = (uint16_t)(v * (uint32_t)tiles_per_view + (y0 + ty) * (uint32_t)gx + x0 + tx);
+        values[o] = g - v * (uint32_t)P;
     }
 }
-void launch_emit_tiles(int P, int grid_x, int tiles_per_view, const uint32_t* rects, const uint32_t* order,
-                       const uint32_t* offsets, uint16_t* keys, uint32_t* values, int cap, int* overflow,
-                       const EngineCtl* ctl, cudaStream_t s) {
+void launch_emit_tiles(int P, int grid_x, int tiles_per_view, const uint64_t* pairs, const uint32_t* offsets, uint16_t* keys,
+                       uint32_t* values, int cap, int* overflow, const EngineCtl* ctl, cudaStream_t s) {
     const int threads = 2 * P > cap ? 2 * P : cap;
     if (threads <= 0) return;
-    emit_tiles_kernel<<<(threads + 255) / 256, 256, 0, s>>>(P, grid_x, tiles_per_view, rects, order, offsets, keys, values, cap,
-                                                           overflow, ctl);
+    emit_tiles_kernel<<<(threads + 255) / 256, 256, 0, s>>>(P, grid_x, tiles_per_view, pairs, offsets, keys, values, cap, overflow,
+                                                           ctl);
 }
 
 // Eight keys per thread (one 16-byte load + the key before them).
@@ -299,14 +326,6 @@ void launch_identify_ranges16(const uint16_t* keys, uint2* ranges, int ntiles_to
     if (cap <= 0) return;
     const int threads = (cap + 7) / 8;
     identify_ranges16_kernel<<<(threads + 255) / 256, 256, 0, s>>>(keys, ranges, n_dev, cap);
-}
-
-__global__ void iota_kernel(uint32_t* out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (uint32_t)i;
-}
-void launch_iota(uint32_t* out, int n, cudaStream_t s) {
-    if (n > 0) iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(out, n);
 }
 
 // Parity-test helper: rebuild the reference's 64-bit keys of one view from the engine's sorted lists.

@@ -79,17 +79,23 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
 #pragma unroll
     for (int k = 0; k < GSEVT_NPART; k++) acc[k] = 0.0f;
 
-    for (long long chunk = (long long)blockIdx.x * GEOM_CHUNK; chunk < n; chunk += (long long)gridDim.x * GEOM_CHUNK) {
+    // ENGINE: the work list was compacted by geom_compact_kernel (only a few per cent of the pairs carry a
+    // gradient); a chunk is a slice of that list.  OPERATOR: every visible Gaussian is active (per-Gaussian outputs),
+    // compacted per chunk of consecutive ids in shared memory.
+    const long long n_work = ENGINE ? (long long)*a.active_count : n;
+    constexpr int CH = ENGINE ? 256 : GEOM_CHUNK;   // engine: one dense item per thread, spread over many CTAs
+    for (long long chunk = (long long)blockIdx.x * CH; chunk < n_work; chunk += (long long)gridDim.x * CH) {
+        if constexpr (ENGINE) {
+            const int cnt = (int)min((long long)CH, n_work - chunk);
+            for (int i = threadIdx.x; i < cnt; i += 256) s_list[i] = a.active_list[chunk + i];
+            if (threadIdx.x == 0) s_count = cnt;
+            __syncthreads();
+        } else {
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();
         for (int k = 0; k < GEOM_CHUNK / 256; k++) {
             const long long gid = chunk + k * 256 + threadIdx.x;
-            bool active = gid < n && a.radii[gid] > 0;
-            if (ENGINE && active) {
-                const float4 g0 = __ldg(a.grad8 + 2 * gid);
-                const float2 g1 = __ldg(reinterpret_cast<const float2*>(a.grad8 + 2 * gid + 1));
-                active = g0.x != 0.f || g0.y != 0.f || g0.z != 0.f || g0.w != 0.f || g1.x != 0.f || g1.y != 0.f;
-            }
+            const bool active = gid < n && a.radii[gid] > 0;
             const unsigned bal = __ballot_sync(0xffffffffu, active);
             if (lane_id == 0) s_wcount[warp_id] = __popc(bal);
             __syncthreads();
@@ -104,9 +110,10 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
             }
             __syncthreads();
         }
+        }
         const int count = s_count;
     for (int li = threadIdx.x; li < count; li += 256) {
-        const long long gid = chunk + s_list[li];
+        const long long gid = ENGINE ? (long long)s_list[li] : chunk + s_list[li];
         const float4 g0 = __ldg(a.grad8 + 2 * gid);
         const float4 g1 = __ldg(a.grad8 + 2 * gid + 1);
         const int view = (int)(gid / P);
@@ -390,6 +397,37 @@ void launch_geom_bwd_aos(const GeomBwdArgs& a, cudaStream_t s) {
 }
 void launch_geom_bwd_map(const GeomBwdArgs& a, cudaStream_t s) {
     geom_bwd_kernel<true><<<geom_bwd_blocks(a.P, a.nviews), 256, 0, s>>>(a);
+}
+
+// Streaming compaction at full occupancy: list of (view, Gaussian) pairs with a non-zero blend gradient.
+// One warp-aggregated atomic per warp that found something.
+__global__ void __launch_bounds__(256) geom_compact_kernel(int n, const int* __restrict__ radii, const float4* __restrict__ grad8,
+                                                           uint32_t* __restrict__ list, uint32_t* __restrict__ count,
+                                                           const EngineCtl* __restrict__ ctl) {
+    if (ctl && ctl->level_done) return;
+    const int lane = threadIdx.x & 31;
+    for (int gid = blockIdx.x * 256 + threadIdx.x; gid - lane < n; gid += gridDim.x * 256) {
+        bool active = gid < n && radii[gid] > 0;
+        if (active) {
+            const float4 g0 = __ldg(grad8 + 2 * (size_t)gid);
+            const float2 g1 = __ldg(reinterpret_cast<const float2*>(grad8 + 2 * (size_t)gid + 1));
+            active = g0.x != 0.f || g0.y != 0.f || g0.z != 0.f || g0.w != 0.f || g1.x != 0.f || g1.y != 0.f;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, active);
+        if (bal) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (active) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)gid;
+        }
+    }
+}
+void launch_geom_compact(int n_pairs, const int* radii, const float4* grad8, uint32_t* list, uint32_t* count, const EngineCtl* ctl,
+                         cudaStream_t s) {
+    if (n_pairs <= 0) return;
+    int blocks = (n_pairs + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    geom_compact_kernel<<<blocks, 256, 0, s>>>(n_pairs, radii, grad8, list, count, ctl);
 }
 
 // partials[12][nblocks] -> out12, fixed summation order, double accumulation.

@@ -79,7 +79,7 @@ struct PreMapArgs {
     uint32_t* tiles_touched;  // [2P]
     uint8_t* clamped;         // [2P]
     uint32_t* depth_key;      // [2P] float bits of the view depth, 0xFFFFFFFF when culled
-    uint32_t* rect;           // [2P] packed tile rect (x0 | y0<<8 | x1<<16 | y1<<24), 0 when culled
+    uint64_t* pairs;          // [2P] {packed tile rect x0 | y0<<8 | x1<<16 | y1<<24 (0 when culled)} << 32 | pair id
     float4* rec;              // [2][2P]
     float4* grad8;            // [2][2P]
 };
@@ -113,18 +113,15 @@ size_t sort32_temp_bytes(int n);
 size_t sort16_temp_bytes(int n);
 size_t scan_gather_temp_bytes(int n);
 void launch_sort_pairs32(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
-                         const uint32_t* vals_in, uint32_t* vals_out, int n, cudaStream_t s);
+                         const uint64_t* vals_in, uint64_t* vals_out, int n, cudaStream_t s);
 void launch_sort_pairs16(void* temp, size_t temp_bytes, const uint16_t* keys_in, uint16_t* keys_out,
                          const uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit, cudaStream_t s);
-// offsets = inclusive sum of the tile-rect areas, visited in `order` (identity when order == NULL)
-void launch_scan_gather(void* temp, size_t temp_bytes, const uint32_t* rects, const uint32_t* order, uint32_t* offsets, int n,
-                        cudaStream_t s);
-void launch_emit_tiles(int P, int grid_x, int tiles_per_view, const uint32_t* rects, const uint32_t* order,
-                       const uint32_t* offsets, uint16_t* keys, uint32_t* values, int cap, int* overflow,
-                       const EngineCtl* ctl, cudaStream_t s);
+// offsets = inclusive sum of the tile-rect areas of `pairs` ({rect (high 32) | pair id (low 32)}), in array order
+void launch_scan_gather(void* temp, size_t temp_bytes, const uint64_t* pairs, uint32_t* offsets, int n, cudaStream_t s);
+void launch_emit_tiles(int P, int grid_x, int tiles_per_view, const uint64_t* pairs, const uint32_t* offsets, uint16_t* keys,
+                       uint32_t* values, int cap, int* overflow, const EngineCtl* ctl, cudaStream_t s);
 void launch_identify_ranges16(const uint16_t* keys, uint2* ranges, int ntiles_total, const uint32_t* n_dev, int cap,
                               cudaStream_t s);
-void launch_iota(uint32_t* out, int n, cudaStream_t s);
 void launch_rebuild_keys(const uint16_t* tile_keys, const uint32_t* vals, const float4* rec_view, uint32_t tile_base,
                          uint32_t first, uint32_t count, uint64_t* keys_out, uint32_t* list_out, cudaStream_t s);
 
@@ -185,6 +182,8 @@ struct GeomBwdArgs {
     const int* radii;            // [nviews][P]
     const uint8_t* clamped;      // [nviews][P]
     const float4* grad8;         // [nviews][2P]
+    const uint32_t* active_list; // engine: compacted ids of the (view, Gaussian) pairs that carry a gradient
+    uint32_t* active_count;      // engine: their number (device); the compaction kernel fills both
     const float2* gradc;         // operator only
     // map (AoS operator / packed engine)
     const float* means3D; const float* shs; const float* cov3D;            // operator
@@ -200,11 +199,14 @@ struct GeomBwdArgs {
 int geom_bwd_blocks(int P, int nviews);
 void launch_geom_bwd_aos(const GeomBwdArgs& a, cudaStream_t s);
 void launch_geom_bwd_map(const GeomBwdArgs& a, cudaStream_t s);
+// engine: list of pairs with radius > 0 and a non-zero blend gradient (count must be zero on entry)
+void launch_geom_compact(int n_pairs, const int* radii, const float4* grad8, uint32_t* list, uint32_t* count, const EngineCtl* ctl,
+                         cudaStream_t s);
 void launch_reduce_partials(const float* partials, int nblocks, float* out12, cudaStream_t s);
 
 // ---- loss (engine) -----------------------------------------------------------------------------
 void launch_loss_stats(const float* gray, const float* event_frame, int HW, EngineCtl* ctl, double* partials,
-                       int nblocks, cudaStream_t s);
+                       int nblocks, uint32_t* zero_me, cudaStream_t s);
 int loss_blocks(int HW);
 
 // ---- engine control kernels ----------------------------------------------------------------------

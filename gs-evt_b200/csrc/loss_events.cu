@@ -155,7 +155,8 @@ int loss_blocks(int HW) {
 // partials: [nblocks][3] doubles followed by one unsigned ticket counter (zero on entry, reset on exit).
 __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict__ gray, const float* __restrict__ ev,
                                                          int HW, EngineCtl* __restrict__ ctl,
-                                                         double* __restrict__ partials, int nblocks) {
+                                                         double* __restrict__ partials, int nblocks,
+                                                         uint32_t* __restrict__ zero_me) {
     if (ctl->level_done) return;
     __shared__ double s_w[8][3];
     __shared__ bool s_last;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict
         t2 += __shfl_xor_sync(0xffffffffu, t2, o);
     }
     if (threadIdx.x != 0) return;
+    if (zero_me) *zero_me = 0u;   // per-iteration counter of the backward's work list (consumed two kernels later)
     *ticket = 0u;
     const double n = sqrt(t0);
     double L2 = 1.0 - 2.0 * t1 / n + t2;
@@ -219,8 +221,8 @@ __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict
 }
 
 void launch_loss_stats(const float* gray, const float* event_frame, int HW, EngineCtl* ctl, double* partials,
-                       int nblocks, cudaStream_t s) {
-    loss_stats_kernel<<<nblocks, 256, 0, s>>>(gray, event_frame, HW, ctl, partials, nblocks);
+                       int nblocks, uint32_t* zero_me, cudaStream_t s) {
+    loss_stats_kernel<<<nblocks, 256, 0, s>>>(gray, event_frame, HW, ctl, partials, nblocks, zero_me);
 }
 
 // ---- workload counters (bench / profiling only) ---------------------------------------------------

@@ -134,7 +134,8 @@ void launch_preprocess_aos(const PreAosArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Engine path: packed map, two views per thread.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) preprocess_map_kernel(PreMapArgs a) {
+template <int D>
+__global__ void __launch_bounds__(256, 3) preprocess_map_kernel(PreMapArgs a) {
     if (a.ctl && a.ctl->level_done) return;
     __shared__ ViewParams s_vp[2];
     load_views(s_vp, a.views, 2);
@@ -156,27 +157,28 @@ __global__ void __launch_bounds__(256) preprocess_map_kernel(PreMapArgs a) {
         const size_t j = (size_t)v * a.P + idx;
         a.radii[j] = ok[v] ? o[v].radius : 0;
         a.depth_key[j] = ok[v] ? __float_as_uint(o[v].depth) : 0xFFFFFFFFu;
-        a.rect[j] = ok[v] ? o[v].rect : 0u;
+        a.pairs[j] = ((uint64_t)(ok[v] ? o[v].rect : 0u) << 32) | (uint64_t)j;
     }
     if (!ok[0] && !ok[1]) return;
-    // SH -> RGB for both views from ONE pass over the 48 planar coefficients (coalesced 128-byte lines)
+    // SH -> RGB for both views from ONE pass over the planar coefficients (coalesced 128-byte lines).  The degree
+    // is a template parameter so that all (D+1)^2 * 3 loads are issued back to back, unconditionally.
     const float* sh = a.sh_planar + idx;
     const size_t P = (size_t)a.P;
+    constexpr int NB = (D + 1) * (D + 1);
+    float coef[NB * 3];
+#pragma unroll
+    for (int k = 0; k < NB * 3; k++) coef[k] = __ldg(sh + (size_t)k * P);
     float basis[2][16];
 #pragma unroll
     for (int v = 0; v < 2; v++)
-        sh_basis(a.D, xo.x - s_vp[v].campos[0], xo.y - s_vp[v].campos[1], xo.z - s_vp[v].campos[2], basis[v]);
+        sh_basis(D, xo.x - s_vp[v].campos[0], xo.y - s_vp[v].campos[1], xo.z - s_vp[v].campos[2], basis[v]);
     float rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-    const int nb = (a.D + 1) * (a.D + 1);
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        if (k < nb) {
+    for (int k = 0; k < NB; k++) {
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                const float c = __ldg(sh + (size_t)(k * 3 + ch) * P);
-                rgb[0][ch] += basis[0][k] * c;
-                rgb[1][ch] += basis[1][k] * c;
-            }
+        for (int ch = 0; ch < 3; ch++) {
+            rgb[0][ch] += basis[0][k] * coef[k * 3 + ch];
+            rgb[1][ch] += basis[1][k] * coef[k * 3 + ch];
         }
     }
 #pragma unroll
@@ -202,7 +204,13 @@ __global__ void __launch_bounds__(256) preprocess_map_kernel(PreMapArgs a) {
 
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
-    preprocess_map_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a);
+    const int blocks = (a.P + 255) / 256;
+    switch (a.D) {
+        case 0: preprocess_map_kernel<0><<<blocks, 256, 0, s>>>(a); break;
+        case 1: preprocess_map_kernel<1><<<blocks, 256, 0, s>>>(a); break;
+        case 2: preprocess_map_kernel<2><<<blocks, 256, 0, s>>>(a); break;
+        default: preprocess_map_kernel<3><<<blocks, 256, 0, s>>>(a); break;
+    }
 }
 
 // checkFrustum (rasterizer_impl.cu:54-66)
