@@ -413,6 +413,7 @@ struct GsevtEngine {
     uint32_t *vals_u = nullptr, *vals = nullptr;
     void* sort_temp = nullptr; size_t sort_bytes = 0;
     uint2* ranges = nullptr;
+    uint32_t* hitmask = nullptr; size_t hitmask_stride = 0;   // forward -> backward: what each warp blended
     float* gray = nullptr; float* final_T = nullptr; uint32_t* n_contrib = nullptr;
     double* loss_partials = nullptr;
     float* geom_partials = nullptr;
@@ -457,6 +458,12 @@ static long long slots_for(long long total) {
     return (want + 4095) / 4096 * 4096;
 }
 
+// Words per warp row of the hit-mask table: word (range.x >> 5) + tile index + group, see blend.cu.
+static size_t hitmask_stride_for(const GsevtEngine* e, long long cap) {
+    const LevelInfo& L0 = e->lv[0];
+    return (size_t)(cap / 32 + 2 * (long long)L0.gx * L0.gy + 64);
+}
+
 // Grows the instance buffers (never inside a captured graph).
 static int ensure_capacity(GsevtEngine* e, long long slots) {
     if (slots <= e->cap) return 0;
@@ -466,10 +473,13 @@ static int ensure_capacity(GsevtEngine* e, long long slots) {
     cudaDeviceSynchronize();
     if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
     dev_free(e, e->keys_u); dev_free(e, e->keys); dev_free(e, e->vals_u); dev_free(e, e->vals); dev_free(e, e->sort_temp);
-    e->keys_u = e->keys = nullptr; e->vals_u = e->vals = nullptr; e->sort_temp = nullptr;
+    dev_free(e, e->hitmask);
+    e->keys_u = e->keys = nullptr; e->vals_u = e->vals = nullptr; e->sort_temp = nullptr; e->hitmask = nullptr;
     e->cap = (int)cap;
     e->sort_bytes = sort16_temp_bytes(e->cap);
+    e->hitmask_stride = hitmask_stride_for(e, e->cap);
     int rc = 0;
+    rc |= dev_alloc(e, &e->hitmask, 8 * e->hitmask_stride);
     rc |= dev_alloc(e, &e->keys_u, (size_t)e->cap);
     rc |= dev_alloc(e, &e->keys, (size_t)e->cap);
     rc |= dev_alloc(e, &e->vals_u, (size_t)e->cap);
@@ -537,6 +547,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     f.W = L.W; f.H = L.H; f.grid_x = L.gx; f.grid_y = L.gy; f.nviews = 2;
     f.ranges = e->ranges; f.point_list = e->vals; f.rec = e->rec; f.view_stride_gauss = (size_t)P;
     f.views = e->views; f.final_T = e->final_T; f.n_contrib = e->n_contrib; f.out_color = e->gray; f.ctl = e->ctl;
+    f.hitmask = e->hitmask; f.hitmask_stride = e->hitmask_stride;
     launch_blend_fwd_gray(f, s);
     mark();
     const float* evf = e->ev_sign + L.ev_offset;
@@ -547,7 +558,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     b.W = L.W; b.H = L.H; b.grid_x = L.gx; b.grid_y = L.gy; b.nviews = 2;
     b.ranges = e->ranges; b.point_list = e->vals; b.rec = e->rec; b.view_stride_gauss = (size_t)P; b.views = e->views;
     b.final_T = e->final_T; b.n_contrib = e->n_contrib; b.gray = e->gray; b.event_frame = evf; b.ctl = e->ctl;
-    b.grad8 = e->grad8;
+    b.grad8 = e->grad8; b.hitmask = e->hitmask; b.hitmask_stride = e->hitmask_stride;
     launch_blend_bwd_gray(b, s);
     mark();
     GeomBwdArgs q;
@@ -676,6 +687,8 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
     rc |= dev_alloc(e, (char**)&e->sort_temp, e->sort_bytes);
     rc |= dev_alloc(e, &e->ranges, 2 * (size_t)L0.gx * L0.gy);
+    e->hitmask_stride = hitmask_stride_for(e, e->cap);
+    rc |= dev_alloc(e, &e->hitmask, 8 * e->hitmask_stride);
     rc |= dev_alloc(e, &e->gray, 2 * hw);
     rc |= dev_alloc(e, &e->final_T, 2 * hw);
     rc |= dev_alloc(e, &e->n_contrib, 2 * hw);

@@ -2,17 +2,24 @@
 //
 // Forward restates renderCUDA (dgr/cuda_rasterizer/forward.cu:263-392); backward restates renderCUDA
 // (dgr/cuda_rasterizer/backward.cu:679-903).  One CTA = one 16x16 tile, one thread = one pixel, the
-// tile's depth-sorted instance list is staged through shared memory in batches.
+// tile's depth-sorted instance list is staged through shared memory in batches of 256 (double-buffered:
+// one block barrier per batch).
 //
 // What is different from the reference (results identical):
-//  * each warp owns a compact 8x4 pixel block and skips an instance with one warp-uniform bounding-box
-//    test against the ellipse {alpha >= 1/255} (computed once per instance by the thread that stages it);
-//  * one 32-byte record per Gaussian {x, y, A, B | C, opacity, gray, depth} = one DRAM/L2 sector per
-//    gather instead of three separate arrays; colours ride along (RGB in a second 16-byte record);
-//  * backward starts at the last instance any pixel of the tile actually blended (max n_contrib) instead
-//    of the end of the list, reduces each instance's gradient with warp shuffles, parks per-warp partial
-//    sums in shared memory and issues one vector atomic per instance per batch — no block barrier inside
-//    the per-instance loop (the reference has ~12);
+//  * each warp owns a compact 8x4 pixel block.  32 staged instances at a time, lane l tests instance j0+l
+//    against the block — first the bounding box of the ellipse {alpha >= 1/255}, then (engine forward) the
+//    exact minimum of the quadratic form over the block's rectangle — and the ballot is the ordered hit
+//    list: only hits are evaluated per pixel, list order is preserved;
+//  * one 32-byte record per Gaussian {x, y, A, B | C, opacity, gray, depth} = one sector per gather
+//    instead of three separate arrays (RGB rides in a second 16-byte record on the operator path);
+//  * engine: the forward records, per warp and per group of 32 list positions, which instances some pixel
+//    of the warp actually blended; the backward walks exactly those bits (an instance contributes to the
+//    backward of a warp iff it contributed to its forward), so it runs no culling test at all;
+//  * backward starts at the deepest list position any pixel of the tile blended (max n_contrib), reduces
+//    each instance's per-lane terms with a reduce-scatter over the warp (9 shuffles for 8 values) and
+//    issues ONE red.add instruction per warp and instance straight into the Gaussian's 32-byte
+//    accumulator record — no shared-memory parking, no barrier inside the per-instance loop (the
+//    reference has ~12 barriers and a 256-thread tree reduction per Gaussian-tile instance);
 //  * the engine variant renders one grayscale channel for BOTH views in one launch (blockIdx.z = view)
 //    and its backward derives dL/dpixel on the fly from the normalised event loss (frame.py:86-92,
 //    tracker.py:93-103) instead of reading upstream gradient images.
@@ -26,15 +33,37 @@ namespace {
 
 constexpr float kAlphaMin = 1.0f / 255.0f;
 
+// Conservative bound on the quadratic form: alpha >= 1/255  =>  A dx^2 + 2B dx dy + C dy^2 <= tau.
+__device__ __forceinline__ float cull_tau(float o) { return 2.0f * __logf(255.0f * o) * 1.01f + 0.05f; }
+
 // Half extents (plus the warp block's own half size) of the bounding box of {Q(d) <= tau}; +inf when the
 // conic is degenerate, -1 when the instance can never reach alpha >= 1/255.
-__device__ __forceinline__ float2 cull_extent(float A, float B, float C, float o) {
-    const float tau = 2.0f * __logf(255.0f * o) * 1.01f + 0.05f;  // conservative
+__device__ __forceinline__ float2 cull_extent(float A, float B, float C, float tau) {
     const float det = A * C - B * B;
     if (!(tau > 0.0f)) return make_float2(-1.0f, -1.0f);
     if (!(det > 0.0f) || !(A > 0.0f) || !(C > 0.0f)) return make_float2(3.0e38f, 3.0e38f);
     const float inv = tau / det;
     return make_float2(sqrtf(inv * C) * 1.001f + 3.5f + 0.05f, sqrtf(inv * A) * 1.001f + 1.5f + 0.05f);
+}
+
+// Exact test: does the ellipse {Q(d) <= tau} centred at (x, y) meet the pixel rectangle [bx, bx+7] x [by, by+3]?
+// Q is convex, so its minimum over the rectangle is 0 when the centre is inside, else it lies on an edge.
+__device__ __forceinline__ bool ellipse_hits_block(float x, float y, float A, float B, float C, float tau, float bx, float by) {
+    if (!(A > 0.0f) || !(C > 0.0f)) return true;   // degenerate conic: keep (the bounding-box stage already said "hit")
+    const float x0 = bx - x, x1 = bx + 7.0f - x, y0 = by - y, y1 = by + 3.0f - y;
+    if (x0 <= 0.0f && x1 >= 0.0f && y0 <= 0.0f && y1 >= 0.0f) return true;
+    const float rA = 1.0f / A, rC = 1.0f / C;
+    float qmin = 3.0e38f;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const float xe = e ? x1 : x0;                                   // vertical edge dx = xe
+        const float ys = fminf(fmaxf(-B * xe * rC, y0), y1);
+        qmin = fminf(qmin, A * xe * xe + (2.0f * B * xe + C * ys) * ys);
+        const float ye = e ? y1 : y0;                                   // horizontal edge dy = ye
+        const float xs = fminf(fmaxf(-B * ye * rA, x0), x1);
+        qmin = fminf(qmin, C * ye * ye + (2.0f * B * ye + A * xs) * xs);
+    }
+    return qmin <= tau;
 }
 
 // alpha and its ingredients in the reference's rounding order (forward.cu:342-353).
@@ -54,13 +83,15 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     __shared__ float4 s_r0[2][256];
     __shared__ float4 s_r1[2][256];
     __shared__ float4 s_cull[2][256];   // {x, y, half extent x, half extent y} of the alpha >= 1/255 ellipse's box
+    __shared__ float s_tau[OPERATOR ? 1 : 2][OPERATOR ? 1 : 256];
     __shared__ float4 s_rgb[OPERATOR ? 2 : 1][OPERATOR ? 256 : 1];
     __shared__ int s_id[OPERATOR ? 2 : 1][OPERATOR ? 256 : 1];
 
     const int view = blockIdx.z;
     const int tiles = a.grid_x * a.grid_y;
     const int HW = a.W * a.H;
-    const uint2 range = a.ranges[view * tiles + blockIdx.y * a.grid_x + blockIdx.x];
+    const int tile_lin = view * tiles + blockIdx.y * a.grid_x + blockIdx.x;
+    const uint2 range = a.ranges[tile_lin];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bx = blockIdx.x * GSEVT_TILE + (warp & 1) * 8, by = blockIdx.y * GSEVT_TILE + (warp >> 1) * 4;
     const int pixx = bx + (lane & 7), pixy = by + (lane >> 3);
@@ -72,6 +103,10 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     const float4* __restrict__ rec = a.rec + 2 * (size_t)view * a.view_stride_gauss;
     const int todo = (int)(range.y - range.x);
     const int rounds = (todo + 255) / 256;
+    // engine: this warp's row of the hit-mask table; word (range.x >> 5) + tile_lin + g holds list positions
+    // [32 g, 32 g + 32) of this tile (rows of consecutive tiles cannot overlap: floor(len/32) + 1 >= ceil(len/32))
+    uint32_t* __restrict__ hitrow =
+        OPERATOR || !a.hitmask ? nullptr : a.hitmask + (size_t)warp * a.hitmask_stride + (range.x >> 5) + (uint32_t)tile_lin;
 
     float T = 1.0f;
     uint32_t last_contributor = 0;
@@ -89,11 +124,14 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
             const float4 r1 = __ldg(rec + 2 * (size_t)id + 1);
             s_r0[buf][threadIdx.x] = r0;
             s_r1[buf][threadIdx.x] = r1;
-            const float2 ext = cull_extent(r0.z, r0.w, r1.x, r1.y);
+            const float tau = cull_tau(r1.y);
+            const float2 ext = cull_extent(r0.z, r0.w, r1.x, tau);
             s_cull[buf][threadIdx.x] = make_float4(r0.x, r0.y, ext.x, ext.y);
             if constexpr (OPERATOR) {
                 s_rgb[buf][threadIdx.x] = __ldg(a.rgb4 + id);
                 s_id[buf][threadIdx.x] = (int)id;
+            } else {
+                s_tau[buf][threadIdx.x] = tau;
             }
         }
     };
@@ -104,44 +142,61 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
         if (i + 1 < rounds) stage(i + 1, buf ^ 1);
         const int base = i * 256;
         const int cnt = min(256, todo - base);
-        // 32 staged instances at a time: lane l tests instance j0+l against this warp's 8x4 pixel block, the
-        // ballot is the ordered hit list, and only hits are evaluated per pixel (list order is preserved).
         for (int j0 = 0; j0 < cnt; j0 += 32) {
             if (__all_sync(0xffffffffu, done)) break;
             bool hit = false;
             if (j0 + lane < cnt) {
                 const float4 c = s_cull[buf][j0 + lane];
                 hit = fabsf(c.x - cxw) <= c.z && fabsf(c.y - cyw) <= c.w;
+                if constexpr (!OPERATOR) {
+                    if (hit) {
+                        const float4 q0 = s_r0[buf][j0 + lane];
+                        hit = ellipse_hits_block(c.x, c.y, q0.z, q0.w, s_r1[buf][j0 + lane].x, s_tau[buf][j0 + lane], (float)bx, (float)by);
+                    }
+                }
             }
             unsigned hits = __ballot_sync(0xffffffffu, hit);
+            uint32_t blended = 0;   // engine: bit b set <=> some pixel of this warp blended instance j0 + b
             while (hits) {
-                const int j = j0 + __ffs(hits) - 1;
+                const int b = __ffs(hits) - 1;
+                const int j = j0 + b;
                 hits &= hits - 1;
-                if (done) continue;
-                const float4 r0 = s_r0[buf][j];
-                const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
-                const float4 r1 = s_r1[buf][j];
-                const float power = eval_power(dx, dy, r0.z, r0.w, r1.x);
-                if (power > 0.0f) continue;
-                const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
-                if (alpha < kAlphaMin) continue;
-                const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
-                if (test_T < 0.0001f) {
-                    done = true;
-                    continue;
+                bool contributed = false;
+                if (!done) {
+                    const float4 r0 = s_r0[buf][j];
+                    const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
+                    const float4 r1 = s_r1[buf][j];
+                    const float power = eval_power(dx, dy, r0.z, r0.w, r1.x);
+                    if (!(power > 0.0f)) {
+                        const float alpha = fminf(0.99f, __fmul_rn(r1.y, expf(power)));
+                        if (!(alpha < kAlphaMin)) {
+                            const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
+                            if (test_T < 0.0001f) {
+                                done = true;
+                            } else {
+                                if constexpr (OPERATOR) {
+                                    const float4 col = s_rgb[buf][j];
+                                    acc[0] = __fmaf_rn(T, __fmul_rn(alpha, col.x), acc[0]);
+                                    acc[1] = __fmaf_rn(T, __fmul_rn(alpha, col.y), acc[1]);
+                                    acc[2] = __fmaf_rn(T, __fmul_rn(alpha, col.z), acc[2]);
+                                    D = __fmaf_rn(T, __fmul_rn(alpha, r1.w), D);
+                                    if (a.n_touched && test_T > 0.5f) atomicAdd(a.n_touched + s_id[buf][j], 1);
+                                } else {
+                                    acc[0] = __fmaf_rn(T, __fmul_rn(alpha, r1.z), acc[0]);
+                                }
+                                T = test_T;
+                                last_contributor = (uint32_t)(base + j + 1);
+                                contributed = true;
+                            }
+                        }
+                    }
                 }
-                if constexpr (OPERATOR) {
-                    const float4 col = s_rgb[buf][j];
-                    acc[0] = __fmaf_rn(T, __fmul_rn(alpha, col.x), acc[0]);
-                    acc[1] = __fmaf_rn(T, __fmul_rn(alpha, col.y), acc[1]);
-                    acc[2] = __fmaf_rn(T, __fmul_rn(alpha, col.z), acc[2]);
-                    D = __fmaf_rn(T, __fmul_rn(alpha, r1.w), D);
-                    if (a.n_touched && test_T > 0.5f) atomicAdd(a.n_touched + s_id[buf][j], 1);
-                } else {
-                    acc[0] = __fmaf_rn(T, __fmul_rn(alpha, r1.z), acc[0]);
+                if constexpr (!OPERATOR) {
+                    if (__any_sync(0xffffffffu, contributed)) blended |= 1u << b;
                 }
-                T = test_T;
-                last_contributor = (uint32_t)(base + j + 1);
+            }
+            if constexpr (!OPERATOR) {
+                if (hitrow && lane == 0) hitrow[(base + j0) >> 5] = blended;
             }
         }
     }
@@ -178,8 +233,8 @@ void launch_blend_fwd_gray(const BlendFwdArgs& a, cudaStream_t s) {
 // Values reduced per instance.  Engine: dmx dmy dA dB dC dgray (6, padded to 8 for the reduction).
 // Operator: dmx dmy dA dB dC dop dc0 ddepth | dc1 dc2 (10, padded to 16).
 template <bool OPERATOR> struct BwdCfg;
-template <> struct BwdCfg<false> { static constexpr int K = 6, KR = 8, BATCH = 256; };
-template <> struct BwdCfg<true> { static constexpr int K = 10, KR = 16, BATCH = 256; };
+template <> struct BwdCfg<false> { static constexpr int K = 6, KR = 8; };
+template <> struct BwdCfg<true> { static constexpr int K = 10, KR = 16; };
 
 // Sum of each of N (power of two <= 32) per-lane values over the warp.  Returns, on every lane, the total of
 // component lane / (32 / N).  Halving exchange: at each step a lane keeps one half of its values and trades
@@ -205,30 +260,22 @@ __device__ __forceinline__ float warp_reduce_scatter(float (&v)[N], int lane) {
     return r;
 }
 
-// Back-to-front traversal.  Per staged batch (double-buffered: one block barrier per batch):
-//   * lane l tests instance j0+l against the warp's 8x4 pixel block and against the deepest position any of the
-//     warp's pixels blended; the ballot is the ordered hit list;
-//   * per hit: recompute alpha, rebuild T and the colour behind, per-lane gradient terms;
-//   * reduce-scatter over the warp and ONE red.add instruction per warp and hit: the lanes that own a component
-//     add it straight into the Gaussian's 32-byte accumulator record (same sector, one L2 request).
-// No shared-memory parking, no per-instance barrier; the reference has ~12 barriers and a 256-thread tree
-// reduction per Gaussian-tile instance (backward.cu:783-900).
 template <int C, bool OPERATOR>
 __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     if (a.ctl && a.ctl->level_done) return;
-    constexpr int K = BwdCfg<OPERATOR>::K, KR = BwdCfg<OPERATOR>::KR, BATCH = BwdCfg<OPERATOR>::BATCH;
-    static_assert(BATCH == 256, "one staged instance per thread");
-    __shared__ float4 s_r0[2][BATCH];
-    __shared__ float4 s_r1[2][BATCH];
-    __shared__ float4 s_cull[2][BATCH];
-    __shared__ float4 s_rgb[OPERATOR ? 2 : 1][OPERATOR ? BATCH : 1];
-    __shared__ uint32_t s_id[2][BATCH];
+    constexpr int K = BwdCfg<OPERATOR>::K, KR = BwdCfg<OPERATOR>::KR;
+    __shared__ float4 s_r0[2][256];
+    __shared__ float4 s_r1[2][256];
+    __shared__ float4 s_cull[OPERATOR ? 2 : 1][OPERATOR ? 256 : 1];
+    __shared__ float4 s_rgb[OPERATOR ? 2 : 1][OPERATOR ? 256 : 1];
+    __shared__ uint32_t s_id[2][256];
     __shared__ uint32_t s_max[8];
 
     const int view = blockIdx.z;
     const int tiles = a.grid_x * a.grid_y;
     const int HW = a.W * a.H;
-    const uint2 range = a.ranges[view * tiles + blockIdx.y * a.grid_x + blockIdx.x];
+    const int tile_lin = view * tiles + blockIdx.y * a.grid_x + blockIdx.x;
+    const uint2 range = a.ranges[tile_lin];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bx = blockIdx.x * GSEVT_TILE + (warp & 1) * 8, by = blockIdx.y * GSEVT_TILE + (warp >> 1) * 4;
     const int pixx = bx + (lane & 7), pixy = by + (lane >> 3);
@@ -277,6 +324,8 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     const float4* __restrict__ rec = a.rec + 2 * (size_t)view * a.view_stride_gauss;
     float* __restrict__ grad_f = reinterpret_cast<float*>(a.grad8 + 2 * (size_t)view * a.view_stride_gauss);
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+    const uint32_t* __restrict__ hitrow =
+        OPERATOR ? nullptr : a.hitmask + (size_t)warp * a.hitmask_stride + (range.x >> 5) + (uint32_t)tile_lin;
 
     float T = T_final;
     float accum_rec[C], last_color[C];
@@ -289,105 +338,132 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     const int comp = lane / LPC;
     const bool owner = (lane % LPC) == 0 && comp < K;
 
+    // Batches are aligned to 256 list positions (so the forward's 32-position mask words never straddle one):
+    // batch b holds positions [top - 256 b - 255, top - 256 b]; staged entry t <-> position hi - t.
+    const int top = (int)((max_lc - 1) | 255u);
+    const int len = (int)(range.y - range.x);
     auto stage = [&](int b, int buf) {
-        const int hi = (int)max_lc - 1 - b * BATCH;    // list position of batch entry 0
-        if ((int)threadIdx.x <= hi) {
-            const uint32_t id = __ldg(a.point_list + range.x + (uint32_t)(hi - (int)threadIdx.x));
+        const int pos = top - b * 256 - (int)threadIdx.x;
+        if (pos < len) {   // pos >= 0 always: top - 256 b - 255 >= 0 for b < nbatches
+            const uint32_t id = __ldg(a.point_list + range.x + (uint32_t)pos);
             const float4 r0 = __ldg(rec + 2 * (size_t)id);
             const float4 r1 = __ldg(rec + 2 * (size_t)id + 1);
             s_r0[buf][threadIdx.x] = r0;
             s_r1[buf][threadIdx.x] = r1;
-            const float2 ext = cull_extent(r0.z, r0.w, r1.x, r1.y);
-            s_cull[buf][threadIdx.x] = make_float4(r0.x, r0.y, ext.x, ext.y);
             s_id[buf][threadIdx.x] = id;
-            if constexpr (OPERATOR) s_rgb[buf][threadIdx.x] = __ldg(a.rgb4 + id);
+            if constexpr (OPERATOR) {
+                const float2 ext = cull_extent(r0.z, r0.w, r1.x, cull_tau(r1.y));
+                s_cull[buf][threadIdx.x] = make_float4(r0.x, r0.y, ext.x, ext.y);
+                s_rgb[buf][threadIdx.x] = __ldg(a.rgb4 + id);
+            }
         }
     };
 
-    const int nbatches = ((int)max_lc + BATCH - 1) / BATCH;
+    // one instance, all pixels of the warp: recompute alpha, rebuild T and the colour behind, reduce, add
+    auto process = [&](int buf, int j, uint32_t pos) {
+        const float4 r0 = s_r0[buf][j];
+        const float4 r1 = s_r1[buf][j];
+        const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
+        const float power = eval_power(dx, dy, r0.z, r0.w, r1.x);
+        const float G = expf(power);
+        const float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
+        const bool skip = pos >= last_contributor || power > 0.0f || alpha < kAlphaMin;   // !inside => last_contributor == 0
+        if constexpr (OPERATOR) {
+            if (__all_sync(0xffffffffu, skip)) return;
+        }
+        float v[KR];
+#pragma unroll
+        for (int k = 0; k < KR; k++) v[k] = 0.0f;
+        if (!skip) {
+            const float inv = __frcp_rn(1.0f - alpha);
+            T = T * inv;
+            const float w = alpha * T;
+            float dL_dalpha = 0.0f;
+            if constexpr (OPERATOR) {
+                const float4 col = s_rgb[buf][j];
+                const float c3[3] = {col.x, col.y, col.z};
+#pragma unroll
+                for (int ch = 0; ch < C; ch++) {
+                    accum_rec[ch] = last_alpha * last_color[ch] + (1.0f - last_alpha) * accum_rec[ch];
+                    last_color[ch] = c3[ch];
+                    dL_dalpha += (c3[ch] - accum_rec[ch]) * dpix[ch];
+                }
+                v[6] = w * dpix[0];
+                v[8] = w * dpix[1];
+                v[9] = w * dpix[2];
+                accum_rec_depth = last_alpha * last_depth + (1.0f - last_alpha) * accum_rec_depth;
+                last_depth = r1.w;
+                dL_dalpha += (r1.w - accum_rec_depth) * dpix_depth;
+                v[7] = w * dpix_depth;
+            } else {
+                accum_rec[0] = last_alpha * last_color[0] + (1.0f - last_alpha) * accum_rec[0];
+                last_color[0] = r1.z;
+                dL_dalpha += (r1.z - accum_rec[0]) * dpix[0];
+                v[5] = w * dpix[0];
+            }
+            dL_dalpha *= T;
+            last_alpha = alpha;
+            dL_dalpha += (-T_final * inv) * bg_dot;
+            const float dL_dG = r1.y * dL_dalpha;
+            const float gdx = G * dx, gdy = G * dy;
+            const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
+            const float dG_ddely = -gdy * r1.x - gdx * r0.w;
+            v[0] = dL_dG * dG_ddelx * ddelx_dx;
+            v[1] = dL_dG * dG_ddely * ddely_dy;
+            v[2] = -0.5f * gdx * dx * dL_dG;
+            v[3] = -0.5f * gdx * dy * dL_dG;
+            v[4] = -0.5f * gdy * dy * dL_dG;
+            if constexpr (OPERATOR) v[5] = G * dL_dalpha;
+        }
+        const float mine = warp_reduce_scatter<KR>(v, lane);
+        if (owner) {
+            const uint32_t id = s_id[buf][j];
+            if constexpr (OPERATOR) {
+                float* dst = comp < 8 ? grad_f + 8 * (size_t)id + comp : reinterpret_cast<float*>(a.gradc + id) + (comp - 8);
+                atomicAdd(dst, mine);
+            } else {
+                atomicAdd(grad_f + 8 * (size_t)id + comp, mine);
+            }
+        }
+    };
+
+    const int nbatches = (top + 1) / 256;
     stage(0, 0);
     for (int b = 0; b < nbatches; b++) {
         const int buf = b & 1;
         __syncthreads();                                   // batch b staged; everyone is done with buffer buf^1
         if (b + 1 < nbatches) stage(b + 1, buf ^ 1);
-        const int hi = (int)max_lc - 1 - b * BATCH;
-        const int cnt = min(BATCH, hi + 1);
-        // entries of this batch with list position >= wmax cannot touch any pixel of this warp
-        const int jskip = max(0, hi + 1 - (int)wmax);      // first batch entry with pos < wmax
-        for (int j0 = jskip & ~31; j0 < cnt; j0 += 32) {
-            bool hit = false;
-            const int jl = j0 + lane;
-            if (jl < cnt && jl >= jskip) {
-                const float4 c = s_cull[buf][jl];
-                hit = fabsf(c.x - cxw) <= c.z && fabsf(c.y - cyw) <= c.w;
-            }
-            unsigned hits = __ballot_sync(0xffffffffu, hit);
-            while (hits) {
-                const int j = j0 + __ffs(hits) - 1;
-                hits &= hits - 1;
-                const float4 r0 = s_r0[buf][j];
-                const uint32_t pos = (uint32_t)(hi - j);
-                const float4 r1 = s_r1[buf][j];
-                const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
-                const float power = eval_power(dx, dy, r0.z, r0.w, r1.x);
-                const float G = expf(power);
-                const float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
-                const bool skip = pos >= last_contributor || power > 0.0f || alpha < kAlphaMin;   // !inside => last_contributor == 0
-                if (__all_sync(0xffffffffu, skip)) continue;
-
-                float v[KR];
-#pragma unroll
-                for (int k = 0; k < KR; k++) v[k] = 0.0f;
-                if (!skip) {
-                    const float inv = __frcp_rn(1.0f - alpha);
-                    T = T * inv;
-                    const float w = alpha * T;
-                    float dL_dalpha = 0.0f;
-                    if constexpr (OPERATOR) {
-                        const float4 col = s_rgb[buf][j];
-                        const float c3[3] = {col.x, col.y, col.z};
-#pragma unroll
-                        for (int ch = 0; ch < C; ch++) {
-                            accum_rec[ch] = last_alpha * last_color[ch] + (1.0f - last_alpha) * accum_rec[ch];
-                            last_color[ch] = c3[ch];
-                            dL_dalpha += (c3[ch] - accum_rec[ch]) * dpix[ch];
-                        }
-                        v[6] = w * dpix[0];
-                        v[8] = w * dpix[1];
-                        v[9] = w * dpix[2];
-                        accum_rec_depth = last_alpha * last_depth + (1.0f - last_alpha) * accum_rec_depth;
-                        last_depth = r1.w;
-                        dL_dalpha += (r1.w - accum_rec_depth) * dpix_depth;
-                        v[7] = w * dpix_depth;
-                    } else {
-                        accum_rec[0] = last_alpha * last_color[0] + (1.0f - last_alpha) * accum_rec[0];
-                        last_color[0] = r1.z;
-                        dL_dalpha += (r1.z - accum_rec[0]) * dpix[0];
-                        v[5] = w * dpix[0];
-                    }
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final * inv) * bg_dot;
-                    const float dL_dG = r1.y * dL_dalpha;
-                    const float gdx = G * dx, gdy = G * dy;
-                    const float dG_ddelx = -gdx * r0.z - gdy * r0.w;
-                    const float dG_ddely = -gdy * r1.x - gdx * r0.w;
-                    v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                    v[1] = dL_dG * dG_ddely * ddely_dy;
-                    v[2] = -0.5f * gdx * dx * dL_dG;
-                    v[3] = -0.5f * gdx * dy * dL_dG;
-                    v[4] = -0.5f * gdy * dy * dL_dG;
-                    if constexpr (OPERATOR) v[5] = G * dL_dalpha;
+        const int hi = top - b * 256;                      // list position of staged entry 0
+        if ((uint32_t)(hi - 255) >= wmax) continue;        // nothing of this batch can touch this warp's pixels
+        if constexpr (OPERATOR) {
+            const int jskip = max(0, hi + 1 - (int)wmax);  // first staged entry with position < wmax
+            for (int j0 = jskip & ~31; j0 < 256; j0 += 32) {
+                bool hit = false;
+                const int jl = j0 + lane;
+                if (jl >= jskip && hi - jl < len) {
+                    const float4 c = s_cull[buf][jl];
+                    hit = fabsf(c.x - cxw) <= c.z && fabsf(c.y - cyw) <= c.w;
                 }
-                const float mine = warp_reduce_scatter<KR>(v, lane);
-                if (owner) {
-                    const uint32_t id = s_id[buf][j];
-                    if constexpr (OPERATOR) {
-                        float* dst = comp < 8 ? grad_f + 8 * (size_t)id + comp : reinterpret_cast<float*>(a.gradc + id) + (comp - 8);
-                        atomicAdd(dst, mine);
-                    } else {
-                        atomicAdd(grad_f + 8 * (size_t)id + comp, mine);
-                    }
+                unsigned hits = __ballot_sync(0xffffffffu, hit);
+                while (hits) {
+                    const int j = j0 + __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    process(buf, j, (uint32_t)(hi - j));
+                }
+            }
+        } else {
+            // the forward's record of what this warp blended: 8 words cover this batch's 256 positions
+            const uint32_t g0 = (uint32_t)(hi - 255) >> 5;
+            const uint32_t gmax = (wmax - 1) >> 5;          // words above were never written for this warp
+            uint32_t mw = 0;
+            if (lane < 8 && g0 + lane <= gmax) mw = __ldg(hitrow + g0 + lane);
+            for (int k = 7; k >= 0; k--) {
+                uint32_t m = __shfl_sync(0xffffffffu, mw, k);
+                while (m) {
+                    const int bit = 31 - __clz(m);
+                    m &= ~(1u << bit);
+                    const uint32_t pos = ((g0 + k) << 5) + bit;
+                    process(buf, hi - (int)pos, pos);
                 }
             }
         }

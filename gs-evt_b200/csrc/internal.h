@@ -142,6 +142,8 @@ struct BlendFwdArgs {
     float* out_depth;            // operator only
     float* out_opacity;          // operator only
     int* n_touched;              // operator only, may be NULL
+    uint32_t* hitmask;           // engine: [8 warps][hitmask_stride] which list positions each warp blended (may be NULL)
+    size_t hitmask_stride;
     const EngineCtl* ctl;
 };
 void launch_blend_fwd_rgb(const BlendFwdArgs& a, cudaStream_t s);
@@ -167,6 +169,8 @@ struct BlendBwdArgs {
     const float* event_frame;    // [HW] at this level (signed)
     const EngineCtl* ctl;
     // outputs (accumulated with float atomics, must be zero on entry)
+    const uint32_t* hitmask;     // engine: written by the forward (required on the engine path)
+    size_t hitmask_stride;
     float4* grad8;               // [nviews][2P]: operator {dmx, dmy, dA, dB | dC, dopacity, dcol0, ddepth}
                                  //               engine   {dmx, dmy, dA, dB | dC, dgray, 0, 0}
     float2* gradc;               // operator: [P] {dcol1, dcol2}
