@@ -272,7 +272,8 @@ def run_ours(args):
     eng.iterate(3)
     stages = eng.profile(10)
     wl = eng.workload()
-    roof, stage_table = roofline(stages, wl, args.gaussians, d["W"] * d["H"], clocks)
+    default_wl = (args.gaussians, d["W"], d["H"], args.camera, args.seed) == (1_000_000, 640, 480, "robot", 1)
+    roof, stage_table = roofline(stages, wl, args.gaussians, d["W"] * d["H"], clocks, default_wl)
 
     out = None
     if rank == 0:
@@ -310,9 +311,20 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def roofline(stages, wl, P, HW, clocks):
+def load_traffic():
+    """DRAM bytes per launch of each stage from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); {} when absent."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return {k: v["traffic_bytes"] for k, v in j["stages"].items()}, j.get("source")
+    except Exception:
+        return {}, None
+
+
+def roofline(stages, wl, P, HW, clocks, default_workload=True):
     """Algorithmic bytes / flops per launch (DESIGN.md "Kernels and rooflines") over the measured stage time."""
     hbm_peak, sm_max, how = load_peaks()
+    traffic, traffic_src = load_traffic() if default_workload else ({}, None)
     Pv, N, S = sum(wl["visible"]), sum(wl["instances"]), sum(wl["pairs_walked"])
     Pg = wl["gaussians_with_grad"]
     slots = wl["sorted_slots"]
@@ -344,13 +356,16 @@ def roofline(stages, wl, P, HW, clocks):
         if name in flops_alg and ms > 0:
             row.update(bound="fp32", achieved_tflops=round(flops_alg[name] / (ms * 1e-3) / 1e12, 3),
                        frac=round(flops_alg[name] / (ms * 1e-3) / 1e12 / fp32_peak, 4), alg_flops=int(flops_alg[name]))
+        if name in traffic:
+            row["traffic_bytes"] = int(traffic[name])
         table[name] = row
     # the dominant HBM-bound kernel carries the contract's `roofline` object
     hb = max((n for n in table if table[n].get("bound") == "hbm"), key=lambda n: table[n]["ms"])
     top = max(table, key=lambda n: table[n]["ms"])
     r = table[hb]
     roof = {"kernel": hb, "bound": "hbm", "achieved": r["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": r["frac"],
-            "traffic": None, "peak_source": how, "ms_per_launch": r["ms"],
+            "traffic": r.get("traffic_bytes"), "traffic_source": f"profiles/{traffic_src} (ncu --set full, same workload)" if traffic_src else None,
+            "alg_bytes": r["alg_bytes"], "peak_source": how, "ms_per_launch": r["ms"],
             "top_stage": top, "top_stage_ms": table[top]["ms"],
             "fp32_peak_tflops_at_clock": round(fp32_peak, 2)}
     if table[top].get("bound") == "fp32":
