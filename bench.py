@@ -311,6 +311,95 @@ def run_ours(args):
         print(json.dumps(out))
 
 
+# --------------------------------------------------------------------------------------------------
+# this repo, screen-tile split: ONE hypothesis over all ranks (BASELINE configs[4]; strong scaling)
+# --------------------------------------------------------------------------------------------------
+def run_tilesplit(args):
+    """`--mode tilesplit`: the tile rows of one hypothesis are split over the N ranks; the loss sums and the 12-float
+    gradient are exchanged inside the kernels over NVLink peer memory (gsevt/tilesplit.py).  Not the driver's default
+    line (that is the hypothesis-parallel weak-scaling mode): run explicitly, e.g.
+      torchrun --nproc-per-node 8 bench.py --gpus 8 --mode tilesplit --gaussians 5000000 --width 1280 --height 720"""
+    sys.path.insert(0, PKG)
+    import torch
+    dist, world, rank, local = dist_setup(args)
+    from gsevt import lib, tilesplit
+    from gsevt.engine import PackedMap, TrackingEngine
+    from utils.event_camera.event import EventArray, EventFrame
+    lib.require_device()
+    dev = torch.device("cuda", local)
+    d, raw, synth = scene_description(args)
+    act = synth.activate(raw)
+    A = {k: torch.from_numpy(v).to(dev) for k, v in act.items()}
+    pm = PackedMap(A["xyz"], A["scales"], A["rotations"], A["opacities"], A["shs"], 3)
+    del A, act, raw
+    eng = TrackingEngine(pm, d["W"], d["H"], d["fx"], d["fy"], levels=3, lr_rot=d["lr"]["cam_rot_delta"],
+                         lr_trans=d["lr"]["cam_trans_delta"], lr_w=d["lr"]["cam_w_delta"], lr_v=d["lr"]["cam_v_delta"],
+                         converged_threshold=0.0, max_optim_iter=1 << 20)
+    K = np.array([d["fx"], 0, d["cx"], 0, d["fy"], d["cy"], 0, 0, 1.0]).reshape(3, 3)
+    Rt = np.asarray(d["R"], np.float32).reshape(3, 3)
+    Tt = np.asarray(d["T"], np.float32)
+    wt, vt = np.asarray(d["angular_vel"], np.float32), np.asarray(d["linear_vel"], np.float32)
+    # events from the ground-truth intensity change, rendered unsplit on every rank (identical everywhere)
+    dummy = EventFrame(d["W"], d["H"], K, d["dist"], 9, EventArray(*np.zeros((4, 1), np.int64)), device=dev)
+    eng.set_state(Rt, Tt, wt, vt)
+    eng.begin_frame(d["delta_tau"], dummy.sign_pyramid, dummy.unsign_pyramid)
+    eng.eval(0, True)
+    g_last, g_next = eng.gray_images(0)
+    tab = synth.sample_events((g_next - g_last).cpu().numpy(), args.events, 0, 50000, K, d["dist"], seed=1000)
+    ef = EventFrame(d["W"], d["H"], K, d["dist"], 9, EventArray(tab[:, 0], tab[:, 1], tab[:, 2], tab[:, 3]), device=dev)
+    R0, T0, w0, v0 = perturbed_state(d, 0)          # the same hypothesis on every rank
+    grp = tilesplit.TileSplitGroup(eng, rank, world, timeout_s=30.0) if world > 1 else None
+    eng.set_state(R0, T0, w0, v0)
+    eng.begin_frame(d["delta_tau"], ef.sign_pyramid, ef.unsign_pyramid)
+    eng.begin_level(0, True)
+    eng.iterate(max(args.warmup, 3))
+    eng.stream.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier_sync(dist, torch)
+    e0.record(eng.stream)
+    eng.iterate(args.steps)
+    e1.record(eng.stream)
+    eng.stream.synchronize()
+    barrier_sync(dist, torch)
+    ms_max = max_over_ranks(dist, torch, e0.elapsed_time(e1))
+    st = eng.status()
+    assert st.iters_executed == max(args.warmup, 3) + args.steps, f"work skipped: {st.iters_executed} iterations executed"
+    info = eng.split_info()
+    assert info["comm_error"] == 0
+    clocks = sampler.stop() if rank == 0 else None
+    stages = eng.profile(10)                          # collective: every rank replays 10 un-graphed iterations
+    wl = eng.workload()
+    rows = [None] * world
+    mine = dict(rank=rank, rows=info["rows"], instances=sum(wl["instances"]), pairs_walked=sum(wl["pairs_walked"]),
+                stages_ms={k: round(v, 4) for k, v in stages.items()}, loss=float(st.last_loss))
+    if dist is not None:
+        dist.all_gather_object(rows, mine)
+    else:
+        rows = [mine]
+    if rank == 0:
+        assert all(r["loss"] == rows[0]["loss"] for r in rows), "ranks diverged"
+        out = {"metric": "pose-track iters/sec (fwd+bwd), one hypothesis, screen-tile split", "value": round(args.steps / (ms_max / 1e3), 2),
+               "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": round(ms_max / args.steps, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"configs[4]-shaped: {args.gaussians}-Gaussian map, {d['W']}x{d['H']}, one hypothesis, tile rows split "
+                                      f"over {world} GPUs", "gaussians": args.gaussians, "width": d["W"], "height": d["H"],
+                          "parallelism": f"tilesplit{world}: in-kernel exchange of 3 loss sums + 12 gradient sums over NVLink peer memory",
+                          "l2": "map alone exceeds the 126 MB L2"},
+               "clocks": clocks, "gpu_launches": eng.launches_per_iteration * args.steps, "ranks": rows}
+        print(json.dumps(out))
+    if grp is not None:
+        dist.barrier()
+        grp.close()
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def load_traffic():
     """DRAM bytes per launch of each stage from the committed `ncu --set full` capture of this workload
     (profiles/ncu_traffic.json, written by tools/ncu_traffic.py); {} when absent."""
@@ -497,6 +586,9 @@ def main():
     ap.add_argument("--iters-per-frame", type=int, default=50)
     ap.add_argument("--cpu-sample-gaussians", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", choices=["hypotheses", "tilesplit"], default="hypotheses",
+                    help="hypotheses: one independent hypothesis per GPU (weak scaling, the driver's line); "
+                         "tilesplit: one hypothesis, screen tiles split over the GPUs (strong scaling, configs[4])")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 200 if args.impl == "ours" else 60
@@ -504,6 +596,8 @@ def main():
         args.warmup = 10 if args.impl == "ours" else 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "tilesplit":
+        run_tilesplit(args)
     else:
         run_ours(args)
 

@@ -240,7 +240,7 @@ GSEVT_API int gsevt_raster_forward_render(const GsevtRasterArgs* a, void* stream
     DBG("ranges");
     BlendFwdArgs f;
     memset(&f, 0, sizeof(f));
-    f.W = a->width; f.H = a->height; f.grid_x = gx; f.grid_y = gy; f.nviews = 1;
+    f.W = a->width; f.H = a->height; f.grid_x = gx; f.grid_y = gy; f.nviews = 1; f.tile_y0 = 0; f.tile_rows = gy;
     f.ranges = (const uint2*)(im + I.ranges); f.point_list = list;
     f.rec = (const float4*)(g + L.rec); f.rgb4 = (const float4*)(g + L.rgb4);
     f.view_stride_gauss = (size_t)a->P; f.bg = a->background; f.views = vp;
@@ -281,7 +281,7 @@ GSEVT_API int gsevt_raster_backward(const GsevtRasterArgs* a, void* stream) {
     const int gx = (a->width + 15) / 16, gy = (a->height + 15) / 16;
     BlendBwdArgs b;
     memset(&b, 0, sizeof(b));
-    b.W = a->width; b.H = a->height; b.grid_x = gx; b.grid_y = gy; b.nviews = 1;
+    b.W = a->width; b.H = a->height; b.grid_x = gx; b.grid_y = gy; b.nviews = 1; b.tile_y0 = 0; b.tile_rows = gy;
     b.ranges = (const uint2*)(im + I.ranges); b.point_list = (const uint32_t*)(bn + B.list);
     b.rec = (const float4*)(g + L.rec); b.rgb4 = (const float4*)(g + L.rgb4);
     b.view_stride_gauss = (size_t)a->P; b.bg = a->background; b.views = vp;
@@ -426,10 +426,17 @@ struct GsevtEngine {
     int sort_n = 0;     // number of slots sorted in the current level
     int geom_blocks = 0, loss_nb = 0;
     cudaGraphExec_t graph = nullptr;
-    int graph_level = -1, graph_sort_n = -1;
+    int graph_level = -1, graph_sort_n = -1, graph_y0 = -1, graph_y1 = -1;
     cudaStream_t graph_stream = nullptr;
+    // screen-tile split (one engine per rank; strips of tile rows per pyramid level)
+    int split_rank = 0, split_n = 1;
+    int strip_y0 = 0, strip_y1 = 0;      // current level
+    MailBox* mailbox = nullptr;          // this rank's box (its own 2 MiB allocation: exportable through CUDA IPC)
+    SplitComm* comm = nullptr;           // device copy of the peer table, NULL unless split
+    uint32_t* row_hist = nullptr;        // [256]
     std::vector<void*> allocs;
 };
+#define GSEVT_MAILBOX_BYTES ((size_t)2 << 20)
 
 namespace gsevt {
 
@@ -465,12 +472,15 @@ static size_t hitmask_stride_for(const GsevtEngine* e, long long cap) {
 }
 
 // Grows the instance buffers (never inside a captured graph).
-static int ensure_capacity(GsevtEngine* e, long long slots) {
+static int ensure_capacity(GsevtEngine* e, long long slots, cudaStream_t s) {
     if (slots <= e->cap) return 0;
     long long cap = slots + slots / 2;
     if (cap > 0x3fffffff) cap = 0x3fffffff;
     if (slots > cap) { set_error("instance count %lld exceeds the supported maximum", slots); return GSEVT_EOVERFLOW; }
-    cudaDeviceSynchronize();
+    // only this engine's own work uses the buffers (a device-wide sync would also wait for the kernels of OTHER
+    // engines, which in a one-process tile-split group may be waiting for this rank)
+    cudaStreamSynchronize(s);
+    if (e->graph_stream && e->graph_stream != s) cudaStreamSynchronize(e->graph_stream);
     if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
     dev_free(e, e->keys_u); dev_free(e, e->keys); dev_free(e, e->vals_u); dev_free(e, e->vals); dev_free(e, e->sort_temp);
     dev_free(e, e->hitmask);
@@ -545,17 +555,25 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     BlendFwdArgs f;
     memset(&f, 0, sizeof(f));
     f.W = L.W; f.H = L.H; f.grid_x = L.gx; f.grid_y = L.gy; f.nviews = 2;
+    f.tile_y0 = e->strip_y0; f.tile_rows = e->strip_y1 - e->strip_y0;
     f.ranges = e->ranges; f.point_list = e->vals; f.rec = e->rec; f.view_stride_gauss = (size_t)P;
     f.views = e->views; f.final_T = e->final_T; f.n_contrib = e->n_contrib; f.out_color = e->gray; f.ctl = e->ctl;
     f.hitmask = e->hitmask; f.hitmask_stride = e->hitmask_stride;
     launch_blend_fwd_gray(f, s);
     mark();
     const float* evf = e->ev_sign + L.ev_offset;
-    launch_loss_stats(e->gray, evf, L.W * L.H, e->ctl, e->loss_partials, e->loss_nb, e->active_count, s);
+    {
+        // pixel rows of this engine's strip (the whole image unless split): one contiguous slice of the image
+        const int py0 = e->strip_y0 * GSEVT_TILE < L.H ? e->strip_y0 * GSEVT_TILE : L.H;
+        const int py1 = e->strip_y1 * GSEVT_TILE < L.H ? e->strip_y1 * GSEVT_TILE : L.H;
+        launch_loss_stats(e->gray, evf, L.W * L.H, py0 * L.W, (py1 - py0) * L.W, e->ctl, e->loss_partials, e->loss_nb,
+                          e->active_count, e->comm, e->host_flag_dev, s);
+    }
     mark();
     BlendBwdArgs b;
     memset(&b, 0, sizeof(b));
     b.W = L.W; b.H = L.H; b.grid_x = L.gx; b.grid_y = L.gy; b.nviews = 2;
+    b.tile_y0 = e->strip_y0; b.tile_rows = e->strip_y1 - e->strip_y0;
     b.ranges = e->ranges; b.point_list = e->vals; b.rec = e->rec; b.view_stride_gauss = (size_t)P; b.views = e->views;
     b.final_T = e->final_T; b.n_contrib = e->n_contrib; b.gray = e->gray; b.event_frame = evf; b.ctl = e->ctl;
     b.grad8 = e->grad8; b.hitmask = e->hitmask; b.hitmask_stride = e->hitmask_stride;
@@ -569,7 +587,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     launch_geom_compact(2 * P, e->radii, e->grad8, e->active_list, e->active_count, e->ctl, s);
     launch_geom_bwd_map(q, s);
     mark();
-    launch_engine_update(e->ctl, e->geom_partials, e->geom_blocks, e->host_flag_dev, e->overflow, e->views, e->bg3, s);
+    launch_engine_update(e->ctl, e->geom_partials, e->geom_blocks, e->host_flag_dev, e->overflow, e->views, e->bg3, e->comm, s);
     mark();
 }
 
@@ -581,6 +599,15 @@ static int upload_level(GsevtEngine* e, int level, cudaStream_t s) {
     memcpy(h.proj, L.proj_raw, sizeof(h.proj));
     static_assert(offsetof(EngineCtl, proj_raw) - offsetof(EngineCtl, level) == 9 * 4, "EngineCtl level block layout");
     GSEVT_CUDA_OK(cudaMemcpyAsync((char*)e->ctl + offsetof(EngineCtl, level), &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    return 0;
+}
+
+static int upload_strip(GsevtEngine* e, int y0, int y1, cudaStream_t s) {
+    e->strip_y0 = y0; e->strip_y1 = y1;
+    struct { int y0, y1; } h = {y0, y1};
+    static_assert(offsetof(EngineCtl, strip_y1) - offsetof(EngineCtl, strip_y0) == 4, "EngineCtl strip layout");
+    GSEVT_CUDA_OK(cudaMemcpyAsync((char*)e->ctl + offsetof(EngineCtl, strip_y0), &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // h is a stack buffer
     return 0;
 }
 
@@ -696,7 +723,9 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->geom_partials, (size_t)e->geom_blocks * GSEVT_NPART);
     rc |= dev_alloc(e, &e->lastRT, 12);
     rc |= dev_alloc(e, &e->overflow, 1);
+    rc |= dev_alloc(e, &e->row_hist, 256);
     if (rc) { gsevt_engine_destroy(e); return GSEVT_ECUDA; }
+    e->strip_y0 = 0; e->strip_y1 = e->lv[0].gy;
     if (cudaHostAlloc((void**)&e->host_flag, 4, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&e->host_flag_dev, e->host_flag, 0) != cudaSuccess) {
         set_error("pinned flag allocation failed"); gsevt_engine_destroy(e); return GSEVT_ECUDA;
@@ -708,6 +737,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     h.lr_base[0] = cfg->lr_rot; h.lr_base[1] = cfg->lr_trans; h.lr_base[2] = cfg->lr_w; h.lr_base[3] = cfg->lr_v;
     h.max_optim_iter = cfg->max_optim_iter; h.converged_threshold = cfg->converged_threshold;
     h.level_done = 1;
+    h.strip_y0 = 0; h.strip_y1 = e->lv[0].gy;
     cudaMemcpy(e->ctl, &h, sizeof(h), cudaMemcpyHostToDevice);
     float bg[4] = {cfg->background[0], cfg->background[1], cfg->background[2], 0.f};
     cudaMemcpy(e->bg3, bg, sizeof(bg), cudaMemcpyHostToDevice);
@@ -783,6 +813,64 @@ static int probe_instances(GsevtEngine* e, cudaStream_t s, uint32_t* total) {
     return 0;
 }
 
+}  // extern "C"
+
+namespace gsevt {
+// Contiguous partition of `rows` tile rows into n strips of roughly equal cost (cost = tile instances of the row,
+// + 1 so that empty rows still count).  bounds[k] .. bounds[k+1] is strip k.  Every strip gets at least one row
+// while rows >= n.  Pure host code: identical inputs give identical strips on every rank.
+void balance_rows(const uint32_t* cost, int rows, int n, int* bounds) {
+    std::vector<unsigned long long> prefix((size_t)rows + 1, 0ull);
+    for (int y = 0; y < rows; y++) prefix[y + 1] = prefix[y] + cost[y] + 1ull;
+    const unsigned long long total = prefix[rows];
+    bounds[0] = 0;
+    for (int k = 1; k < n; k++) {
+        const unsigned long long target = total * (unsigned long long)k / (unsigned long long)n;
+        int y = bounds[k - 1];
+        while (y < rows && prefix[y] < target) y++;
+        if (y > 0 && y <= rows && prefix[y] - target > target - prefix[y - 1]) y--;   // nearer boundary
+        int lo = bounds[k - 1] + 1, hi = rows - (n - k);
+        if (hi < lo) { lo = hi = (bounds[k - 1] < rows ? bounds[k - 1] : rows); }    // fewer rows than ranks: empty strips at the end
+        if (rows < n) { lo = bounds[k - 1] < rows ? bounds[k - 1] + 1 : rows; hi = lo; }
+        if (y < lo) y = lo;
+        if (y > hi) y = hi;
+        bounds[k] = y;
+    }
+    bounds[n] = rows;
+}
+
+// Sizes the per-iteration sort of the current level at the current pose; split mode: (re)balances the strips first.
+static int size_level(GsevtEngine* e, cudaStream_t s, bool rebalance, int slack_div) {
+    const LevelInfo& L = e->lv[e->cur_level];
+    uint32_t total = 0;
+    int rc = 0;
+    if (e->split_n > 1 && rebalance) {
+        if ((rc = upload_strip(e, 0, L.gy, s))) return rc;
+        if ((rc = probe_instances(e, s, &total))) return rc;
+        launch_row_histogram(2 * e->map->P, e->pairs, e->row_hist, s);
+        uint32_t h[256];
+        GSEVT_CUDA_OK(cudaMemcpyAsync(h, e->row_hist, sizeof(h), cudaMemcpyDeviceToHost, s));
+        GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+        int bounds[GSEVT_SPLIT_MAX + 1];
+        balance_rows(h, L.gy, e->split_n, bounds);
+        const int y0 = bounds[e->split_rank], y1 = bounds[e->split_rank + 1];
+        if ((rc = upload_strip(e, y0, y1, s))) return rc;
+        total = 0;
+        for (int y = y0; y < y1; y++) total += h[y];
+    } else {
+        if (e->split_n <= 1 && (rc = upload_strip(e, 0, L.gy, s))) return rc;
+        if ((rc = probe_instances(e, s, &total))) return rc;
+    }
+    const long long want = slots_for((long long)total + (slack_div > 0 ? total / slack_div : 0));
+    if ((rc = ensure_capacity(e, want, s))) return rc;
+    e->sort_n = (int)want;
+    GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
+    return 0;
+}
+}  // namespace gsevt
+
+extern "C" {
+
 GSEVT_API int gsevt_engine_begin_level(GsevtEngine* e, int32_t level, int32_t opt_vel, void* stream) {
     if (!e || level < 0 || level >= e->nlevels) { set_error("begin_level: bad level"); return GSEVT_EINVAL; }
     if (!e->ev_sign) { set_error("begin_level before begin_frame"); return GSEVT_ESTATE; }
@@ -794,14 +882,8 @@ GSEVT_API int gsevt_engine_begin_level(GsevtEngine* e, int32_t level, int32_t op
     GSEVT_CUDA_OK(cudaMemcpyAsync((char*)e->ctl + offsetof(EngineCtl, opt_vel), &h, sizeof(h), cudaMemcpyHostToDevice, s));
     SETF(n_losses, (int)0);
     SETF(eval_only, (int)0);
-    uint32_t total = 0;
-    rc = probe_instances(e, s, &total);
+    rc = size_level(e, s, true, 0);
     if (rc) return rc;
-    const long long want = slots_for(total);
-    rc = ensure_capacity(e, want);
-    if (rc) return rc;
-    e->sort_n = (int)want;
-    GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
     *e->host_flag = 0;
     return 0;
 }
@@ -812,14 +894,8 @@ GSEVT_API int gsevt_engine_resume(GsevtEngine* e, void* stream) {
     if (!e) { set_error("bad arguments"); return GSEVT_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
-    uint32_t total = 0;
-    int rc = probe_instances(e, s, &total);   // clears level_done
+    int rc = size_level(e, s, false, 8);   // clears level_done; the strips stay as they are
     if (rc) return rc;
-    const long long want = slots_for((long long)total + total / 8);
-    rc = ensure_capacity(e, want);
-    if (rc) return rc;
-    e->sort_n = (int)want;
-    GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     *e->host_flag = 0;
     return 0;
@@ -830,7 +906,8 @@ GSEVT_API int gsevt_engine_iterate(GsevtEngine* e, int32_t n, void* stream) {
     if (!e->ev_sign) { set_error("iterate before begin_frame"); return GSEVT_ESTATE; }
     cudaStream_t s = (cudaStream_t)stream;
     const bool can_graph = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
-    if (can_graph && (e->graph == nullptr || e->graph_level != e->cur_level || e->graph_sort_n != e->sort_n || e->graph_stream != s)) {
+    if (can_graph && (e->graph == nullptr || e->graph_level != e->cur_level || e->graph_sort_n != e->sort_n || e->graph_stream != s ||
+                      e->graph_y0 != e->strip_y0 || e->graph_y1 != e->strip_y1)) {
         if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
         cudaGraph_t g = nullptr;
         GSEVT_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
@@ -841,6 +918,7 @@ GSEVT_API int gsevt_engine_iterate(GsevtEngine* e, int32_t n, void* stream) {
         cudaGraphDestroy(g);
         if (err != cudaSuccess) { e->graph = nullptr; set_error("graph instantiate failed: %s", cudaGetErrorString(err)); return GSEVT_ECUDA; }
         e->graph_level = e->cur_level; e->graph_sort_n = e->sort_n; e->graph_stream = s;
+        e->graph_y0 = e->strip_y0; e->graph_y1 = e->strip_y1;
     }
     for (int i = 0; i < n; i++) {
         if (can_graph) GSEVT_CUDA_OK(cudaGraphLaunch(e->graph, s));
@@ -926,16 +1004,8 @@ GSEVT_API int gsevt_engine_eval(GsevtEngine* e, int32_t level, int32_t signed_lo
     if (rc) return rc;
     SETF(eval_only, (int)1);
     SETF(loss_signed, (int)(signed_loss ? 1 : 0));
-    uint32_t total = 0;
-    rc = probe_instances(e, s, &total);
+    rc = size_level(e, s, true, 0);
     if (rc) return rc;
-    {
-        const long long want = slots_for(total);
-        rc = ensure_capacity(e, want);
-        if (rc) return rc;
-        e->sort_n = (int)want;
-        GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
-    }
     enqueue_iteration(e, s);
     GsevtEngineStatus st;
     rc = gsevt_engine_status(e, &st, stream);
@@ -1038,6 +1108,97 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
     out8[4] = (int64_t)h[2]; out8[5] = (int64_t)h[3];              // sum of n_contrib per view (pairs walked)
     out8[6] = (int64_t)h[4];                                       // (view, Gaussian) pairs with a non-zero blend gradient
     out8[7] = (int64_t)e->sort_n;                                  // slots sorted (instances + padding)
+    return 0;
+}
+
+// ---- screen-tile split ----------------------------------------------------------------------------
+GSEVT_API size_t gsevt_split_mailbox_bytes(void) { return GSEVT_MAILBOX_BYTES; }
+
+GSEVT_API int gsevt_split_balance_rows(const uint32_t* row_cost, int32_t rows, int32_t n, int32_t* bounds) {
+    if (!row_cost || !bounds || rows < 0 || rows > 255 || n < 1 || n > GSEVT_SPLIT_MAX) { set_error("split_balance_rows: bad arguments"); return GSEVT_EINVAL; }
+    int b[GSEVT_SPLIT_MAX + 1];
+    balance_rows(row_cost, rows, n, b);
+    for (int k = 0; k <= n; k++) bounds[k] = b[k];
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_split_mailbox(GsevtEngine* e, void** box) {
+    if (!e || !box) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    if (!e->mailbox) {
+        static_assert(sizeof(MailBox) <= GSEVT_MAILBOX_BYTES, "mailbox allocation too small");
+        static_assert(sizeof(MailSlot) == 128, "MailSlot layout");
+        void* q = nullptr;
+        GSEVT_CUDA_OK(cudaMalloc(&q, GSEVT_MAILBOX_BYTES));
+        e->allocs.push_back(q);
+        e->mailbox = (MailBox*)q;
+        GSEVT_CUDA_OK(cudaMemset(q, 0, GSEVT_MAILBOX_BYTES));
+        GSEVT_CUDA_OK(cudaDeviceSynchronize());
+    }
+    *box = e->mailbox;
+    return 0;
+}
+
+GSEVT_API int gsevt_ipc_export(const void* device_ptr, uint8_t handle64[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!device_ptr || !handle64) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaIpcMemHandle_t h;
+    GSEVT_CUDA_OK(cudaIpcGetMemHandle(&h, const_cast<void*>(device_ptr)));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+GSEVT_API int gsevt_ipc_open(const uint8_t handle64[64], void** device_ptr) {
+    if (!device_ptr || !handle64) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    GSEVT_CUDA_OK(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+GSEVT_API int gsevt_ipc_close(void* device_ptr) {
+    if (!device_ptr) return 0;
+    GSEVT_CUDA_OK(cudaIpcCloseMemHandle(device_ptr));
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_split_attach(GsevtEngine* e, int32_t rank, int32_t n, void* const* boxes, double timeout_s) {
+    if (!e || n < 1 || n > GSEVT_SPLIT_MAX || rank < 0 || rank >= n || (n > 1 && !boxes)) { set_error("split_attach: bad arguments"); return GSEVT_EINVAL; }
+    GSEVT_CUDA_OK(cudaDeviceSynchronize());
+    if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+    if (n == 1) {   // detach
+        e->split_rank = 0; e->split_n = 1;
+        if (e->comm) { dev_free(e, e->comm); e->comm = nullptr; }
+        return 0;
+    }
+    if (!e->mailbox) { set_error("split_attach: call gsevt_engine_split_mailbox first"); return GSEVT_ESTATE; }
+    if (boxes[rank] != (void*)e->mailbox) { set_error("split_attach: boxes[rank] must be this engine's own mailbox"); return GSEVT_EINVAL; }
+    SplitComm h;
+    memset(&h, 0, sizeof(h));
+    h.rank = rank; h.n = n;
+    h.timeout_ns = (unsigned long long)((timeout_s > 0.0 ? timeout_s : 5.0) * 1e9);
+    for (int r = 0; r < n; r++) {
+        if (!boxes[r]) { set_error("split_attach: box %d is NULL", r); return GSEVT_EINVAL; }
+        h.box[r] = (MailBox*)boxes[r];
+    }
+    if (!e->comm) { int rc = dev_alloc(e, &e->comm, 1); if (rc) return rc; }
+    GSEVT_CUDA_OK(cudaMemcpy(e->comm, &h, sizeof(h), cudaMemcpyHostToDevice));
+    // a fresh group starts at sequence 0 with clean slots (every rank attaches before any rank iterates:
+    // the caller puts a barrier between attach and the first collective call)
+    GSEVT_CUDA_OK(cudaMemset(e->mailbox, 0, sizeof(MailBox)));
+    GSEVT_CUDA_OK(cudaMemset((char*)e->ctl + offsetof(EngineCtl, comm_error), 0, 4));
+    GSEVT_CUDA_OK(cudaDeviceSynchronize());
+    e->split_rank = rank; e->split_n = n;
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_split_info(GsevtEngine* e, int32_t out6[6], void* stream) {
+    if (!e || !out6) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int err = 0;
+    unsigned long long seq[2] = {0, 0};
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&err, (char*)e->ctl + offsetof(EngineCtl, comm_error), 4, cudaMemcpyDeviceToHost, s));
+    if (e->comm) GSEVT_CUDA_OK(cudaMemcpyAsync(seq, (char*)e->comm + offsetof(SplitComm, seq), 16, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    out6[0] = e->split_rank; out6[1] = e->split_n; out6[2] = e->strip_y0; out6[3] = e->strip_y1; out6[4] = err;
+    out6[5] = (int32_t)(seq[0] + seq[1]);
     return 0;
 }
 

@@ -328,6 +328,28 @@ void launch_identify_ranges16(const uint16_t* keys, uint2* ranges, int ntiles_to
     identify_ranges16_kernel<<<(threads + 255) / 256, 256, 0, s>>>(keys, ranges, n_dev, cap);
 }
 
+// Screen-tile split: tile instances per tile row (both views), the cost model the strips are balanced on.
+__global__ void __launch_bounds__(256) row_histogram_kernel(int n, const uint64_t* __restrict__ pairs, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const uint32_t r = (uint32_t)(pairs[i] >> 32);
+        const uint32_t w = (r >> 16 & 255u) - (r & 255u);
+        if (w == 0) continue;
+        for (uint32_t y = r >> 8 & 255u; y < r >> 24; y++) atomicAdd(&s_h[y], w);
+    }
+    __syncthreads();
+    if (s_h[threadIdx.x]) atomicAdd(hist + threadIdx.x, s_h[threadIdx.x]);
+}
+void launch_row_histogram(int n_pairs, const uint64_t* pairs, uint32_t* hist256, cudaStream_t s) {
+    cudaMemsetAsync(hist256, 0, 256 * sizeof(uint32_t), s);
+    if (n_pairs <= 0) return;
+    int blocks = (n_pairs + 255) / 256;
+    if (blocks > 1184) blocks = 1184;   // 8 CTAs per SM
+    row_histogram_kernel<<<blocks, 256, 0, s>>>(n_pairs, pairs, hist256);
+}
+
 // Parity-test helper: rebuild the reference's 64-bit keys of one view from the engine's sorted lists.
 __global__ void rebuild_keys_kernel(const uint16_t* __restrict__ tile_keys, const uint32_t* __restrict__ vals,
                                     const float4* __restrict__ rec_view, uint32_t tile_base, uint32_t first, uint32_t count,

@@ -90,10 +90,11 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     const int view = blockIdx.z;
     const int tiles = a.grid_x * a.grid_y;
     const int HW = a.W * a.H;
-    const int tile_lin = view * tiles + blockIdx.y * a.grid_x + blockIdx.x;
+    const int tile_y = blockIdx.y + a.tile_y0;
+    const int tile_lin = view * tiles + tile_y * a.grid_x + blockIdx.x;
     const uint2 range = a.ranges[tile_lin];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bx = blockIdx.x * GSEVT_TILE + (warp & 1) * 8, by = blockIdx.y * GSEVT_TILE + (warp >> 1) * 4;
+    const int bx = blockIdx.x * GSEVT_TILE + (warp & 1) * 8, by = tile_y * GSEVT_TILE + (warp >> 1) * 4;
     const int pixx = bx + (lane & 7), pixy = by + (lane >> 3);
     const float cxw = (float)bx + 3.5f, cyw = (float)by + 1.5f;
     const float pxf = (float)pixx, pyf = (float)pixy;
@@ -219,11 +220,13 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
 }
 
 void launch_blend_fwd_rgb(const BlendFwdArgs& a, cudaStream_t s) {
-    dim3 grid(a.grid_x, a.grid_y, a.nviews);
+    dim3 grid(a.grid_x, a.tile_rows, a.nviews);
+    if (a.tile_rows <= 0) return;
     blend_fwd_kernel<3, true><<<grid, 256, 0, s>>>(a);
 }
 void launch_blend_fwd_gray(const BlendFwdArgs& a, cudaStream_t s) {
-    dim3 grid(a.grid_x, a.grid_y, a.nviews);
+    dim3 grid(a.grid_x, a.tile_rows, a.nviews);
+    if (a.tile_rows <= 0) return;
     blend_fwd_kernel<1, false><<<grid, 256, 0, s>>>(a);
 }
 
@@ -274,10 +277,11 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     const int view = blockIdx.z;
     const int tiles = a.grid_x * a.grid_y;
     const int HW = a.W * a.H;
-    const int tile_lin = view * tiles + blockIdx.y * a.grid_x + blockIdx.x;
+    const int tile_y = blockIdx.y + a.tile_y0;
+    const int tile_lin = view * tiles + tile_y * a.grid_x + blockIdx.x;
     const uint2 range = a.ranges[tile_lin];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bx = blockIdx.x * GSEVT_TILE + (warp & 1) * 8, by = blockIdx.y * GSEVT_TILE + (warp >> 1) * 4;
+    const int bx = blockIdx.x * GSEVT_TILE + (warp & 1) * 8, by = tile_y * GSEVT_TILE + (warp >> 1) * 4;
     const int pixx = bx + (lane & 7), pixy = by + (lane >> 3);
     const float cxw = (float)bx + 3.5f, cyw = (float)by + 1.5f;
     const float pxf = (float)pixx, pyf = (float)pixy;
@@ -471,11 +475,13 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
 }
 
 void launch_blend_bwd_rgb(const BlendBwdArgs& a, cudaStream_t s) {
-    dim3 grid(a.grid_x, a.grid_y, a.nviews);
+    dim3 grid(a.grid_x, a.tile_rows, a.nviews);
+    if (a.tile_rows <= 0) return;
     blend_bwd_kernel<3, true><<<grid, 256, 0, s>>>(a);
 }
 void launch_blend_bwd_gray(const BlendBwdArgs& a, cudaStream_t s) {
-    dim3 grid(a.grid_x, a.grid_y, a.nviews);
+    dim3 grid(a.grid_x, a.tile_rows, a.nviews);
+    if (a.tile_rows <= 0) return;
     blend_bwd_kernel<1, false><<<grid, 256, 0, s>>>(a);
 }
 

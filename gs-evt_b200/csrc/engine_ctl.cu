@@ -13,6 +13,7 @@
 // All arithmetic is fp32 in torch's operation order unless noted (python scalars are doubles that
 // torch rounds to fp32 when they meet an fp32 tensor).
 #include "internal.h"
+#include "split_comm.cuh"
 
 namespace gsevt {
 
@@ -178,9 +179,48 @@ __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineC
                                                                           const float* __restrict__ partials,
                                                                           int nblocks, int* host_flag,
                                                                           const int* __restrict__ overflow,
-                                                                          ViewParams* views, const float* bg3) {
+                                                                          ViewParams* views, const float* bg3,
+                                                                          SplitComm* comm) {
     if (ctl->level_done) return;
-    if (overflow && *overflow) {
+    __shared__ double s_d[16];
+    __shared__ double s_t[16];
+    __shared__ float s_g[GSEVT_NPART];
+    __shared__ int s_overflow;
+    {
+        const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        double s = 0.0;
+        for (int b = lane; b < nblocks; b += 32) s += (double)partials[(size_t)k * nblocks + b];   // [12][nblocks]: coalesced
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) { s_d[k] = s; s_g[k] = (float)s; }
+    }
+    if (threadIdx.x == 0) s_overflow = overflow ? *overflow : 0;
+    __syncthreads();
+    if (comm) {
+        // screen-tile split: s_d holds the gradient of this rank's strip.  All ranks exchange {12 sums, overflow flag}
+        // over peer memory and add them in rank order, so the replicated Adam / pose state stays bit-identical; an
+        // overflow on ANY rank voids the iteration on ALL of them.
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) s_d[GSEVT_NPART] = (double)s_overflow;
+            __syncwarp();
+            const bool ok = split_exchange(comm, 1, GSEVT_NPART + 1, s_d, s_t);
+            __syncwarp();
+            if (threadIdx.x < GSEVT_NPART) s_g[threadIdx.x] = (float)s_t[threadIdx.x];
+            if (threadIdx.x == 0) {
+                s_overflow = s_t[GSEVT_NPART] != 0.0 ? 1 : 0;
+                if (!ok) {
+                    ctl->comm_error = 1;
+                    ctl->level_done = 3;
+                    if (host_flag) *host_flag = 3;
+                    __threadfence_system();
+                    s_overflow = -1;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_overflow < 0) return;
+    }
+    if (s_overflow) {
         // The instance list outgrew the slots sorted this iteration: void the iteration (state untouched), pause
         // the level (2) and tell the host, which re-sizes and resumes (gsevt_engine_resume).
         if (threadIdx.x == 0) {
@@ -191,16 +231,6 @@ __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineC
         }
         return;
     }
-    __shared__ float s_g[GSEVT_NPART];
-    {
-        const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        double s = 0.0;
-        for (int b = lane; b < nblocks; b += 32) s += (double)partials[(size_t)k * nblocks + b];   // [12][nblocks]: coalesced
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) s_g[k] = (float)s;
-    }
-    __syncthreads();
     if (threadIdx.x != 0) return;
     EngineCtl* c = ctl;
     for (int k = 0; k < GSEVT_NPART; k++) c->grads[k] = s_g[k];
@@ -275,8 +305,8 @@ __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineC
     }
 }
 void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, const int* overflow,
-                          ViewParams* views, const float* bg3, cudaStream_t s) {
-    engine_update_kernel<<<1, 32 * GSEVT_NPART, 0, s>>>(ctl, partials, nblocks, host_flag, overflow, views, bg3);
+                          ViewParams* views, const float* bg3, SplitComm* comm, cudaStream_t s) {
+    engine_update_kernel<<<1, 32 * GSEVT_NPART, 0, s>>>(ctl, partials, nblocks, host_flag, overflow, views, bg3, comm);
 }
 
 // ---- per-frame helpers ----------------------------------------------------------------------------

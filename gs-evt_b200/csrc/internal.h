@@ -40,9 +40,36 @@ struct EngineCtl {
     float loss_alpha, loss_beta, last_loss;
     int loss_signed;
     int eval_only;        // 1: compute loss + gradients, skip the optimiser / pose update
+    // screen-tile split: this engine bins / blends / scores tile rows [strip_y0, strip_y1) only
+    int strip_y0, strip_y1;
+    int comm_error;       // a peer did not answer inside the exchange time-out (split mode)
     float grads[12];      // rho, theta, v, w
     float losses[GSEVT_MAX_LOSSES];
 };
+
+// ---- screen-tile split: in-kernel exchange over peer memory --------------------------------------
+// Every rank owns one MailBox in its own HBM, mapped into its peers (CUDA IPC across processes, plain
+// peer access inside one process).  An exchange is an all-gather by remote stores: the rank writes its
+// contribution into slot [channel][parity][own rank] of EVERY box (its own included), then waits for
+// the sequence numbers of all slots of its own box, and sums the slots in rank order — so every rank
+// computes bit-identical totals and the replicated optimiser state never diverges.  Two parities per
+// channel: a rank can run at most one exchange ahead of a peer on the same channel.
+#define GSEVT_SPLIT_MAX 8
+#define GSEVT_SPLIT_VALS 14
+struct MailSlot {
+    double v[GSEVT_SPLIT_VALS];
+    unsigned long long seq;
+    unsigned long long pad_;
+};   // 128 B
+struct MailBox { MailSlot slot[2][2][GSEVT_SPLIT_MAX]; };   // [channel: 0 loss, 1 gradient][parity][source rank]
+struct SplitComm {
+    int rank, n;
+    unsigned long long seq[2];          // exchanges completed per channel
+    unsigned long long timeout_ns;
+    MailBox* box[GSEVT_SPLIT_MAX];      // box[rank] is local
+};
+// Pairs' tile-rect rows: hist[y] += width of every rect covering tile row y (both views), for strip balancing.
+void launch_row_histogram(int n_pairs, const uint64_t* pairs, uint32_t* hist256, cudaStream_t s);
 
 // ---- preprocess ------------------------------------------------------------------------------
 struct PreAosArgs {
@@ -128,6 +155,7 @@ void launch_rebuild_keys(const uint16_t* tile_keys, const uint32_t* vals, const 
 // ---- blending --------------------------------------------------------------------------------
 struct BlendFwdArgs {
     int W, H, grid_x, grid_y;
+    int tile_y0, tile_rows;      // tile rows [tile_y0, tile_y0 + tile_rows) are blended (the whole grid unless split)
     int nviews;
     const uint2* ranges;         // [nviews][tiles]
     const uint32_t* point_list;
@@ -151,6 +179,7 @@ void launch_blend_fwd_gray(const BlendFwdArgs& a, cudaStream_t s);
 
 struct BlendBwdArgs {
     int W, H, grid_x, grid_y;
+    int tile_y0, tile_rows;
     int nviews;
     const uint2* ranges;
     const uint32_t* point_list;
@@ -209,14 +238,15 @@ void launch_geom_compact(int n_pairs, const int* radii, const float4* grad8, uin
 void launch_reduce_partials(const float* partials, int nblocks, float* out12, cudaStream_t s);
 
 // ---- loss (engine) -----------------------------------------------------------------------------
-void launch_loss_stats(const float* gray, const float* event_frame, int HW, EngineCtl* ctl, double* partials,
-                       int nblocks, uint32_t* zero_me, cudaStream_t s);
+// Scores pixels [pix0, pix0 + npix) (the whole image unless split); comm != NULL: the three sums are exchanged.
+void launch_loss_stats(const float* gray, const float* event_frame, int HW, int pix0, int npix, EngineCtl* ctl,
+                       double* partials, int nblocks, uint32_t* zero_me, SplitComm* comm, int* host_flag, cudaStream_t s);
 int loss_blocks(int HW);
 
 // ---- engine control kernels ----------------------------------------------------------------------
 void launch_pose_setup(EngineCtl* ctl, ViewParams* views, const float* bg3, float znear, float zfar, cudaStream_t s);
 void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, const int* overflow,
-                          ViewParams* views, const float* bg3, cudaStream_t s);
+                          ViewParams* views, const float* bg3, SplitComm* comm, cudaStream_t s);
 void launch_const_vel(EngineCtl* ctl, float tau, cudaStream_t s);
 void launch_weighted_velocity(EngineCtl* ctl, const float* lastRT, float delta_tau, float weight, cudaStream_t s);
 

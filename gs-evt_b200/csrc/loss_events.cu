@@ -15,6 +15,7 @@
 //   L^2 = 1 - 2*S2/n + SE2,  dL/dd = alpha*d - beta*E_eff,  alpha = S2/(n^3 L),  beta = 1/(L n)
 // (closed form of autograd through norm / div / abs / sub / norm; derivation in DESIGN.md).
 #include "internal.h"
+#include "split_comm.cuh"
 
 namespace gsevt {
 
@@ -154,15 +155,16 @@ int loss_blocks(int HW) {
 
 // partials: [nblocks][3] doubles followed by one unsigned ticket counter (zero on entry, reset on exit).
 __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict__ gray, const float* __restrict__ ev,
-                                                         int HW, EngineCtl* __restrict__ ctl,
+                                                         int HW, int pix0, int npix, EngineCtl* __restrict__ ctl,
                                                          double* __restrict__ partials, int nblocks,
-                                                         uint32_t* __restrict__ zero_me) {
+                                                         uint32_t* __restrict__ zero_me, SplitComm* comm, int* host_flag) {
     if (ctl->level_done) return;
     __shared__ double s_w[8][3];
+    __shared__ double s_x[8];
     __shared__ bool s_last;
     const bool sgn = ctl->loss_signed != 0;
     double sd2 = 0.0, s2 = 0.0, se2 = 0.0;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) {
+    for (int i = pix0 + blockIdx.x * 256 + threadIdx.x; i < pix0 + npix; i += gridDim.x * 256) {
         const float d = gray[(size_t)HW + i] - gray[i];
         const float E = ev[i];
         sd2 += (double)d * (double)d;
@@ -202,6 +204,20 @@ __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict
         t1 += __shfl_xor_sync(0xffffffffu, t1, o);
         t2 += __shfl_xor_sync(0xffffffffu, t2, o);
     }
+    if (comm) {
+        // screen-tile split: these are the sums over this rank's strip; exchange them over peer memory
+        if (threadIdx.x == 0) { s_x[0] = t0; s_x[1] = t1; s_x[2] = t2; }
+        __syncwarp();
+        const bool ok = split_exchange(comm, 0, 3, s_x, s_x + 4);
+        __syncwarp();
+        t0 = s_x[4]; t1 = s_x[5]; t2 = s_x[6];
+        if (!ok && threadIdx.x == 0) {
+            ctl->comm_error = 1;
+            ctl->level_done = 3;
+            if (host_flag) *host_flag = 3;
+            __threadfence_system();
+        }
+    }
     if (threadIdx.x != 0) return;
     if (zero_me) *zero_me = 0u;   // per-iteration counter of the backward's work list (consumed two kernels later)
     *ticket = 0u;
@@ -220,9 +236,9 @@ __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict
     }
 }
 
-void launch_loss_stats(const float* gray, const float* event_frame, int HW, EngineCtl* ctl, double* partials,
-                       int nblocks, uint32_t* zero_me, cudaStream_t s) {
-    loss_stats_kernel<<<nblocks, 256, 0, s>>>(gray, event_frame, HW, ctl, partials, nblocks, zero_me);
+void launch_loss_stats(const float* gray, const float* event_frame, int HW, int pix0, int npix, EngineCtl* ctl,
+                       double* partials, int nblocks, uint32_t* zero_me, SplitComm* comm, int* host_flag, cudaStream_t s) {
+    loss_stats_kernel<<<nblocks, 256, 0, s>>>(gray, event_frame, HW, pix0, npix, ctl, partials, nblocks, zero_me, comm, host_flag);
 }
 
 // ---- workload counters (bench / profiling only) ---------------------------------------------------

@@ -24,6 +24,7 @@ __device__ __forceinline__ bool project_geometry(const ViewParams& vp, float px,
                                                  const float* __restrict__ cov3D, ProjOut& o) {
     o.radius = 0;
     o.tiles = 0;
+    o.rect = 0;
     const float depth = affine3r(vp.view[2], vp.view[6], vp.view[10], vp.view[14], px, py, pz);
     if (!(depth > 0.2f)) return false;  // in_frustum (auxiliary.h:154): p_view.z <= 0.2 is culled
     const float hx = affine3r(vp.proj[0], vp.proj[4], vp.proj[8], vp.proj[12], px, py, pz);
@@ -152,6 +153,18 @@ __global__ void __launch_bounds__(256, 3) preprocess_map_kernel(PreMapArgs a) {
     bool ok[2];
 #pragma unroll
     for (int v = 0; v < 2; v++) ok[v] = project_geometry(s_vp[v], xo.x, xo.y, xo.z, cov, o[v]);
+    if (a.ctl) {
+        // screen-tile split: keep only the part of the tile rect inside this engine's strip of tile rows
+        // (the whole grid unless split, where this changes nothing)
+        const uint32_t sy0 = (uint32_t)a.ctl->strip_y0, sy1 = (uint32_t)a.ctl->strip_y1;
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            const uint32_t r = o[v].rect;
+            const uint32_t y0 = max(r >> 8 & 255u, sy0), y1 = min(r >> 24, sy1);
+            ok[v] = ok[v] && y1 > y0;
+            o[v].rect = (r & 0x00FF00FFu) | (y0 << 8) | (y1 << 24);
+        }
+    }
 #pragma unroll
     for (int v = 0; v < 2; v++) {
         const size_t j = (size_t)v * a.P + idx;

@@ -130,8 +130,16 @@ class TrackingEngine:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.gsevt_engine_iterate(self.handle, int(n), self.stream.cuda_stream), "gsevt_engine_iterate")
 
+    def split_info(self):
+        """Screen-tile split state: dict(rank, n, rows=(first, end) tile rows of the current level, comm_error, exchanges)."""
+        out = (C.c_int32 * 6)()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_split_info(self.handle, out, self.stream.cuda_stream), "gsevt_engine_split_info")
+        return dict(rank=out[0], n=out[1], rows=(out[2], out[3]), comm_error=out[4], exchanges=out[5])
+
     def poll_done(self):
-        """0 running, 1 level finished, 2 paused (instance list outgrew the sorted slots: call resume())."""
+        """0 running, 1 level finished, 2 paused (instance list outgrew the sorted slots: call resume()),
+        3 a tile-split peer did not answer."""
         return int(self._lib.gsevt_engine_poll_done(self.handle))
 
     def resume(self):
@@ -160,6 +168,8 @@ class TrackingEngine:
             flag = self.poll_done()
             if flag == 2:
                 self.resume()
+            elif flag == 3:
+                raise _lib.GsevtError("tile-split exchange timed out: a peer rank did not answer (see gsevt.tilesplit)")
             elif flag:
                 break
         return self.status()

@@ -107,6 +107,14 @@ PROTOTYPES = {
     "gsevt_engine_stage_name": (C.c_char_p, [C.c_int32]),
     "gsevt_engine_profile": (C.c_int, [c_void_p, C.c_int32, c_float_p, c_void_p]),
     "gsevt_engine_workload": (C.c_int, [c_void_p, C.POINTER(C.c_int64), c_void_p]),
+    "gsevt_engine_split_mailbox": (C.c_int, [c_void_p, C.POINTER(c_void_p)]),
+    "gsevt_split_mailbox_bytes": (C.c_size_t, []),
+    "gsevt_ipc_export": (C.c_int, [c_void_p, C.POINTER(C.c_uint8)]),
+    "gsevt_ipc_open": (C.c_int, [C.POINTER(C.c_uint8), C.POINTER(c_void_p)]),
+    "gsevt_ipc_close": (C.c_int, [c_void_p]),
+    "gsevt_engine_split_attach": (C.c_int, [c_void_p, C.c_int32, C.c_int32, C.POINTER(c_void_p), C.c_double]),
+    "gsevt_engine_split_info": (C.c_int, [c_void_p, C.POINTER(C.c_int32), c_void_p]),
+    "gsevt_split_balance_rows": (C.c_int, [C.POINTER(C.c_uint32), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
 }
 
 _lib = None

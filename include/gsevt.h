@@ -286,6 +286,39 @@ GSEVT_API int gsevt_engine_resume(GsevtEngine* e, void* stream);
  * gsevt_engine_resume (read from mapped pinned memory, no stream synchronisation). */
 GSEVT_API int gsevt_engine_poll_done(GsevtEngine* e);
 
+/* ------------------------------------------------------------------------------------------------
+ * 4. Screen-tile split of ONE hypothesis over the GPUs of a box (BASELINE.json configs[4]).
+ *    The reference has no multi-GPU path; the only reference arithmetic this touches is the whole-image
+ *    L2 normalisation of the rendered difference (utils/render_camera/frame.py:90-91) and the sum over
+ *    Gaussians of dL/dtau, dL/dvel (dgr/diff_gaussian_rasterization/__init__.py:163-167).
+ *    One engine per rank, identical state and event frame everywhere.  Rank r bins, blends and scores
+ *    a contiguous strip of tile rows (balanced on tile instances per row at every begin_level); the
+ *    three loss sums and the 12 gradient sums (+ the overflow flag) are exchanged INSIDE the loss and
+ *    update kernels by stores into the peers' mailboxes over NVLink and added in rank order, so all
+ *    ranks apply bit-identical optimiser steps and an iteration is still one CUDA-graph launch.
+ *    Every engine call after attach is collective: all ranks make the same calls in the same order.
+ * ---------------------------------------------------------------------------------------------- */
+/* This engine's mailbox: library-owned device memory of gsevt_split_mailbox_bytes() bytes in its own
+ * cudaMalloc allocation (so that it can be exported).  Created on first call. */
+GSEVT_API int gsevt_engine_split_mailbox(GsevtEngine* e, void** box);
+GSEVT_API size_t gsevt_split_mailbox_bytes(void);
+/* CUDA IPC plumbing for one-process-per-GPU groups: export a 64-byte handle of a mailbox, open a
+ * peer's handle (enables peer access lazily), close it again before the owner is destroyed. */
+GSEVT_API int gsevt_ipc_export(const void* device_ptr, uint8_t handle64[64]);
+GSEVT_API int gsevt_ipc_open(const uint8_t handle64[64], void** device_ptr);
+GSEVT_API int gsevt_ipc_close(void* device_ptr);
+/* boxes[n]: device pointers, valid on this engine's device, of all ranks' mailboxes in rank order
+ * (boxes[rank] = this engine's own).  Resets the exchange sequence: every rank must attach before any
+ * rank iterates (put a barrier in between).  n = 1 detaches.  timeout_s <= 0 selects 5 s: a peer that
+ * does not answer in time sets level_done = 3 / poll_done() = 3 instead of hanging the GPU. */
+GSEVT_API int gsevt_engine_split_attach(GsevtEngine* e, int32_t rank, int32_t n, void* const* boxes, double timeout_s);
+/* out6 = {rank, n, first tile row, end tile row of the current level's strip, comm error flag,
+ * exchanges completed}.  Synchronises. */
+GSEVT_API int gsevt_engine_split_info(GsevtEngine* e, int32_t out6[6], void* stream);
+/* The strip partition itself (host code): bounds[k] .. bounds[k+1] = tile rows of rank k, balanced on
+ * row_cost (tile instances per tile row).  rows <= 255, n <= 8. */
+GSEVT_API int gsevt_split_balance_rows(const uint32_t* row_cost, int32_t rows, int32_t n, int32_t* bounds);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,10 @@ import sys
 
 import pytest
 
+# the one-GPU tile-split tests run up to 8 engines ("ranks") on one device, each spinning briefly on its peers: give
+# every stream its own hardware queue so that no rank queues behind a waiting one (read at CUDA initialisation)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "gs-evt_b200")
 for p in (PKG, ROOT):

@@ -1,0 +1,176 @@
+"""Screen-tile split (BASELINE configs[4]) on ONE GPU: n engines in one process play the ranks, each
+driven by its own host thread and stream, mailboxes addressed directly (the one-process-per-GPU IPC path is
+covered by test_tilesplit_multi_gpu below when the box has >= 2 GPUs).  The split must change nothing but the
+summation order of the loss sums and of the 12 gradient sums."""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _scene_engines(dev, n, P=20000, W=320, Hh=240, levels=3, seed=4, **kw):
+    import torch
+    from gsevt import synth
+    from gsevt.engine import EventFrameBuilder, PackedMap, TrackingEngine
+    sc = H.small_scene(P, W, Hh, seed=seed)
+    A = {k: torch.from_numpy(v).to(dev) for k, v in sc["act"].items()}
+    pm = PackedMap(A["xyz"], A["scales"], A["rotations"], A["opacities"], A["shs"], 3)
+    K = np.array([sc["fx"], 0, W / 2, 0, sc["fy"], Hh / 2, 0, 0, 1.0]).reshape(3, 3)
+    b = EventFrameBuilder(W, Hh, K, synth.DESK["dist"], levels=levels, device=dev)
+    ev = synth.random_events(30000 * W // 640, W, Hh, 0, 50000, seed=3)
+    sign, unsign = b.build(ev[:, 1].astype(np.int16), ev[:, 2].astype(np.int16), ev[:, 3].astype(np.uint8))
+    engines = []
+    for _ in range(n):
+        e = TrackingEngine(pm, W, Hh, sc["fx"], sc["fy"], levels=levels, **kw)
+        e.set_state(sc["R"], sc["T"], sc["w"], sc["v"])
+        e.begin_frame(sc["dtau"], sign, unsign)
+        engines.append(e)
+    return sc, pm, engines
+
+
+def _collective(engines, fn):
+    """Runs fn(rank, engine) for every rank concurrently (every call after attach is collective)."""
+    out, err = [None] * len(engines), []
+
+    def work(r):
+        try:
+            out[r] = fn(r, engines[r])
+        except Exception as ex:  # noqa: BLE001
+            err.append((r, ex))
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(len(engines))]
+    [t.start() for t in th]
+    [t.join(120) for t in th]
+    assert not any(t.is_alive() for t in th), "a rank is stuck"
+    if err:
+        raise err[0][1]
+    return out
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("level,signed", [(0, True), (1, False)])
+def test_split_eval_equals_unsplit(built, cuda_dev, n, level, signed):
+    from gsevt import tilesplit
+    sc, pm, engs = _scene_engines(cuda_dev, n + 1)
+    whole, ranks = engs[0], engs[1:]
+    L0, g0 = whole.eval(level, signed)
+    keys0 = [whole.binning(v, level) for v in (0, 1)]
+    tilesplit.attach_local(ranks, timeout_s=20.0)
+    res = _collective(ranks, lambda r, e: e.eval(level, signed))
+    gy = ((int(240 * 0.5 ** level)) + 15) // 16
+    gx = ((int(320 * 0.5 ** level)) + 15) // 16
+    rows = [e.split_info()["rows"] for e in ranks]
+    # the strips tile the grid, in rank order, without gaps
+    assert rows[0][0] == 0 and rows[-1][1] == gy and all(rows[i][1] == rows[i + 1][0] for i in range(n - 1))
+    assert all(b > a for a, b in rows) or gy < n
+    for r, (L, g) in enumerate(res):
+        # every rank holds the SAME numbers, bit for bit (sums are taken in rank order on every rank)
+        assert L == res[0][0] and np.array_equal(g, res[0][1])
+    L, g = res[0]
+    assert abs(L - L0) <= 2e-6 * abs(L0)
+    assert H.rel_max(g, g0) < (2e-5 if signed else 2e-4)
+    # binning of a strip == the unsplit engine's lists restricted to the strip's tiles, bit-exact
+    for r, e in enumerate(ranks):
+        for v in (0, 1):
+            keys, ids, ranges = e.binning(v, level)
+            k0, i0, r0 = keys0[v]
+            for ty in range(gy):
+                for tx in range(gx):
+                    t = ty * gx + tx
+                    a, b = ranges[t]
+                    if rows[r][0] <= ty < rows[r][1]:
+                        a0, b0 = r0[t]
+                        assert b - a == b0 - a0
+                        assert np.array_equal(ids[a:b], i0[a0:b0]) and np.array_equal(keys[a:b], k0[a0:b0])
+                    else:
+                        assert a == b == 0
+
+
+def test_split_optimisation_tracks_unsplit(built, cuda_dev):
+    """40 fine-stage iterations on 4 strips vs the unsplit engine: identical control flow, losses and state equal to
+    rounding (only the summation order of 3 + 12 numbers per iteration differs), ranks bit-identical to each other."""
+    from gsevt import tilesplit
+    n = 4
+    sc, pm, engs = _scene_engines(cuda_dev, n + 1, converged_threshold=0.0, max_optim_iter=60)
+    whole, ranks = engs[0], engs[1:]
+    whole.begin_level(0, True)
+    whole.iterate(40)
+    whole.stream.synchronize()
+    want_l, want_s = whole.losses(), whole.get_state()
+    tilesplit.attach_local(ranks, timeout_s=20.0)
+
+    def run(r, e):
+        e.begin_level(0, True)
+        e.iterate(40)
+        e.stream.synchronize()
+        return e.losses(), e.get_state(), e.status().iters_executed, e.split_info()
+
+    res = _collective(ranks, run)
+    for l, s, it, info in res:
+        assert it == 40 and info["comm_error"] == 0 and info["exchanges"] == 80
+        assert np.array_equal(l, res[0][0]) and all(np.array_equal(a, b) for a, b in zip(s, res[0][1]))
+    assert np.abs(res[0][0] - want_l).max() < 2e-5
+    assert all(np.abs(a - b).max() < 2e-5 for a, b in zip(res[0][1], want_s))
+
+
+def test_split_overflow_on_one_rank_pauses_all(built, cuda_dev):
+    """The overflow flag rides in the gradient exchange: when ONE strip outgrows its sorted slots every rank voids
+    the iteration and pauses; after resume() on every rank the run continues."""
+    from gsevt import tilesplit
+    n = 2
+    sc, pm, ranks = _scene_engines(cuda_dev, n, converged_threshold=0.0, max_optim_iter=50)
+    tilesplit.attach_local(ranks, timeout_s=20.0)
+    away = np.array([[-1, 0, 0], [0, 1, 0], [0, 0, -1]], np.float32) @ sc["R"]
+
+    def run(r, e):
+        e.set_state(away, sc["T"], sc["w"], sc["v"])
+        e.begin_level(0, True)
+        e.set_state(sc["R"], sc["T"], sc["w"], sc["v"])
+        e.iterate(3)
+        e.stream.synchronize()
+        flag, it = e.poll_done(), e.status().iters_executed
+        e.resume()
+        e.iterate(3)
+        e.stream.synchronize()
+        return flag, it, e.status().iters_executed, e.get_state()
+
+    res = _collective(ranks, run)
+    for flag, it0, it1, st in res:
+        assert flag == 2 and it0 == 0 and it1 == 3
+        assert all(np.array_equal(a, b) for a, b in zip(st, res[0][3]))
+
+
+def test_split_missing_peer_times_out_instead_of_hanging(built, cuda_dev):
+    from gsevt import lib, tilesplit
+    sc, pm, ranks = _scene_engines(cuda_dev, 2, P=4000, W=160, Hh=120, levels=1)
+    tilesplit.attach_local(ranks, timeout_s=0.3)
+    e = ranks[0]          # rank 1 never runs
+    e.begin_level(0, True)
+    e.iterate(2)
+    e.stream.synchronize()
+    assert e.poll_done() == 3 and e.split_info()["comm_error"] == 1
+    with pytest.raises(lib.GsevtError):
+        e.run_level(0, True)
+
+
+def test_tilesplit_multi_gpu(built, cuda_dev):
+    """One process per GPU, mailboxes mapped through CUDA IPC, exchange over NVLink: tools/tilesplit_check.py under
+    torchrun compares the split run with an unsplit run on rank 0."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    n = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tools", "tilesplit_check.py")]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "TILESPLIT OK" in p.stdout
