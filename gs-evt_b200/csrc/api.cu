@@ -773,6 +773,7 @@ GSEVT_API int gsevt_engine_get_state(GsevtEngine* e, float* R, float* T, float* 
     if (!e) { set_error("bad arguments"); return GSEVT_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
     float h[18];
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // see gsevt_engine_status
     GSEVT_CUDA_OK(cudaMemcpyAsync(h, e->ctl, sizeof(h), cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     if (R) memcpy(R, h, 36);
@@ -799,6 +800,7 @@ GSEVT_API int gsevt_engine_begin_frame(GsevtEngine* e, double delta_tau, const f
 static int probe_instances(GsevtEngine* e, cudaStream_t s, uint32_t* total) {
     // pose_setup + projection + scan only, to size the sort for this level.
     const GsevtMap* m = e->map;
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // pending iterations first (see gsevt_engine_status)
     SETF(level_done, (int)0);
     launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, s);
     PreMapArgs pa;
@@ -875,6 +877,7 @@ GSEVT_API int gsevt_engine_begin_level(GsevtEngine* e, int32_t level, int32_t op
     if (!e || level < 0 || level >= e->nlevels) { set_error("begin_level: bad level"); return GSEVT_EINVAL; }
     if (!e->ev_sign) { set_error("begin_level before begin_frame"); return GSEVT_ESTATE; }
     cudaStream_t s = (cudaStream_t)stream;
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // see gsevt_engine_status
     e->cur_level = level;
     int rc = upload_level(e, level, s);
     if (rc) return rc;
@@ -936,6 +939,10 @@ GSEVT_API int gsevt_engine_status(GsevtEngine* e, GsevtEngineStatus* out, void* 
     static thread_local EngineCtl h;
     uint32_t offs[2] = {0, 0};
     int ov = 0;
+    // Wait for the stream BEFORE the device->host copies: a copy into pageable memory waits for the stream inside
+    // the driver, and while it does, other host threads of this process cannot submit work — fatal when the work
+    // being waited for is a tile-split exchange whose peer is driven by one of those threads.
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     GSEVT_CUDA_OK(cudaMemcpyAsync(&h, e->ctl, offsetof(EngineCtl, losses), cudaMemcpyDeviceToHost, s));
     // instances of view 0 = start of the first non-empty range of view 1 = number of sorted keys below `tiles`;
     // read it from the ranges: the first touched tile of view 1 starts where view 0 ends.
@@ -964,6 +971,7 @@ GSEVT_API int gsevt_engine_losses(GsevtEngine* e, float* out, int32_t capacity, 
     if (!e || !out || capacity < 0) { set_error("bad arguments"); return GSEVT_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
     int n = 0;
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // see gsevt_engine_status
     GSEVT_CUDA_OK(cudaMemcpyAsync(&n, (char*)e->ctl + offsetof(EngineCtl, n_losses), 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     int c = n < capacity ? n : capacity;
@@ -999,6 +1007,7 @@ GSEVT_API int gsevt_engine_eval(GsevtEngine* e, int32_t level, int32_t signed_lo
     if (!e || level < 0 || level >= e->nlevels) { set_error("bad arguments"); return GSEVT_EINVAL; }
     if (!e->ev_sign) { set_error("eval before begin_frame"); return GSEVT_ESTATE; }
     cudaStream_t s = (cudaStream_t)stream;
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // see gsevt_engine_status
     e->cur_level = level;
     int rc = upload_level(e, level, s);
     if (rc) return rc;
@@ -1038,6 +1047,7 @@ GSEVT_API int gsevt_engine_binning(GsevtEngine* e, int32_t view, uint64_t* keys_
     const LevelInfo& L = e->lv[e->cur_level];
     const int tiles = L.gx * L.gy;
     std::vector<uint2> r((size_t)2 * tiles);
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // see gsevt_engine_status
     GSEVT_CUDA_OK(cudaMemcpyAsync(r.data(), e->ranges, r.size() * sizeof(uint2), cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     uint32_t n0 = 0, n1 = 0;
@@ -1088,6 +1098,7 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
     cudaStream_t s = (cudaStream_t)stream;
     const LevelInfo& L = e->lv[e->cur_level];
     unsigned long long* d = nullptr;
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // see gsevt_engine_status
     GSEVT_CUDA_OK(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
     GSEVT_CUDA_OK(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), s));
     launch_workload_counters(e->map->P, e->radii, e->grad8, L.W * L.H, e->n_contrib, d, s);
@@ -1194,6 +1205,7 @@ GSEVT_API int gsevt_engine_split_info(GsevtEngine* e, int32_t out6[6], void* str
     cudaStream_t s = (cudaStream_t)stream;
     int err = 0;
     unsigned long long seq[2] = {0, 0};
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // see gsevt_engine_status
     GSEVT_CUDA_OK(cudaMemcpyAsync(&err, (char*)e->ctl + offsetof(EngineCtl, comm_error), 4, cudaMemcpyDeviceToHost, s));
     if (e->comm) GSEVT_CUDA_OK(cudaMemcpyAsync(seq, (char*)e->comm + offsetof(SplitComm, seq), 16, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
