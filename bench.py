@@ -273,7 +273,7 @@ def run_ours(args):
     stages = eng.profile(10)
     wl = eng.workload()
     default_wl = (args.gaussians, d["W"], d["H"], args.camera, args.seed) == (1_000_000, 640, 480, "robot", 1)
-    roof, stage_table = roofline(stages, wl, args.gaussians, d["W"] * d["H"], clocks, default_wl)
+    roof, stage_table = roofline(stages, wl, args.gaussians, d["W"] * d["H"], clocks, default_wl, tiles=((d["W"] + 15) // 16) * ((d["H"] + 15) // 16))
 
     out = None
     if rank == 0:
@@ -295,9 +295,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": round(status_bytes * frames_run / args.steps, 1),
                     "frames": frames_run, "note": "per frame: events pinned-host->device, GPU event frame, iterations, loss+pose read-back"},
             "gpu_launches": eng.launches_per_iteration * args.steps,
-            "gpu_launches_note": "our own kernels per iteration (preprocess_map, emit_tiles, identify_ranges16, blend_fwd, loss_stats, "
-                                 "blend_bwd, geom_bwd, engine_update) x steps; plus CUB library kernels (two radix sorts, one scan) and "
-                                 "one memset per iteration, all inside one CUDA graph launch",
+            "gpu_launches_note": "our own kernels per iteration (preprocess_map, compact_finish, tile_count, tile_scan, tile_starts, "
+                                 "tile_scatter, blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, engine_update) x steps; plus CUB "
+                                 "library kernels (one radix sort over the visible pairs, one scan), all inside one CUDA graph launch",
             "roofline": roof,
             "stages_ms": stage_table,
             "workload_counters": wl,
@@ -410,24 +410,24 @@ def load_traffic():
         return {}, None
 
 
-def roofline(stages, wl, P, HW, clocks, default_workload=True):
+def roofline(stages, wl, P, HW, clocks, default_workload=True, tiles=1200):
     """Algorithmic bytes / flops per launch (DESIGN.md "Kernels and rooflines") over the measured stage time."""
     hbm_peak, sm_max, how = load_peaks()
     traffic, traffic_src = load_traffic() if default_workload else ({}, None)
     Pv, N, S = sum(wl["visible"]), sum(wl["instances"]), sum(wl["pairs_walked"])
     Pg = wl["gaussians_with_grad"]
-    slots = wl["sorted_slots"]
+    chunks = (N + 4095) // 4096
     bytes_alg = {
         # map read once for both views (40 B) + SH for Gaussians visible in >= 1 view (192 B); per pair: radius, depth key,
         # {rect | id}; per visible pair: 32-B record, 32-B zeroed gradient accumulator, clamp byte
-        "preprocess_map": 40 * P + 192 * max(wl["visible"]) + 2 * P * 16 + Pv * (32 + 32 + 1),
-        # 2P (u32 depth key, u64 {rect | id}) pairs: histogram read + 4 digit passes of (12 B in + 12 B out)
-        "depth_sort(cub)": 2 * P * (4 + 4 * 24),
-        "scan(cub)": 2 * P * 12,
-        "emit_tiles": 2 * P * 12 + slots * 6,
-        # (u16 tile key, u32 id) pairs: histogram read + 2 digit passes of (6 B in + 6 B out)
-        "tile_sort(cub)": slots * 2 + 2 * 12 * slots,
-        "identify_ranges": N * 2,
+        "preprocess_map": 40 * P + 192 * max(wl["visible"]) + 2 * P * 4 + Pv * (12 + 32 + 32 + 1),
+        # visible (u32 depth key, u64 {rect | id}) pairs: histogram read + 4 digit passes of (12 B in + 12 B out)
+        "depth_sort(cub)": Pv * (4 + 4 * 24),
+        "scan(cub)": Pv * 12,
+        # tile binning without instance records (csrc/tilebin.cu): chunks of 4096 instances x (2 x tiles) bins
+        "tile_count": Pv * 12 + chunks * 2 * tiles * 2,
+        "tile_scan": chunks * 2 * tiles * (2 + 4),
+        "tile_scatter": Pv * 12 + chunks * 2 * tiles * 4 + N * 4,
         # compaction scan (radius + 24 B of the accumulator per visible pair) + per active pair: list entry out/in,
         # accumulator, xyz/opacity + covariance, SH (AoS copy), clamp byte
         "geom_bwd_pose": 2 * P * 4 + Pv * 24 + Pg * (8 + 32 + 40 + 192 + 1),

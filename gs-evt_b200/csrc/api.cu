@@ -406,12 +406,15 @@ struct GsevtEngine {
     uint32_t* active_list = nullptr;   // [2P] compacted pairs with a gradient
     uint32_t* active_count = nullptr;
     void* scan_temp = nullptr; size_t scan_bytes = 0;
+    unsigned long long* comp_state = nullptr;            // projection kernel: chained-scan state + tile counter
+    uint32_t* n_vis = nullptr;                           // device: visible (view, Gaussian) pairs of the last projection
+    int vis_cap = 0;                                     // slots the depth sort covers: upper bound on n_vis the current level's graph was sized for
     uint32_t *depth_key = nullptr, *depth_sorted = nullptr;
     uint64_t *pairs = nullptr, *pairs_sorted = nullptr;   // {tile rect | pair id}: projection order / depth order
     void* sortA_temp = nullptr; size_t sortA_bytes = 0;
-    uint16_t *keys_u = nullptr, *keys = nullptr;
-    uint32_t *vals_u = nullptr, *vals = nullptr;
-    void* sort_temp = nullptr; size_t sort_bytes = 0;
+    // tile binning (tilebin.cu): per-chunk tile counts, their prefix over the chunks, chunk pair ranges, per-tile totals
+    uint16_t* tb_hist = nullptr; uint32_t* tb_base = nullptr; uint2* tb_chunks = nullptr; uint32_t* tb_total = nullptr;
+    uint32_t* vals = nullptr;            // per-tile lists: Gaussian index per slot
     uint2* ranges = nullptr;
     uint32_t* hitmask = nullptr; size_t hitmask_stride = 0;   // forward -> backward: what each warp blended
     float* gray = nullptr; float* final_T = nullptr; uint32_t* n_contrib = nullptr;
@@ -426,7 +429,7 @@ struct GsevtEngine {
     int sort_n = 0;     // number of slots sorted in the current level
     int geom_blocks = 0, loss_nb = 0;
     cudaGraphExec_t graph = nullptr;
-    int graph_level = -1, graph_sort_n = -1, graph_y0 = -1, graph_y1 = -1;
+    int graph_level = -1, graph_sort_n = -1, graph_y0 = -1, graph_y1 = -1, graph_vis_cap = -1;
     cudaStream_t graph_stream = nullptr;
     // screen-tile split (one engine per rank; strips of tile rows per pyramid level)
     int split_rank = 0, split_n = 1;
@@ -482,19 +485,18 @@ static int ensure_capacity(GsevtEngine* e, long long slots, cudaStream_t s) {
     cudaStreamSynchronize(s);
     if (e->graph_stream && e->graph_stream != s) cudaStreamSynchronize(e->graph_stream);
     if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
-    dev_free(e, e->keys_u); dev_free(e, e->keys); dev_free(e, e->vals_u); dev_free(e, e->vals); dev_free(e, e->sort_temp);
+    dev_free(e, e->vals); dev_free(e, e->tb_hist); dev_free(e, e->tb_base); dev_free(e, e->tb_chunks);
     dev_free(e, e->hitmask);
-    e->keys_u = e->keys = nullptr; e->vals_u = e->vals = nullptr; e->sort_temp = nullptr; e->hitmask = nullptr;
+    e->vals = nullptr; e->tb_hist = nullptr; e->tb_base = nullptr; e->tb_chunks = nullptr; e->hitmask = nullptr;
     e->cap = (int)cap;
-    e->sort_bytes = sort16_temp_bytes(e->cap);
     e->hitmask_stride = hitmask_stride_for(e, e->cap);
+    const int tiles0 = e->lv[0].gx * e->lv[0].gy;
     int rc = 0;
     rc |= dev_alloc(e, &e->hitmask, 8 * e->hitmask_stride);
-    rc |= dev_alloc(e, &e->keys_u, (size_t)e->cap);
-    rc |= dev_alloc(e, &e->keys, (size_t)e->cap);
-    rc |= dev_alloc(e, &e->vals_u, (size_t)e->cap);
     rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
-    rc |= dev_alloc(e, (char**)&e->sort_temp, e->sort_bytes);
+    rc |= dev_alloc(e, (char**)&e->tb_hist, tilebin_hist_bytes(e->cap, tiles0));
+    rc |= dev_alloc(e, (char**)&e->tb_base, tilebin_base_bytes(e->cap, tiles0));
+    rc |= dev_alloc(e, (char**)&e->tb_chunks, tilebin_chunk_bytes(e->cap));
     return rc ? GSEVT_ECUDA : 0;
 }
 
@@ -516,12 +518,25 @@ static void projection_colmajor(double znear, double zfar, double fovX, double f
         for (int r = 0; r < 4; r++) out[4 * c + r] = P[r][c];
 }
 
+static PreMapArgs premap_args(GsevtEngine* e, int vis_cap) {
+    const GsevtMap* m = e->map;
+    PreMapArgs pa;
+    pa.P = m->P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
+    pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
+    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.pairs = e->pairs;
+    pa.rec = e->rec; pa.grad8 = e->grad8;
+    pa.comp_state = e->comp_state;
+    pa.tile_counter = reinterpret_cast<uint32_t*>(e->comp_state + (m->P + 255) / 256);
+    pa.n_vis = e->n_vis; pa.vis_cap = vis_cap; pa.overflow = e->overflow;
+    return pa;
+}
+
 // Enqueue one full optimisation iteration (or one evaluation) on stream s.  When `ev` is non-null an
 // event is recorded before every stage and after the last one (GSEVT_NSTAGES + 1 events): used by
 // gsevt_engine_profile for per-stage device times, never inside a captured graph.
 #define GSEVT_NSTAGES 11
 static const char* const kStageNames[GSEVT_NSTAGES] = {
-    "preprocess_map", "depth_sort(cub)", "scan(cub)", "emit_tiles", "tile_sort(cub)", "identify_ranges",
+    "preprocess_map", "depth_sort(cub)", "scan(cub)", "tile_count", "tile_scan", "tile_scatter",
     "blend_fwd_gray", "loss_stats", "blend_bwd_gray", "geom_bwd_pose", "engine_update"};
 
 static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = nullptr) {
@@ -533,24 +548,25 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     // the two ViewParams blocks are current on entry: written by the previous iteration's update kernel, or by
     // the stand-alone pose kernel after any host-side change of state / level (probe_instances, set_state, ...)
     mark();
-    PreMapArgs pa;
-    pa.P = P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
-    pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
-    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.pairs = e->pairs;
-    pa.rec = e->rec; pa.grad8 = e->grad8;
+    const PreMapArgs pa = premap_args(e, e->vis_cap);
     launch_preprocess_map(pa, s);
     mark();
-    launch_sort_pairs32(e->sortA_temp, e->sortA_bytes, e->depth_key, e->depth_sorted, e->pairs, e->pairs_sorted, 2 * P, s);
+    const int nv = e->vis_cap;   // pairs sorted / scanned / emitted: the visible ones + sentinel slack
+    launch_sort_pairs32(e->sortA_temp, e->sortA_bytes, e->depth_key, e->depth_sorted, e->pairs, e->pairs_sorted, nv, s);
     mark();
-    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs_sorted, e->offsets, 2 * P, s);
+    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs_sorted, e->offsets, nv, s);
     mark();
     const int tiles = L.gx * L.gy;
-    launch_emit_tiles(P, L.gx, tiles, e->pairs_sorted, e->offsets, e->keys_u, e->vals_u, e->sort_n, e->overflow, e->ctl, s);
+    TileBinArgs tb;
+    tb.P = P; tb.n_pairs = nv; tb.grid_x = L.gx; tb.tiles_per_view = tiles;
+    tb.pairs = e->pairs_sorted; tb.offsets = e->offsets; tb.hist = e->tb_hist; tb.base = e->tb_base; tb.chunk_pairs = e->tb_chunks;
+    tb.tile_total = e->tb_total; tb.ranges = e->ranges; tb.values = e->vals; tb.cap = e->sort_n; tb.overflow = e->overflow;
+    tb.ctl = e->ctl;
+    launch_tile_count(tb, s);
     mark();
-    const int bit = (int)higher_msb((uint32_t)(2 * tiles));
-    launch_sort_pairs16(e->sort_temp, e->sort_bytes, e->keys_u, e->keys, e->vals_u, e->vals, e->sort_n, bit, s);
+    launch_tile_scan(tb, s);
     mark();
-    launch_identify_ranges16(e->keys, e->ranges, 2 * tiles, e->offsets + (2 * P - 1), e->sort_n, s);
+    launch_tile_scatter(tb, s);
     mark();
     BlendFwdArgs f;
     memset(&f, 0, sizeof(f));
@@ -685,7 +701,6 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     e->scan_bytes = scan_temp_bytes((int)p2);
     { const size_t g = scan_gather_temp_bytes((int)p2); if (g > e->scan_bytes) e->scan_bytes = g; }
     e->sortA_bytes = sort32_temp_bytes((int)p2);
-    e->sort_bytes = sort16_temp_bytes(e->cap);
     e->geom_blocks = geom_bwd_blocks(P, 2);
     const LevelInfo& L0 = e->lv[0];
     const size_t hw = (size_t)L0.W * L0.H;
@@ -703,17 +718,20 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->active_list, p2);
     rc |= dev_alloc(e, &e->active_count, 1);
     rc |= dev_alloc(e, (char**)&e->scan_temp, e->scan_bytes);
+    rc |= dev_alloc(e, (char**)&e->comp_state, preprocess_map_state_bytes(P));
+    rc |= dev_alloc(e, &e->n_vis, 1);
     rc |= dev_alloc(e, &e->depth_key, p2);
     rc |= dev_alloc(e, &e->depth_sorted, p2);
     rc |= dev_alloc(e, &e->pairs, p2);
     rc |= dev_alloc(e, &e->pairs_sorted, p2);
     rc |= dev_alloc(e, (char**)&e->sortA_temp, e->sortA_bytes);
-    rc |= dev_alloc(e, &e->keys_u, (size_t)e->cap);
-    rc |= dev_alloc(e, &e->keys, (size_t)e->cap);
-    rc |= dev_alloc(e, &e->vals_u, (size_t)e->cap);
     rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
-    rc |= dev_alloc(e, (char**)&e->sort_temp, e->sort_bytes);
+    rc |= dev_alloc(e, (char**)&e->tb_hist, tilebin_hist_bytes(e->cap, L0.gx * L0.gy));
+    rc |= dev_alloc(e, (char**)&e->tb_base, tilebin_base_bytes(e->cap, L0.gx * L0.gy));
+    rc |= dev_alloc(e, (char**)&e->tb_chunks, tilebin_chunk_bytes(e->cap));
+    rc |= dev_alloc(e, &e->tb_total, 2 * (size_t)L0.gx * L0.gy);
     rc |= dev_alloc(e, &e->ranges, 2 * (size_t)L0.gx * L0.gy);
+    if (tilebin_configure(L0.gx * L0.gy)) { set_error("image too large for the tile binning kernels"); gsevt_engine_destroy(e); return GSEVT_EINVAL; }
     e->hitmask_stride = hitmask_stride_for(e, e->cap);
     rc |= dev_alloc(e, &e->hitmask, 8 * e->hitmask_stride);
     rc |= dev_alloc(e, &e->gray, 2 * hw);
@@ -726,6 +744,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->row_hist, 256);
     if (rc) { gsevt_engine_destroy(e); return GSEVT_ECUDA; }
     e->strip_y0 = 0; e->strip_y1 = e->lv[0].gy;
+    e->vis_cap = (int)p2;
     if (cudaHostAlloc((void**)&e->host_flag, 4, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&e->host_flag_dev, e->host_flag, 0) != cudaSuccess) {
         set_error("pinned flag allocation failed"); gsevt_engine_destroy(e); return GSEVT_ECUDA;
@@ -742,6 +761,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     float bg[4] = {cfg->background[0], cfg->background[1], cfg->background[2], 0.f};
     cudaMemcpy(e->bg3, bg, sizeof(bg), cudaMemcpyHostToDevice);
     cudaMemset(e->overflow, 0, 4);
+    cudaMemset(e->comp_state, 0, preprocess_map_state_bytes(P));   // every later launch leaves it zeroed (compact_finish_kernel)
     cudaMemset(e->loss_partials, 0, ((size_t)e->loss_nb * 3 + 2) * 8);
     cudaMemset(e->grad8, 0, 2 * p2 * 16);
     cudaMemset(e->radii, 0, p2 * 4);
@@ -797,21 +817,23 @@ GSEVT_API int gsevt_engine_begin_frame(GsevtEngine* e, double delta_tau, const f
     return 0;
 }
 
-static int probe_instances(GsevtEngine* e, cudaStream_t s, uint32_t* total) {
-    // pose_setup + projection + scan only, to size the sort for this level.
+static int probe_instances(GsevtEngine* e, cudaStream_t s, uint32_t* total, uint32_t* n_vis) {
+    // pose_setup + projection + scan only, to size the sorts for this level: tile instances and visible pairs.
     const GsevtMap* m = e->map;
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // pending iterations first (see gsevt_engine_status)
     SETF(level_done, (int)0);
     launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, s);
-    PreMapArgs pa;
-    pa.P = m->P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
-    pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
-    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.pairs = e->pairs;
-    pa.rec = e->rec; pa.grad8 = e->grad8;
+    const int n2 = 2 * m->P;
+    PreMapArgs pa = premap_args(e, n2);   // no bound on the count
+    pa.overflow = nullptr;
     launch_preprocess_map(pa, s);
-    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs, e->offsets, 2 * m->P, s);   // projection order: only the total matters here
-    GSEVT_CUDA_OK(cudaMemcpyAsync(total, e->offsets + (2 * (size_t)m->P - 1), 4, cudaMemcpyDeviceToHost, s));
+    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs, e->offsets, n2, s);   // projection order: only the total matters here
+    uint32_t h[2] = {0, 0};
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&h[0], e->offsets + ((size_t)n2 - 1), 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&h[1], e->n_vis, 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    *total = h[0];
+    if (n_vis) *n_vis = h[1];
     return 0;
 }
 
@@ -844,28 +866,31 @@ void balance_rows(const uint32_t* cost, int rows, int n, int* bounds) {
 // Sizes the per-iteration sort of the current level at the current pose; split mode: (re)balances the strips first.
 static int size_level(GsevtEngine* e, cudaStream_t s, bool rebalance, int slack_div) {
     const LevelInfo& L = e->lv[e->cur_level];
-    uint32_t total = 0;
+    uint32_t total = 0, n_vis = 0;
     int rc = 0;
     if (e->split_n > 1 && rebalance) {
         if ((rc = upload_strip(e, 0, L.gy, s))) return rc;
-        if ((rc = probe_instances(e, s, &total))) return rc;
-        launch_row_histogram(2 * e->map->P, e->pairs, e->row_hist, s);
+        if ((rc = probe_instances(e, s, &total, &n_vis))) return rc;
+        launch_row_histogram((int)n_vis, e->pairs, e->row_hist, s);
         uint32_t h[256];
         GSEVT_CUDA_OK(cudaMemcpyAsync(h, e->row_hist, sizeof(h), cudaMemcpyDeviceToHost, s));
         GSEVT_CUDA_OK(cudaStreamSynchronize(s));
         int bounds[GSEVT_SPLIT_MAX + 1];
         balance_rows(h, L.gy, e->split_n, bounds);
-        const int y0 = bounds[e->split_rank], y1 = bounds[e->split_rank + 1];
-        if ((rc = upload_strip(e, y0, y1, s))) return rc;
-        total = 0;
-        for (int y = y0; y < y1; y++) total += h[y];
-    } else {
-        if (e->split_n <= 1 && (rc = upload_strip(e, 0, L.gy, s))) return rc;
-        if ((rc = probe_instances(e, s, &total))) return rc;
+        if ((rc = upload_strip(e, bounds[e->split_rank], bounds[e->split_rank + 1], s))) return rc;
+    } else if (e->split_n <= 1) {
+        if ((rc = upload_strip(e, 0, L.gy, s))) return rc;
     }
+    if ((rc = probe_instances(e, s, &total, &n_vis))) return rc;   // with this engine's strip in force
     const long long want = slots_for((long long)total + (slack_div > 0 ? total / slack_div : 0));
     if ((rc = ensure_capacity(e, want, s))) return rc;
     e->sort_n = (int)want;
+    // visible pairs: the count moves while the pose is optimised; above the cap the device voids the iteration and pauses
+    long long vslack = (long long)n_vis / 16 + 8192;
+    if (slack_div > 0) vslack += n_vis / slack_div;
+    long long cap = ((long long)n_vis + vslack + 4095) / 4096 * 4096;
+    if (cap > 2LL * e->map->P) cap = 2LL * e->map->P;
+    e->vis_cap = (int)cap;
     GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
     return 0;
 }
@@ -910,7 +935,8 @@ GSEVT_API int gsevt_engine_iterate(GsevtEngine* e, int32_t n, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const bool can_graph = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
     if (can_graph && (e->graph == nullptr || e->graph_level != e->cur_level || e->graph_sort_n != e->sort_n || e->graph_stream != s ||
-                      e->graph_y0 != e->strip_y0 || e->graph_y1 != e->strip_y1)) {
+                      e->graph_y0 != e->strip_y0 || e->graph_y1 != e->strip_y1 ||
+                      e->graph_vis_cap != e->vis_cap)) {
         if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
         cudaGraph_t g = nullptr;
         GSEVT_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
@@ -921,7 +947,7 @@ GSEVT_API int gsevt_engine_iterate(GsevtEngine* e, int32_t n, void* stream) {
         cudaGraphDestroy(g);
         if (err != cudaSuccess) { e->graph = nullptr; set_error("graph instantiate failed: %s", cudaGetErrorString(err)); return GSEVT_ECUDA; }
         e->graph_level = e->cur_level; e->graph_sort_n = e->sort_n; e->graph_stream = s;
-        e->graph_y0 = e->strip_y0; e->graph_y1 = e->strip_y1;
+        e->graph_y0 = e->strip_y0; e->graph_y1 = e->strip_y1; e->graph_vis_cap = e->vis_cap;
     }
     for (int i = 0; i < n; i++) {
         if (can_graph) GSEVT_CUDA_OK(cudaGraphLaunch(e->graph, s));
@@ -946,7 +972,7 @@ GSEVT_API int gsevt_engine_status(GsevtEngine* e, GsevtEngineStatus* out, void* 
     GSEVT_CUDA_OK(cudaMemcpyAsync(&h, e->ctl, offsetof(EngineCtl, losses), cudaMemcpyDeviceToHost, s));
     // instances of view 0 = start of the first non-empty range of view 1 = number of sorted keys below `tiles`;
     // read it from the ranges: the first touched tile of view 1 starts where view 0 ends.
-    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[1], e->offsets + (2 * (size_t)e->map->P - 1), 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[1], e->offsets + ((size_t)e->vis_cap - 1), 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaMemcpyAsync(&ov, e->overflow, 4, cudaMemcpyDeviceToHost, s));
     {
         const LevelInfo& L = e->lv[e->cur_level];
@@ -1054,8 +1080,13 @@ GSEVT_API int gsevt_engine_binning(GsevtEngine* e, int32_t view, uint64_t* keys_
     for (int t = 0; t < tiles; t++) { n0 += r[t].y - r[t].x; n1 += r[tiles + t].y - r[tiles + t].x; }
     const uint32_t first = view == 0 ? 0u : n0, count = view == 0 ? n0 : n1;
     if ((int64_t)count > (int64_t)capacity) { set_error("capacity %d < %u instances", capacity, count); return GSEVT_ENOMEM; }
-    launch_rebuild_keys(e->keys, e->vals, e->rec + 2 * (size_t)view * e->map->P, (uint32_t)(view * tiles), first, count, keys_out,
+    uint16_t* tile_keys = nullptr;   // tile id per slot, as the high word of the reference's sorted keys holds it
+    GSEVT_CUDA_OK(cudaMalloc(&tile_keys, ((size_t)n0 + n1 + 1) * sizeof(uint16_t)));
+    launch_keys_from_ranges(2 * tiles, e->ranges, tile_keys, s);
+    launch_rebuild_keys(tile_keys, e->vals, e->rec + 2 * (size_t)view * e->map->P, (uint32_t)(view * tiles), first, count, keys_out,
                         list_out, s);
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    cudaFree(tile_keys);
     // ranges of this view, rebased to its own list (untouched tiles stay (0,0) like the reference's)
     std::vector<uint32_t> rr((size_t)2 * tiles, 0u);
     for (int t = 0; t < tiles; t++) {
@@ -1105,7 +1136,9 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
     unsigned long long h[8];
     uint32_t offs[2] = {0, 0};
     GSEVT_CUDA_OK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
-    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[1], e->offsets + (2 * (size_t)e->map->P - 1), 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[1], e->offsets + ((size_t)e->vis_cap - 1), 4, cudaMemcpyDeviceToHost, s));
+    uint32_t n_active = 0;   // length of the last iteration's active list (the accumulators themselves are cleared by geom_bwd)
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&n_active, e->active_count, 4, cudaMemcpyDeviceToHost, s));
     {
         const int tiles = L.gx * L.gy;
         std::vector<uint2> r((size_t)2 * tiles);
@@ -1117,7 +1150,7 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
     out8[0] = (int64_t)h[0]; out8[1] = (int64_t)h[1];              // visible Gaussians per view
     out8[2] = (int64_t)offs[0]; out8[3] = (int64_t)(offs[1] - offs[0]);  // tile instances per view
     out8[4] = (int64_t)h[2]; out8[5] = (int64_t)h[3];              // sum of n_contrib per view (pairs walked)
-    out8[6] = (int64_t)h[4];                                       // (view, Gaussian) pairs with a non-zero blend gradient
+    out8[6] = (int64_t)n_active;                                   // (view, Gaussian) pairs with a non-zero blend gradient
     out8[7] = (int64_t)e->sort_n;                                  // slots sorted (instances + padding)
     return 0;
 }
@@ -1216,9 +1249,10 @@ GSEVT_API int gsevt_engine_split_info(GsevtEngine* e, int32_t out6[6], void* str
 
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e) {
     (void)e;
-    // preprocess, emit_tiles, identify_ranges, blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, update = 9 of
-    // ours; plus CUB: two radix sorts (histogram + exclusive sum + one onesweep per 8-bit digit) and a scan, one memset.
-    return 9;
+    // preprocess, compact_finish, tile_count, tile_scan, tile_starts, tile_scatter, blend_fwd, loss_stats, blend_bwd,
+    // geom_compact, geom_bwd, update = 12 of ours; plus CUB: one radix sort (histogram + exclusive sum + four onesweep
+    // passes) and a scan.
+    return 12;
 }
 
 }  // extern "C"

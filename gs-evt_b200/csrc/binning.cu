@@ -234,7 +234,7 @@ void launch_scan_gather(void* temp, size_t temp_bytes, const uint64_t* pairs, ui
 // — so the (tile, id) stores are fully coalesced and the work is balanced whatever the rect sizes are.
 // (The reference emits one serial, divergent loop per Gaussian: rasterizer_impl.cu:85-109.)
 // Threads past the pair list fill the unused capacity [total, cap) with sentinel keys.
-__global__ void __launch_bounds__(256) emit_tiles_kernel(int P, int gx, int tiles_per_view, const uint64_t* __restrict__ pairs,
+__global__ void __launch_bounds__(256) emit_tiles_kernel(int P, int n, int gx, int tiles_per_view, const uint64_t* __restrict__ pairs,
                                                          const uint32_t* __restrict__ offsets, uint16_t* __restrict__ keys,
                                                          uint32_t* __restrict__ values, int cap, int* __restrict__ overflow,
                                                          const EngineCtl* __restrict__ ctl) {
@@ -243,8 +243,7 @@ __global__ void __launch_bounds__(256) emit_tiles_kernel(int P, int gx, int tile
     __shared__ uint32_t s_rect[256];
     __shared__ uint32_t s_gid[256];
     __shared__ float s_rcpw[256];
-    const int n = 2 * P;
-    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int i = blockIdx.x * 256 + threadIdx.x;   // n = pairs in the (depth-sorted, compacted) list incl. sentinel slack
     const uint32_t total = offsets[n - 1];
     if (i == 0 && total > (uint32_t)cap) *overflow = 1;
     if (i < cap && (uint32_t)i >= total) {
@@ -288,12 +287,12 @@ __global__ void __launch_bounds__(256) emit_tiles_kernel(int P, int gx, int tile
         values[o] = g - v * (uint32_t)P;
     }
 }
-void launch_emit_tiles(int P, int grid_x, int tiles_per_view, const uint64_t* pairs, const uint32_t* offsets, uint16_t* keys,
-                       uint32_t* values, int cap, int* overflow, const EngineCtl* ctl, cudaStream_t s) {
-    const int threads = 2 * P > cap ? 2 * P : cap;
-    if (threads <= 0) return;
-    emit_tiles_kernel<<<(threads + 255) / 256, 256, 0, s>>>(P, grid_x, tiles_per_view, pairs, offsets, keys, values, cap, overflow,
-                                                           ctl);
+void launch_emit_tiles(int P, int n_pairs, int grid_x, int tiles_per_view, const uint64_t* pairs, const uint32_t* offsets,
+                       uint16_t* keys, uint32_t* values, int cap, int* overflow, const EngineCtl* ctl, cudaStream_t s) {
+    const int threads = n_pairs > cap ? n_pairs : cap;
+    if (threads <= 0 || n_pairs <= 0) return;
+    emit_tiles_kernel<<<(threads + 255) / 256, 256, 0, s>>>(P, n_pairs, grid_x, tiles_per_view, pairs, offsets, keys, values, cap,
+                                                           overflow, ctl);
 }
 
 // Eight keys per thread (one 16-byte load + the key before them).

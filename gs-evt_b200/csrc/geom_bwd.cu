@@ -114,8 +114,19 @@ __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
         const int count = s_count;
     for (int li = threadIdx.x; li < count; li += 256) {
         const long long gid = ENGINE ? (long long)s_list[li] : chunk + s_list[li];
-        const float4 g0 = __ldg(a.grad8 + 2 * gid);
-        const float4 g1 = __ldg(a.grad8 + 2 * gid + 1);
+        float4 g0, g1;
+        if constexpr (ENGINE) {
+            // consume and clear: the engine's accumulators are all-zero between iterations (only the pairs on this
+            // list were touched by the blend backward), so the projection never has to zero 32 B per visible pair
+            float4* acc8 = const_cast<float4*>(a.grad8) + 2 * gid;
+            g0 = acc8[0];
+            g1 = acc8[1];
+            acc8[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            acc8[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            g0 = __ldg(a.grad8 + 2 * gid);
+            g1 = __ldg(a.grad8 + 2 * gid + 1);
+        }
         const int view = (int)(gid / P);
         const int idx = (int)(gid - (long long)view * P);
         float dmx = g0.x, dmy = g0.y, dA = g0.z, dB = g0.w, dC = g1.x;
@@ -399,35 +410,66 @@ void launch_geom_bwd_map(const GeomBwdArgs& a, cudaStream_t s) {
     geom_bwd_kernel<true><<<geom_bwd_blocks(a.P, a.nviews), 256, 0, s>>>(a);
 }
 
-// Streaming compaction at full occupancy: list of (view, Gaussian) pairs with a non-zero blend gradient.
-// One warp-aggregated atomic per warp that found something.
-__global__ void __launch_bounds__(256) geom_compact_kernel(int n, const int* __restrict__ radii, const float4* __restrict__ grad8,
-                                                           uint32_t* __restrict__ list, uint32_t* __restrict__ count,
-                                                           const EngineCtl* __restrict__ ctl) {
+// Streaming compaction: list of (view, Gaussian) pairs with a non-zero blend gradient.  Every CTA owns a contiguous
+// slice of the pairs, collects its hits in shared memory and reserves its part of the list with ONE global atomic
+// (a warp-aggregated atomic per hit warp serialises tens of thousands of adds on a single L2 address).
+constexpr int GC_PER_CTA = 2048;
+__global__ void __launch_bounds__(256) geom_compact_kernel(int n, int per_cta, const int* __restrict__ radii,
+                                                           const float4* __restrict__ grad8, uint32_t* __restrict__ list,
+                                                           uint32_t* __restrict__ count, const EngineCtl* __restrict__ ctl) {
     if (ctl && ctl->level_done) return;
+    __shared__ uint32_t s_list[GC_PER_CTA];
+    __shared__ uint32_t s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    for (int gid = blockIdx.x * 256 + threadIdx.x; gid - lane < n; gid += gridDim.x * 256) {
-        bool active = gid < n && radii[gid] > 0;
-        if (active) {
-            const float4 g0 = __ldg(grad8 + 2 * (size_t)gid);
-            const float2 g1 = __ldg(reinterpret_cast<const float2*>(grad8 + 2 * (size_t)gid + 1));
-            active = g0.x != 0.f || g0.y != 0.f || g0.z != 0.f || g0.w != 0.f || g1.x != 0.f || g1.y != 0.f;
+    const int first = blockIdx.x * per_cta;
+    for (int k0 = 0; k0 < per_cta; k0 += 4 * 256) {
+        int gid[4], rad[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            gid[u] = first + k0 + u * 256 + threadIdx.x;
+            rad[u] = (k0 + u * 256 < per_cta && gid[u] < n) ? __ldg(radii + gid[u]) : 0;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, active);
-        if (bal) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (active) list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)gid;
+        float4 g0[4];
+        float2 g1[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (rad[u] > 0) {
+                g0[u] = __ldg(grad8 + 2 * (size_t)gid[u]);
+                g1[u] = __ldg(reinterpret_cast<const float2*>(grad8 + 2 * (size_t)gid[u] + 1));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool active = rad[u] > 0 && (g0[u].x != 0.f || g0[u].y != 0.f || g0[u].z != 0.f || g0[u].w != 0.f ||
+                                               g1[u].x != 0.f || g1[u].y != 0.f);
+            const unsigned bal = __ballot_sync(0xffffffffu, active);
+            if (bal) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_n, (uint32_t)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (active) s_list[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)gid[u];
+            }
         }
     }
+    __syncthreads();
+    const uint32_t cnt = s_n;
+    if (cnt == 0) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(count, cnt);
+    __syncthreads();
+    const uint32_t base = s_base;
+    for (uint32_t i = threadIdx.x; i < cnt; i += 256) list[base + i] = s_list[i];
 }
 void launch_geom_compact(int n_pairs, const int* radii, const float4* grad8, uint32_t* list, uint32_t* count, const EngineCtl* ctl,
                          cudaStream_t s) {
     if (n_pairs <= 0) return;
-    int blocks = (n_pairs + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    geom_compact_kernel<<<blocks, 256, 0, s>>>(n_pairs, radii, grad8, list, count, ctl);
+    // slices of <= GC_PER_CTA pairs, at least ~4 CTAs per SM
+    int per = (n_pairs + 148 * 4 - 1) / (148 * 4);
+    per = (per + 255) / 256 * 256;
+    if (per > GC_PER_CTA) per = GC_PER_CTA;
+    const int blocks = (n_pairs + per - 1) / per;
+    geom_compact_kernel<<<blocks, 256, 0, s>>>(n_pairs, per, radii, grad8, list, count, ctl);
 }
 
 // partials[12][nblocks] -> out12, fixed summation order, double accumulation.

@@ -105,12 +105,19 @@ struct PreMapArgs {
     int* radii;               // [2P]
     uint32_t* tiles_touched;  // [2P]
     uint8_t* clamped;         // [2P]
-    uint32_t* depth_key;      // [2P] float bits of the view depth, 0xFFFFFFFF when culled
-    uint64_t* pairs;          // [2P] {packed tile rect x0 | y0<<8 | x1<<16 | y1<<24 (0 when culled)} << 32 | pair id
+    // visible pairs only, compacted in index order per view (see preprocess.cu): entries [0, *n_vis)
+    uint32_t* depth_key;      // [2P] float bits of the view depth
+    uint64_t* pairs;          // [2P] {packed tile rect x0 | y0<<8 | x1<<16 | y1<<24} << 32 | pair id (= view * P + Gaussian)
+    unsigned long long* comp_state;   // chained-scan state, preprocess_map_state_bytes(P); the last word is the tile counter
+    uint32_t* tile_counter;   // = (uint32_t*)(comp_state + number of CTAs + 1)
+    uint32_t* n_vis;          // out: number of visible pairs
+    int vis_cap;              // slots the depth sort covers: [*n_vis, vis_cap) are filled with sentinels after the projection
+    int* overflow;            // set when *n_vis > vis_cap (may be NULL)
     float4* rec;              // [2][2P]
     float4* grad8;            // [2][2P]
 };
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s);
+size_t preprocess_map_state_bytes(int P);
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s);
 void launch_pack_map(int P, int M, const float* xyz, const float* scales, const float* rots, const float* opac,
                      const float* shs, float mod, float4* xyz_opacity, float4* cov_a, float2* cov_b, float* sh_planar,
@@ -145,8 +152,32 @@ void launch_sort_pairs16(void* temp, size_t temp_bytes, const uint16_t* keys_in,
                          const uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit, cudaStream_t s);
 // offsets = inclusive sum of the tile-rect areas of `pairs` ({rect (high 32) | pair id (low 32)}), in array order
 void launch_scan_gather(void* temp, size_t temp_bytes, const uint64_t* pairs, uint32_t* offsets, int n, cudaStream_t s);
-void launch_emit_tiles(int P, int grid_x, int tiles_per_view, const uint64_t* pairs, const uint32_t* offsets, uint16_t* keys,
-                       uint32_t* values, int cap, int* overflow, const EngineCtl* ctl, cudaStream_t s);
+void launch_emit_tiles(int P, int n_pairs, int grid_x, int tiles_per_view, const uint64_t* pairs, const uint32_t* offsets,
+                       uint16_t* keys, uint32_t* values, int cap, int* overflow, const EngineCtl* ctl, cudaStream_t s);
+// ---- tile binning without instance records (tilebin.cu) ----------------------------------------
+struct TileBinArgs {
+    int P, n_pairs, grid_x, tiles_per_view;
+    const uint64_t* pairs;      // depth-sorted {rect | pair id}, n_pairs entries (sentinels with rect 0 at the end)
+    const uint32_t* offsets;    // inclusive sum of the rect areas
+    uint16_t* hist;             // [chunks][2 * tiles_per_view]
+    uint32_t* base;             // [chunks][2 * tiles_per_view]
+    uint2* chunk_pairs;         // [chunks] first / last pair of every chunk
+    uint32_t* tile_total;       // [2 * tiles_per_view]
+    uint2* ranges;              // [2 * tiles_per_view] out
+    uint32_t* values;           // [cap] out: Gaussian index per slot of the per-tile lists
+    int cap;                    // instance slots available; more live instances -> *overflow = 1, nothing written
+    int* overflow;
+    const EngineCtl* ctl;
+};
+int tilebin_chunk();
+size_t tilebin_hist_bytes(int cap, int tiles_per_view);
+size_t tilebin_base_bytes(int cap, int tiles_per_view);
+size_t tilebin_chunk_bytes(int cap);
+int tilebin_configure(int max_tiles_per_view);
+void launch_tile_count(const TileBinArgs& a, cudaStream_t s);
+void launch_tile_scan(const TileBinArgs& a, cudaStream_t s);
+void launch_tile_scatter(const TileBinArgs& a, cudaStream_t s);
+void launch_keys_from_ranges(int nt, const uint2* ranges, uint16_t* keys, cudaStream_t s);
 void launch_identify_ranges16(const uint16_t* keys, uint2* ranges, int ntiles_total, const uint32_t* n_dev, int cap,
                               cudaStream_t s);
 void launch_rebuild_keys(const uint16_t* tile_keys, const uint32_t* vals, const float4* rec_view, uint32_t tile_base,

@@ -7,6 +7,7 @@
 //                             BOTH views per thread so the 232 B/Gaussian map read happens once.
 // HBM-bound: grid = ceil(P/256) x 256 threads, all per-Gaussian loads coalesced (AoS inputs are
 // staged through shared memory in 16-byte vectors; planar SH is read as 48 coalesced lines per warp).
+#include <cstdlib>
 #include "internal.h"
 
 namespace gsevt {
@@ -135,24 +136,83 @@ void launch_preprocess_aos(const PreAosArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Engine path: packed map, two views per thread.
 // ------------------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(256, 3) preprocess_map_kernel(PreMapArgs a) {
+// Compaction of the visible (view, Gaussian) pairs, in index order, inside the projection kernel: a chained scan
+// with decoupled look-back over the CTAs' visible counts (one 64-bit state word per CTA: flag << 32 | value; flags
+// 1 = this CTA's count, 2 = inclusive prefix).  CTAs take their tile of 256 Gaussians from an atomic counter, so a
+// CTA can only wait for CTAs that already run.  Within a CTA view-0 pairs come first, then view-1 pairs, each in
+// index order: within a view the compact order is the index order — which is all the stable depth sort needs
+// to reproduce the reference's (depth, index) tie-break; pairs of different views never meet in a tile list.
+// The depth sort / scan / emission then run over ~the visible pairs instead of all 2P (and, under the screen-tile
+// split, over this rank's strip only).
+// Called by all 32 lanes of warp 0; returns (to every lane) the number of visible pairs in all lower tiles.  The
+// look-back reads 32 predecessors per step, so a CTA never walks a long chain one L2 round trip at a time.
+__device__ __forceinline__ uint32_t compact_base(unsigned long long* state, uint32_t tile, uint32_t count) {
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (tile > 0) {
+        if (lane == 0) atomicExch(state + tile, (1ull << 32) | count);
+        int t = (int)tile - 1 - lane;   // this lane's predecessor in the current window of 32
+        while (true) {
+            unsigned long long w = 2ull << 32;   // lanes before tile 0: an (empty) inclusive prefix
+            if (t >= 0) {
+                do {
+                    w = *reinterpret_cast<volatile unsigned long long*>(state + t);
+                } while ((w >> 32) == 0ull);
+            }
+            const unsigned incl = __ballot_sync(0xffffffffu, (w >> 32) == 2ull);
+            const int stop = incl ? __ffs(incl) - 1 : 31;   // nearest predecessor that already holds a prefix
+            uint32_t v = lane <= stop ? (uint32_t)w : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            base += v;
+            if (incl) break;
+            t -= 32;
+        }
+    }
+    if (lane == 0) {
+        __threadfence();
+        atomicExch(state + tile, (2ull << 32) | (unsigned long long)(base + count));
+    }
+    return base;
+}
+
+// After the projection: sentinels behind the visible pairs (key 0xFFFFFFFF sorts last, rect 0 emits nothing) so that
+// the fixed-size depth sort over `cap` slots is well defined whatever the count, and the chained-scan state back to
+// zero for the next launch.
+__global__ void __launch_bounds__(256) compact_finish_kernel(const uint32_t* __restrict__ n_vis, int cap, uint32_t* __restrict__ depth_key,
+                                                             uint64_t* __restrict__ pairs, unsigned long long* __restrict__ state,
+                                                             int state_words) {
+    const int tid = blockIdx.x * 256 + threadIdx.x, stride = gridDim.x * 256;
+    for (int i = (int)*n_vis + tid; i < cap; i += stride) {
+        depth_key[i] = 0xFFFFFFFFu;
+        pairs[i] = 0ull;
+    }
+    for (int i = tid; i < state_words; i += stride) state[i] = 0ull;
+}
+
+template <int D, int MINB>
+__global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a) {
     if (a.ctl && a.ctl->level_done) return;
     __shared__ ViewParams s_vp[2];
-    load_views(s_vp, a.views, 2);
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= a.P) return;
-    const float4 xo = __ldg(a.xyz_opacity + idx);
+    __shared__ uint32_t s_tile, s_base;
+    __shared__ uint32_t s_cnt[2][8];
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.tile_counter, 1u);
+    load_views(s_vp, a.views, 2);   // (barrier inside)
+    const uint32_t tile = s_tile;
+    const int idx = (int)tile * 256 + threadIdx.x;
+    const bool live = idx < a.P;
+    const int idc = live ? idx : a.P - 1;
+    const float4 xo = __ldg(a.xyz_opacity + idc);
     float cov[6];
     {
-        const float4 c0 = __ldg(a.cov3D_a + idx);
-        const float2 c1 = __ldg(a.cov3D_b + idx);
+        const float4 c0 = __ldg(a.cov3D_a + idc);
+        const float2 c1 = __ldg(a.cov3D_b + idc);
         cov[0] = c0.x; cov[1] = c0.y; cov[2] = c0.z; cov[3] = c0.w; cov[4] = c1.x; cov[5] = c1.y;
     }
     ProjOut o[2];
     bool ok[2];
 #pragma unroll
-    for (int v = 0; v < 2; v++) ok[v] = project_geometry(s_vp[v], xo.x, xo.y, xo.z, cov, o[v]);
+    for (int v = 0; v < 2; v++) ok[v] = project_geometry(s_vp[v], xo.x, xo.y, xo.z, cov, o[v]) && live;
     if (a.ctl) {
         // screen-tile split: keep only the part of the tile rect inside this engine's strip of tile rows
         // (the whole grid unless split, where this changes nothing)
@@ -165,65 +225,119 @@ __global__ void __launch_bounds__(256, 3) preprocess_map_kernel(PreMapArgs a) {
             o[v].rect = (r & 0x00FF00FFu) | (y0 << 8) | (y1 << 24);
         }
     }
-#pragma unroll
-    for (int v = 0; v < 2; v++) {
-        const size_t j = (size_t)v * a.P + idx;
-        a.radii[j] = ok[v] ? o[v].radius : 0;
-        a.depth_key[j] = ok[v] ? __float_as_uint(o[v].depth) : 0xFFFFFFFFu;
-        a.pairs[j] = ((uint64_t)(ok[v] ? o[v].rect : 0u) << 32) | (uint64_t)j;
+    if (live) {
+        a.radii[idx] = ok[0] ? o[0].radius : 0;
+        a.radii[(size_t)a.P + idx] = ok[1] ? o[1].radius : 0;
     }
-    if (!ok[0] && !ok[1]) return;
     // SH -> RGB for both views from ONE pass over the planar coefficients (coalesced 128-byte lines).  The degree
     // is a template parameter so that all (D+1)^2 * 3 loads are issued back to back, unconditionally.
-    const float* sh = a.sh_planar + idx;
+    const bool any_view = ok[0] || ok[1];
     const size_t P = (size_t)a.P;
     constexpr int NB = (D + 1) * (D + 1);
     float coef[NB * 3];
+    if (any_view) {
+        const float* sh = a.sh_planar + idx;
 #pragma unroll
-    for (int k = 0; k < NB * 3; k++) coef[k] = __ldg(sh + (size_t)k * P);
-    float basis[2][16];
+        for (int k = 0; k < NB * 3; k++) coef[k] = __ldg(sh + (size_t)k * P);
+    }
+    // ---- compaction: rank of this thread's pairs inside the CTA, CTA base from the chained scan — done by warp 0
+    // while the coefficient loads of the whole CTA are in flight, so the look-back latency is not exposed
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned b0 = __ballot_sync(0xffffffffu, ok[0]), b1 = __ballot_sync(0xffffffffu, ok[1]);
+    if (lane == 0) { s_cnt[0][warp] = __popc(b0); s_cnt[1][warp] = __popc(b1); }
+    __syncthreads();
+    uint32_t before[2] = {0, 0}, total[2] = {0, 0};
 #pragma unroll
-    for (int v = 0; v < 2; v++)
-        sh_basis(D, xo.x - s_vp[v].campos[0], xo.y - s_vp[v].campos[1], xo.z - s_vp[v].campos[2], basis[v]);
-    float rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-#pragma unroll
-    for (int k = 0; k < NB; k++) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            rgb[0][ch] += basis[0][k] * coef[k * 3 + ch];
-            rgb[1][ch] += basis[1][k] * coef[k * 3 + ch];
+    for (int w = 0; w < 8; w++) {
+        const uint32_t c0 = s_cnt[0][w], c1 = s_cnt[1][w];
+        if (w < warp) { before[0] += c0; before[1] += c1; }
+        total[0] += c0; total[1] += c1;
+    }
+    if (warp == 0) {
+        const uint32_t count = total[0] + total[1];
+        const uint32_t base = compact_base(a.comp_state, tile, count);
+        if (lane == 0) {
+            s_base = base;
+            if (tile == gridDim.x - 1) {
+                // all pairs counted: publish the total, check it against the slots the depth sort covers
+                const uint32_t n_vis = base + count;
+                *a.n_vis = n_vis;
+                if (a.overflow && n_vis > (uint32_t)a.vis_cap) *a.overflow = 1;
+            }
         }
     }
+    if (any_view) {
+        float basis[2][16];
 #pragma unroll
-    for (int v = 0; v < 2; v++) {
-        if (!ok[v]) continue;
-        unsigned clampbits = 0;
+        for (int v = 0; v < 2; v++)
+            sh_basis(D, xo.x - s_vp[v].campos[0], xo.y - s_vp[v].campos[1], xo.z - s_vp[v].campos[2], basis[v]);
+        float rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            const float c = rgb[v][ch] + 0.5f;
-            if (c < 0.0f) clampbits |= 1u << ch;
-            rgb[v][ch] = fmaxf(c, 0.0f);
+        for (int k = 0; k < NB; k++) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                rgb[0][ch] += basis[0][k] * coef[k * 3 + ch];
+                rgb[1][ch] += basis[1][k] * coef[k * 3 + ch];
+            }
         }
-        const float gray = GSEVT_GRAY_R * rgb[v][0] + GSEVT_GRAY_G * rgb[v][1] + GSEVT_GRAY_B * rgb[v][2];
-        const size_t j = (size_t)v * P + idx;
-        a.clamped[j] = (uint8_t)clampbits;
-        a.rec[2 * j] = make_float4(o[v].mx, o[v].my, o[v].A, o[v].B);
-        a.rec[2 * j + 1] = make_float4(o[v].C, xo.w, gray, o[v].depth);
-        // zero the blend-backward accumulators of every Gaussian that can receive a gradient
-        a.grad8[2 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        a.grad8[2 * j + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            if (!ok[v]) continue;
+            unsigned clampbits = 0;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                const float c = rgb[v][ch] + 0.5f;
+                if (c < 0.0f) clampbits |= 1u << ch;
+                rgb[v][ch] = fmaxf(c, 0.0f);
+            }
+            const float gray = GSEVT_GRAY_R * rgb[v][0] + GSEVT_GRAY_G * rgb[v][1] + GSEVT_GRAY_B * rgb[v][2];
+            const size_t j = (size_t)v * P + idx;
+            a.clamped[j] = (uint8_t)clampbits;
+            a.rec[2 * j] = make_float4(o[v].mx, o[v].my, o[v].A, o[v].B);
+            a.rec[2 * j + 1] = make_float4(o[v].C, xo.w, gray, o[v].depth);
+            // (the blend-backward accumulators grad8 are all-zero here: geom_bwd clears what it consumes)
+        }
+    }
+    __syncthreads();
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t slot[2] = {s_base + before[0] + __popc(b0 & lt), s_base + total[0] + before[1] + __popc(b1 & lt)};
+    if (live) {
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            const size_t j = (size_t)v * a.P + idx;
+            if (ok[v]) {
+                a.depth_key[slot[v]] = __float_as_uint(o[v].depth);
+                a.pairs[slot[v]] = ((uint64_t)o[v].rect << 32) | (uint64_t)j;
+            }
+        }
     }
 }
+
+size_t preprocess_map_state_bytes(int P) { return ((size_t)(P + 255) / 256 + 2) * sizeof(unsigned long long); }
 
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
     const int blocks = (a.P + 255) / 256;
-    switch (a.D) {
-        case 0: preprocess_map_kernel<0><<<blocks, 256, 0, s>>>(a); break;
-        case 1: preprocess_map_kernel<1><<<blocks, 256, 0, s>>>(a); break;
-        case 2: preprocess_map_kernel<2><<<blocks, 256, 0, s>>>(a); break;
-        default: preprocess_map_kernel<3><<<blocks, 256, 0, s>>>(a); break;
+    // comp_state (chained-scan words + tile counter) is zero on entry: zeroed at allocation and by every finish kernel
+    // GSEVT_PRE_MINB=3: 80 registers (88 B of spills at SH degree 3), three CTAs per SM; default 2: 105 registers, no spills
+    static const int minb = [] { const char* v = getenv("GSEVT_PRE_MINB"); return v && atoi(v) == 3 ? 3 : 2; }();
+    if (minb == 3) {
+        switch (a.D) {
+            case 0: preprocess_map_kernel<0, 3><<<blocks, 256, 0, s>>>(a); break;
+            case 1: preprocess_map_kernel<1, 3><<<blocks, 256, 0, s>>>(a); break;
+            case 2: preprocess_map_kernel<2, 3><<<blocks, 256, 0, s>>>(a); break;
+            default: preprocess_map_kernel<3, 3><<<blocks, 256, 0, s>>>(a); break;
+        }
+    } else {
+        switch (a.D) {
+            case 0: preprocess_map_kernel<0, 2><<<blocks, 256, 0, s>>>(a); break;
+            case 1: preprocess_map_kernel<1, 2><<<blocks, 256, 0, s>>>(a); break;
+            case 2: preprocess_map_kernel<2, 2><<<blocks, 256, 0, s>>>(a); break;
+            default: preprocess_map_kernel<3, 2><<<blocks, 256, 0, s>>>(a); break;
+        }
     }
+    compact_finish_kernel<<<148, 256, 0, s>>>(a.n_vis, a.vis_cap, a.depth_key, a.pairs, a.comp_state,
+                                              (int)(preprocess_map_state_bytes(a.P) / sizeof(unsigned long long)));
 }
 
 // checkFrustum (rasterizer_impl.cu:54-66)

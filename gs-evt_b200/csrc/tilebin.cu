@@ -1,0 +1,387 @@
+// Tile binning of the engine path: from the depth-sorted (view, Gaussian) pairs straight to the per-tile lists.
+//
+// What it replaces.  The reference writes one (tile << 32 | depth, id) record per tile instance and radix-sorts
+// all of them (rasterizer_impl.cu:70-111, 303-311), then finds the tile boundaries in the sorted keys (:116-138).
+// The order inside a tile is (depth bits, Gaussian index).  The engine already holds the pairs in exactly that
+// order (stable depth sort of the index-ordered compact list, binning.cu), so the per-tile lists are a STABLE
+// PARTITION of the instance sequence by tile id — a one-pass counting sort over <= 65535 bins — and the instance
+// records never have to exist in memory:
+//
+//   tile_count    chunk c = instances [c*CH, (c+1)*CH) of the sequence, regenerated from the pairs' tile rects;
+//                 counts per (chunk, tile) in shared memory -> hist[c][tile] (u16)
+//   tile_scan     per tile: exclusive prefix of the counts over the chunks -> base[c][tile]; totals per tile
+//   tile_starts   exclusive prefix of the totals over the tiles -> ranges[tile] (untouched tiles stay (0,0) as in
+//                 the reference)
+//   tile_scatter  chunk c again: every instance gets slot ranges[tile].x + base[c][tile] + (its rank among the
+//                 chunk's earlier instances of the same tile) and stores its Gaussian index there.
+//
+// Stability inside a chunk: the chunk is cut into 8 slices in sequence order, one per warp; a first pass counts per
+// (slice, tile), the prefix over the slices gives every warp its own cursor per tile, and each warp then walks its
+// slice in order, 32 instances per step, ranking equal tiles inside a step with match.any (lower lane = earlier
+// instance).  Traffic: the pairs twice (12 B each), hist/base once each way, 4 B per instance out — against
+// (6 B + 2 x 12 B + 2 B) per instance for emit + two radix passes + range scan.
+#include "internal.h"
+
+namespace gsevt {
+
+namespace {
+
+constexpr int TB_THREADS = 256;
+constexpr int TB_IPT = 16;                        // instances per thread
+constexpr int TB_CH = TB_THREADS * TB_IPT;        // instances per chunk (4096)
+constexpr int TB_SLICE = TB_CH / 8;               // instances per warp slice
+
+__device__ __forceinline__ uint32_t rect_area_d(uint32_t r) {
+    return ((r >> 16 & 255u) - (r & 255u)) * ((r >> 24) - (r >> 8 & 255u));
+}
+
+// First index p in [0, n) with off[p] > o, for a non-decreasing off[] with off[n-1] > o.  All 32 lanes call it;
+// every round probes 32 positions, so the depth is log32(n) dependent loads instead of log2(n).
+__device__ __forceinline__ uint32_t upper_bound_warp(const uint32_t* __restrict__ off, uint32_t n, uint32_t o) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t lo = 0, len = n;
+    while (len > 1) {
+        const uint32_t step = (len + 31u) / 32u;
+        const uint32_t last = lo + len - 1u;
+        uint32_t idx = lo + (lane + 1u) * step - 1u;
+        if (idx > last) idx = last;
+        const unsigned b = __ballot_sync(0xffffffffu, __ldg(off + idx) > o);   // monotone in the lane; lane 31 is true
+        const uint32_t L = (uint32_t)__ffs(b) - 1u;
+        const uint32_t nlo = lo + L * step;
+        uint32_t nhi = nlo + step - 1u;
+        if (nhi > last) nhi = last;
+        lo = nlo;
+        len = nhi - nlo + 1u;
+    }
+    return lo;
+}
+
+// Pair range [p_lo, p_hi] whose instances intersect [begin, end), into shared memory (warps 0 and 1 search).
+__device__ __forceinline__ void chunk_pair_range(const uint32_t* __restrict__ off, uint32_t n, uint32_t begin, uint32_t end,
+                                                 uint32_t* s_p) {
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        const uint32_t p = upper_bound_warp(off, n, begin);
+        if ((threadIdx.x & 31) == 0) s_p[0] = p;
+    } else if (warp == 1) {
+        const uint32_t p = upper_bound_warp(off, n, end - 1u);
+        if ((threadIdx.x & 31) == 0) s_p[1] = p;
+    }
+}
+
+// One pair's share of a chunk: instances t in [t0, t1) of its rect (row-major), the first at local index excl - begin.
+struct PairWork { uint32_t excl, t0, t1, tbase, wd, id; };
+
+__device__ __forceinline__ PairWork load_pair(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ off, uint32_t p,
+                                              uint32_t p_hi, uint32_t begin, uint32_t end, int P, int gx, int tiles_per_view) {
+    PairWork w = {0u, 0u, 0u, 0u, 1u, 0u};
+    if (p <= p_hi) {
+        const uint64_t pr = __ldg(pairs + p);
+        const uint32_t rect = (uint32_t)(pr >> 32);
+        const uint32_t incl = __ldg(off + p);
+        w.id = (uint32_t)pr >= (uint32_t)P ? (uint32_t)pr - (uint32_t)P : (uint32_t)pr;
+        w.excl = incl - rect_area_d(rect);
+        w.t0 = (w.excl > begin ? w.excl : begin) - w.excl;
+        w.t1 = (incl < end ? incl : end) - w.excl;
+        if (w.t1 < w.t0) w.t1 = w.t0;
+        w.wd = (rect >> 16 & 255u) - (rect & 255u);
+        w.tbase = ((uint32_t)pr >= (uint32_t)P ? (uint32_t)tiles_per_view : 0u) + (rect >> 8 & 255u) * (uint32_t)gx + (rect & 255u);
+    }
+    return w;
+}
+
+// Visits every instance of the warp's 32 pairs: f(local_instance, tile, Gaussian).  A lane walks its own rect when it
+// has at most TB_SMALL instances in the chunk; larger ones are walked by the whole warp, 32 instances per step, so no
+// lane ever loops over a screen-filling Gaussian alone.
+constexpr uint32_t TB_SMALL = 12;
+template <typename F>
+__device__ __forceinline__ void visit_pair(const PairWork& w, uint32_t begin, int gx, F f) {
+    const bool big = w.t1 - w.t0 > TB_SMALL;
+    if (!big && w.t1 > w.t0) {
+        uint32_t ty = w.t0 / w.wd, tx = w.t0 - ty * w.wd;
+        for (uint32_t t = w.t0; t < w.t1; t++) {
+            f(w.excl + t - begin, w.tbase + ty * (uint32_t)gx + tx, w.id);
+            if (++tx == w.wd) { tx = 0; ty++; }
+        }
+    }
+    unsigned bigs = __ballot_sync(0xffffffffu, big);
+    const uint32_t lane = threadIdx.x & 31u;
+    while (bigs) {
+        const int src = __ffs(bigs) - 1;
+        bigs &= bigs - 1;
+        const uint32_t b_t0 = __shfl_sync(0xffffffffu, w.t0, src), b_t1 = __shfl_sync(0xffffffffu, w.t1, src);
+        const uint32_t b_excl = __shfl_sync(0xffffffffu, w.excl, src), b_wd = __shfl_sync(0xffffffffu, w.wd, src);
+        const uint32_t b_tbase = __shfl_sync(0xffffffffu, w.tbase, src), b_id = __shfl_sync(0xffffffffu, w.id, src);
+        const float rcpw = 1.0f / (float)b_wd;
+        for (uint32_t t = b_t0 + lane; t < b_t1; t += 32u) {
+            const uint32_t ty = (uint32_t)(((float)t + 0.5f) * rcpw);   // exact: t < 65536, wd <= 255
+            const uint32_t tx = t - ty * b_wd;
+            f(b_excl + t - begin, b_tbase + ty * (uint32_t)gx + tx, b_id);
+        }
+    }
+}
+
+// All pairs [p_lo, p_hi] of a chunk, 256 per round, four rounds' loads in flight together.
+template <typename F>
+__device__ __forceinline__ void visit_chunk(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ off, uint32_t p_lo,
+                                            uint32_t p_hi, uint32_t begin, uint32_t end, int P, int gx, int tiles_per_view, F f) {
+    for (uint32_t p0 = p_lo; p0 <= p_hi; p0 += 4u * TB_THREADS) {
+        PairWork w[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            w[u] = load_pair(pairs, off, p0 + (uint32_t)u * TB_THREADS + threadIdx.x, p_hi, begin, end, P, gx, tiles_per_view);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (p0 + (uint32_t)u * TB_THREADS > p_hi) break;   // uniform
+            visit_pair(w[u], begin, gx, f);
+        }
+    }
+}
+
+}  // namespace
+
+// ---- 1. counts per (chunk, tile) ------------------------------------------------------------------
+__global__ void __launch_bounds__(TB_THREADS) tile_count_kernel(int P, int n_pairs, int gx, int tiles_per_view,
+                                                                 const uint64_t* __restrict__ pairs,
+                                                                 const uint32_t* __restrict__ off, uint16_t* __restrict__ hist,
+                                                                 uint2* __restrict__ chunk_pairs, int cap, int* __restrict__ overflow,
+                                                                 const EngineCtl* __restrict__ ctl) {
+    if (ctl && ctl->level_done) return;
+    extern __shared__ uint32_t s_hist[];   // [2 * tiles_per_view]
+    __shared__ uint32_t s_p[2];
+    const uint32_t total = __ldg(off + n_pairs - 1);
+    if (total > (uint32_t)cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+        return;
+    }
+    const uint32_t begin = blockIdx.x * (uint32_t)TB_CH;
+    if (begin >= total) return;
+    const uint32_t end = begin + TB_CH < total ? begin + TB_CH : total;
+    const int nt = 2 * tiles_per_view;
+    for (int t = threadIdx.x; t < nt; t += TB_THREADS) s_hist[t] = 0;
+    chunk_pair_range(off, (uint32_t)n_pairs, begin, end, s_p);
+    __syncthreads();
+    const uint32_t p_lo = s_p[0], p_hi = s_p[1];
+    if (threadIdx.x == 0) chunk_pairs[blockIdx.x] = make_uint2(p_lo, p_hi);
+    visit_chunk(pairs, off, p_lo, p_hi, begin, end, P, gx, tiles_per_view,
+                [&](uint32_t, uint32_t tile, uint32_t) { atomicAdd(&s_hist[tile], 1u); });
+    __syncthreads();
+    uint16_t* row = hist + (size_t)blockIdx.x * nt;
+    for (int t = threadIdx.x; t < nt; t += TB_THREADS) row[t] = (uint16_t)s_hist[t];
+}
+
+// ---- 2. prefix over the chunks, per tile ----------------------------------------------------------
+// CTA = 16 tile columns (one 32-byte sector per hist row) x 64 row groups: thread (col, g) loads its rows into shared
+// memory (all loads independent, in flight together) and sums them, the groups are scanned through shared memory, then
+// every thread re-walks its rows from shared memory writing the running prefix.  150 CTAs for 2 x 1200 tiles.
+constexpr int TS_COLS = 16, TS_GROUPS = 64;
+__global__ void __launch_bounds__(TS_COLS * TS_GROUPS) tile_scan_kernel(int nt, const uint32_t* __restrict__ total_dev, int cap,
+                                                                         const uint16_t* __restrict__ hist,
+                                                                         uint32_t* __restrict__ base,
+                                                                         uint32_t* __restrict__ tile_total, int rows_cached,
+                                                                         const EngineCtl* __restrict__ ctl) {
+    if (ctl && ctl->level_done) return;
+    extern __shared__ uint16_t s_rows[];                 // [rows_cached][TS_COLS]
+    __shared__ uint32_t s_part[TS_GROUPS][TS_COLS + 1];
+    const uint32_t total = *total_dev;
+    const int col = threadIdx.x & (TS_COLS - 1), g = threadIdx.x / TS_COLS;
+    const int tile = blockIdx.x * TS_COLS + col;
+    const int nact = total > (uint32_t)cap ? 0 : (int)((total + TB_CH - 1) / TB_CH);
+    const int R = (nact + TS_GROUPS - 1) / TS_GROUPS;
+    const int r0 = g * R, r1 = min(r0 + R, nact);
+    uint32_t sum = 0;
+    if (tile < nt) {
+#pragma unroll 8
+        for (int r = r0; r < r1; r++) {
+            const uint16_t v = __ldg(hist + (size_t)r * nt + tile);
+            if (r < rows_cached) s_rows[r * TS_COLS + col] = v;
+            sum += v;
+        }
+    }
+    s_part[g][col] = sum;
+    __syncthreads();
+    if (g == 0) {
+        uint32_t run = 0;
+#pragma unroll 8
+        for (int k = 0; k < TS_GROUPS; k++) {
+            const uint32_t v = s_part[k][col];
+            s_part[k][col] = run;
+            run += v;
+        }
+        if (tile < nt) tile_total[tile] = run;
+    }
+    __syncthreads();
+    if (tile < nt) {
+        uint32_t run = s_part[g][col];
+        for (int r = r0; r < r1; r++) {
+            const size_t i = (size_t)r * nt + tile;
+            base[i] = run;
+            run += r < rows_cached ? s_rows[r * TS_COLS + col] : __ldg(hist + i);
+        }
+    }
+}
+
+// ---- 3. prefix over the tiles: the tile ranges ----------------------------------------------------
+__global__ void __launch_bounds__(1024) tile_starts_kernel(int nt, const uint32_t* __restrict__ tile_total,
+                                                            uint2* __restrict__ ranges, const EngineCtl* __restrict__ ctl) {
+    if (ctl && ctl->level_done) return;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < nt; t0 += 1024) {
+        const int t = t0 + threadIdx.x;
+        const uint32_t v = t < nt ? tile_total[t] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], xs = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+                if (lane >= o) xs += y;
+            }
+            s_warp[lane] = xs - w;   // exclusive
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t start = carry + s_warp[warp] + x - v;
+        if (t < nt) ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = start + v;
+        __syncthreads();
+    }
+}
+
+// ---- 4. stable scatter ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(int P, int n_pairs, int gx, int tiles_per_view,
+                                                                   const uint64_t* __restrict__ pairs,
+                                                                   const uint32_t* __restrict__ off,
+                                                                   const uint2* __restrict__ chunk_pairs,
+                                                                   const uint32_t* __restrict__ base,
+                                                                   const uint2* __restrict__ ranges, uint32_t* __restrict__ values,
+                                                                   int cap, const EngineCtl* __restrict__ ctl) {
+    if (ctl && ctl->level_done) return;
+    extern __shared__ uint32_t s_mem[];
+    const int nt = 2 * tiles_per_view;
+    uint32_t* s_gbase = s_mem;                 // [nt]    first slot of (this chunk, tile)
+    uint32_t* s_cnt = s_mem + nt;              // [4][nt] per-slice counts, then cursors: slice w in word w & 3, half w >> 2
+    __shared__ uint16_t s_tile[TB_CH];         // tile id of every instance of the chunk
+    __shared__ uint32_t s_id[TB_CH];           // Gaussian index of every instance of the chunk
+    const uint32_t total = __ldg(off + n_pairs - 1);
+    if (total > (uint32_t)cap) return;         // flagged by tile_count_kernel: the iteration is void
+    const uint32_t begin = blockIdx.x * (uint32_t)TB_CH;
+    if (begin >= total) return;
+    const uint32_t end = begin + TB_CH < total ? begin + TB_CH : total;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t* brow = base + (size_t)blockIdx.x * nt;
+    for (int t = threadIdx.x; t < nt; t += TB_THREADS) {
+        s_gbase[t] = __ldg(&ranges[t].x) + __ldg(brow + t);
+        s_cnt[t] = 0; s_cnt[nt + t] = 0; s_cnt[2 * nt + t] = 0; s_cnt[3 * nt + t] = 0;
+    }
+    const uint2 pr = chunk_pairs[blockIdx.x];
+    __syncthreads();
+    // regenerate the chunk's instances: (tile, id) per local instance index, plus the per-slice counts
+    visit_chunk(pairs, off, pr.x, pr.y, begin, end, P, gx, tiles_per_view, [&](uint32_t li, uint32_t tile, uint32_t id) {
+        s_tile[li] = (uint16_t)tile;
+        s_id[li] = id;
+        const uint32_t slice = li / TB_SLICE;
+        atomicAdd(&s_cnt[(slice & 3u) * nt + tile], 1u << (16u * (slice >> 2)));
+    });
+    __syncthreads();
+    // counts -> exclusive prefix over the 8 slices, in place
+    for (int t = threadIdx.x; t < nt; t += TB_THREADS) {
+        uint32_t w[4] = {s_cnt[t], s_cnt[nt + t], s_cnt[2 * nt + t], s_cnt[3 * nt + t]};
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const uint32_t c = w[k] & 0xFFFFu; w[k] = (w[k] & 0xFFFF0000u) | run; run += c; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const uint32_t c = w[k] >> 16; w[k] = (w[k] & 0xFFFFu) | (run << 16); run += c; }
+        s_cnt[t] = w[0]; s_cnt[nt + t] = w[1]; s_cnt[2 * nt + t] = w[2]; s_cnt[3 * nt + t] = w[3];
+    }
+    __syncthreads();
+    // every warp walks its slice in order
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t shift = 16u * (uint32_t)(warp >> 2);
+    uint32_t* my_cnt = s_cnt + (warp & 3) * nt;
+    const uint32_t n_local = end - begin;
+#pragma unroll 4
+    for (int st = 0; st < TB_SLICE / 32; st++) {
+        const uint32_t li = (uint32_t)warp * TB_SLICE + (uint32_t)st * 32u + (uint32_t)lane;
+        const bool valid = li < n_local;
+        if (!__any_sync(0xffffffffu, valid)) break;
+        const uint32_t tile = valid ? (uint32_t)s_tile[li] : 0xFFFFFFFFu;
+        const unsigned m = __match_any_sync(0xffffffffu, tile);
+        const int leader = __ffs(m) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) old = atomicAdd(&my_cnt[tile], (uint32_t)__popc(m) << shift);
+        old = __shfl_sync(0xffffffffu, old, leader);
+        if (valid) {
+            const uint32_t pos = s_gbase[tile] + ((old >> shift) & 0xFFFFu) + (uint32_t)__popc(m & lt);
+            values[pos] = s_id[li];
+        }
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+int tilebin_chunk() { return TB_CH; }
+size_t tilebin_hist_bytes(int cap, int tiles_per_view) {
+    return (size_t)((cap + TB_CH - 1) / TB_CH) * 2 * (size_t)tiles_per_view * sizeof(uint16_t);
+}
+size_t tilebin_base_bytes(int cap, int tiles_per_view) {
+    return (size_t)((cap + TB_CH - 1) / TB_CH) * 2 * (size_t)tiles_per_view * sizeof(uint32_t);
+}
+size_t tilebin_chunk_bytes(int cap) { return (size_t)((cap + TB_CH - 1) / TB_CH) * sizeof(uint2); }
+
+int tilebin_configure(int max_tiles_per_view) {
+    const size_t smem = (size_t)2 * max_tiles_per_view * 5 * sizeof(uint32_t);
+    if (smem + TB_CH * 6 + 64 > 227 * 1024) return -1;
+    cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * max_tiles_per_view * 4));
+    cudaFuncSetAttribute(tile_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * TS_COLS * 2);
+    return 0;
+}
+
+void launch_tile_count(const TileBinArgs& a, cudaStream_t s) {
+    const int chunks = (a.cap + TB_CH - 1) / TB_CH;
+    if (chunks <= 0 || a.n_pairs <= 0) return;
+    tile_count_kernel<<<chunks, TB_THREADS, (size_t)2 * a.tiles_per_view * 4, s>>>(
+        a.P, a.n_pairs, a.grid_x, a.tiles_per_view, a.pairs, a.offsets, a.hist, a.chunk_pairs, a.cap, a.overflow, a.ctl);
+}
+void launch_tile_scan(const TileBinArgs& a, cudaStream_t s) {
+    const int nt = 2 * a.tiles_per_view;
+    if (a.n_pairs <= 0) return;
+    const int chunks = (a.cap + TB_CH - 1) / TB_CH;
+    const int rows_cached = chunks < 4096 ? chunks : 4096;   // 32 B per cached row: <= 128 KB
+    tile_scan_kernel<<<(nt + TS_COLS - 1) / TS_COLS, TS_COLS * TS_GROUPS, (size_t)rows_cached * TS_COLS * 2, s>>>(
+        nt, a.offsets + (a.n_pairs - 1), a.cap, a.hist, a.base, a.tile_total, rows_cached, a.ctl);
+    tile_starts_kernel<<<1, 1024, 0, s>>>(nt, a.tile_total, a.ranges, a.ctl);
+}
+void launch_tile_scatter(const TileBinArgs& a, cudaStream_t s) {
+    const int chunks = (a.cap + TB_CH - 1) / TB_CH;
+    if (chunks <= 0 || a.n_pairs <= 0) return;
+    tile_scatter_kernel<<<chunks, TB_THREADS, (size_t)2 * a.tiles_per_view * 5 * 4, s>>>(
+        a.P, a.n_pairs, a.grid_x, a.tiles_per_view, a.pairs, a.offsets, a.chunk_pairs, a.base, a.ranges, a.values, a.cap, a.ctl);
+}
+
+// Parity-test helper: tile id of every slot of the per-tile lists (what the sorted keys of the reference hold in
+// their high word), from the ranges.
+__global__ void keys_from_ranges_kernel(int nt, const uint2* __restrict__ ranges, uint16_t* __restrict__ keys) {
+    const int t = blockIdx.x;
+    if (t >= nt) return;
+    const uint2 r = ranges[t];
+    for (uint32_t i = r.x + threadIdx.x; i < r.y; i += blockDim.x) keys[i] = (uint16_t)t;
+}
+void launch_keys_from_ranges(int nt, const uint2* ranges, uint16_t* keys, cudaStream_t s) {
+    if (nt <= 0) return;
+    keys_from_ranges_kernel<<<nt, 128, 0, s>>>(nt, ranges, keys);
+}
+
+}  // namespace gsevt

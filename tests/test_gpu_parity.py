@@ -469,11 +469,30 @@ def test_engine_iterations_match_reference_pipeline(built, cuda_dev, tmp_path):
     # of two correct implementations drift by more than rounding; the gate is on the pose)
     assert np.abs(losses[0] - ref["loss_L2_0"]).max() < 2e-3 and np.abs(losses[1] - ref["loss_L0_1"]).max() < 5e-3
     Rm, T = states[-1][:9].reshape(3, 3), states[-1][9:12]
-    assert np.abs(T - ref["T"]).max() < 1e-3, "translation within 1 mm"
     dR = Rm.astype(np.float64) @ ref["R"].astype(np.float64).T
     ang = np.degrees(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))
-    assert ang < 0.05, "rotation within 0.05 deg"
     print("trajectory parity: dT max %.2e m, dR %.4f deg, loss %.5f vs %.5f" % (np.abs(T - ref["T"]).max(), ang, losses[1][-1], ref["loss_L0_1"][-1]))
+    # how the two free-running trajectories separate, next to the reference against a second run of ITSELF (its
+    # backward accumulates with float atomics, so it is not bit-reproducible either)
+    out2 = str(tmp_path / "out2.npz")
+    subprocess.run([sys.executable, os.path.join(H.ROOT, "oracle", "ref_runner.py"), "iterations", "--inp", inp, "--out", out2],
+                   check=True, timeout=900)
+    ref2 = np.load(out2)
+
+    def separation(a, b):
+        dT = np.abs(a[:, 9:12] - b[:, 9:12]).max(1)
+        Ra, Rb = a[:, :9].reshape(-1, 3, 3).astype(np.float64), b[:, :9].reshape(-1, 3, 3).astype(np.float64)
+        tr = np.einsum("kij,kij->k", Ra, Rb)
+        return dT, np.degrees(np.arccos(np.clip((tr - 1) / 2, -1, 1)))
+
+    ks = [0, 5, 11, 21, 31, 41, 51, 61, 71]
+    dT_or, dR_or = separation(states, ref["states"])
+    dT_rr, dR_rr = separation(ref2["states"], ref["states"])
+    print("separation at iterations", ks)
+    print("  ours vs ref  dT", ["%.1e" % dT_or[k] for k in ks], "dR", ["%.4f" % dR_or[k] for k in ks])
+    print("  ref  vs ref  dT", ["%.1e" % dT_rr[k] for k in ks], "dR", ["%.4f" % dR_rr[k] for k in ks])
+    assert np.abs(T - ref["T"]).max() < 1e-3, "translation within 1 mm"
+    assert ang < 0.05, "rotation within 0.05 deg"
 
 
 # ---- full-size, size-independent properties (BASELINE.json sizes) ----------------------------------------

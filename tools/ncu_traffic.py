@@ -15,7 +15,9 @@ import json
 import os
 
 STAGE_OF = [  # (substring of the kernel name, stage); CUB kernels are attributed by position, see below
-    ("preprocess_map_kernel", "preprocess_map"), ("emit_tiles_kernel", "emit_tiles"), ("identify_ranges16_kernel", "identify_ranges"),
+    ("preprocess_map_kernel", "preprocess_map"), ("compact_finish_kernel", "preprocess_map"),
+    ("tile_count_kernel", "tile_count"), ("tile_scan_kernel", "tile_scan"), ("tile_starts_kernel", "tile_scan"),
+    ("tile_scatter_kernel", "tile_scatter"),
     ("blend_fwd_kernel", "blend_fwd_gray"), ("loss_stats_kernel", "loss_stats"), ("blend_bwd_kernel", "blend_bwd_gray"),
     ("geom_compact_kernel", "geom_bwd_pose"), ("geom_bwd_kernel", "geom_bwd_pose"), ("engine_update_kernel", "engine_update"),
     ("depth_sort_", "depth_sort"), ("tile_sort_", "tile_sort"), ("tile_bin_", "tile_sort"),
@@ -42,7 +44,7 @@ def main():
             if "DeviceScan" in name:
                 stage = "scan(cub)"
             elif "RadixSort" in name:
-                stage = "depth_sort(cub)" if after == "preprocess_map" else "tile_sort(cub)"
+                stage = "depth_sort(cub)"
         if stage is None:
             continue
         if "cub::" not in name:
@@ -50,7 +52,7 @@ def main():
         b = float(row[r]) * sr + float(row[w]) * sw
         per[stage][0] += b
         per[stage][1] += float(row[t])
-        if "preprocess_map_kernel" in name or stage == "preprocess_map":
+        if "preprocess_map_kernel" in name:
             seen_in_iter["iters"] += 1
     iters = max(1, seen_in_iter["iters"])
     out = {"source": os.path.basename(a.raw_csv), "iterations_captured": iters,
