@@ -399,8 +399,8 @@ struct GsevtEngine {
     float* bg3 = nullptr;
     float4* rec = nullptr;
     float4* grad8 = nullptr;
-    int* radii = nullptr;
-    uint32_t* tiles = nullptr;
+    uint32_t* rect_raw = nullptr;        // [padded 2P] tile rect per (view, Gaussian), 0 = not visible
+    uint32_t* depth_raw = nullptr;       // [padded 2P] depth bits per (view, Gaussian)
     uint32_t* offsets = nullptr;
     uint8_t* clamped = nullptr;
     uint32_t* active_list = nullptr;   // [2P] compacted pairs with a gradient
@@ -523,10 +523,9 @@ static PreMapArgs premap_args(GsevtEngine* e, int vis_cap) {
     PreMapArgs pa;
     pa.P = m->P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
     pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
-    pa.radii = e->radii; pa.tiles_touched = e->tiles; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.pairs = e->pairs;
+    pa.rect_raw = e->rect_raw; pa.depth_raw = e->depth_raw; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.pairs = e->pairs;
     pa.rec = e->rec; pa.grad8 = e->grad8;
     pa.comp_state = e->comp_state;
-    pa.tile_counter = reinterpret_cast<uint32_t*>(e->comp_state + (m->P + 255) / 256);
     pa.n_vis = e->n_vis; pa.vis_cap = vis_cap; pa.overflow = e->overflow;
     return pa;
 }
@@ -554,7 +553,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     const int nv = e->vis_cap;   // pairs sorted / scanned / emitted: the visible ones + sentinel slack
     launch_sort_pairs32(e->sortA_temp, e->sortA_bytes, e->depth_key, e->depth_sorted, e->pairs, e->pairs_sorted, nv, s);
     mark();
-    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs_sorted, e->offsets, nv, s);
+    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs_sorted, e->n_vis, e->offsets, nv, s);
     mark();
     const int tiles = L.gx * L.gy;
     TileBinArgs tb;
@@ -597,10 +596,10 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     mark();
     GeomBwdArgs q;
     memset(&q, 0, sizeof(q));
-    q.P = P; q.D = m->D; q.M = 16; q.nviews = 2; q.views = e->views; q.radii = e->radii; q.clamped = e->clamped;
+    q.P = P; q.D = m->D; q.M = 16; q.nviews = 2; q.views = e->views; q.radii = nullptr; q.clamped = e->clamped;
     q.grad8 = e->grad8; q.active_list = e->active_list; q.active_count = e->active_count; q.xyz_opacity = m->xyz_opacity; q.cov3D_a = m->cov_a; q.cov3D_b = m->cov_b;
     q.sh_planar = m->sh_planar; q.sh_aos = m->sh_aos; q.ctl = e->ctl; q.partials = e->geom_partials;
-    launch_geom_compact(2 * P, e->radii, e->grad8, e->active_list, e->active_count, e->ctl, s);
+    launch_geom_compact(2 * P, e->rect_raw, e->grad8, e->active_list, e->active_count, e->ctl, s);
     launch_geom_bwd_map(q, s);
     mark();
     launch_engine_update(e->ctl, e->geom_partials, e->geom_blocks, e->host_flag_dev, e->overflow, e->views, e->bg3, e->comm, s);
@@ -711,8 +710,8 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->bg3, 4);
     rc |= dev_alloc(e, &e->rec, 2 * p2);
     rc |= dev_alloc(e, &e->grad8, 2 * p2);
-    rc |= dev_alloc(e, &e->radii, p2);
-    rc |= dev_alloc(e, &e->tiles, p2);
+    rc |= dev_alloc(e, &e->rect_raw, preprocess_map_raw_items(P));
+    rc |= dev_alloc(e, &e->depth_raw, preprocess_map_raw_items(P));
     rc |= dev_alloc(e, &e->offsets, p2);
     rc |= dev_alloc(e, &e->clamped, p2);
     rc |= dev_alloc(e, &e->active_list, p2);
@@ -761,10 +760,11 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     float bg[4] = {cfg->background[0], cfg->background[1], cfg->background[2], 0.f};
     cudaMemcpy(e->bg3, bg, sizeof(bg), cudaMemcpyHostToDevice);
     cudaMemset(e->overflow, 0, 4);
-    cudaMemset(e->comp_state, 0, preprocess_map_state_bytes(P));   // every later launch leaves it zeroed (compact_finish_kernel)
+    cudaMemset(e->comp_state, 0, preprocess_map_state_bytes(P));   // epoch 0: nothing published (compact_pairs_kernel)
     cudaMemset(e->loss_partials, 0, ((size_t)e->loss_nb * 3 + 2) * 8);
     cudaMemset(e->grad8, 0, 2 * p2 * 16);
-    cudaMemset(e->radii, 0, p2 * 4);
+    cudaMemset(e->rect_raw, 0, preprocess_map_raw_items(P) * 4);
+    cudaMemset(e->depth_raw, 0, preprocess_map_raw_items(P) * 4);
     cudaDeviceSynchronize();
     if (cudaGetLastError() != cudaSuccess) { set_error("engine init failed"); gsevt_engine_destroy(e); return GSEVT_ECUDA; }
     *out = e;
@@ -827,7 +827,7 @@ static int probe_instances(GsevtEngine* e, cudaStream_t s, uint32_t* total, uint
     PreMapArgs pa = premap_args(e, n2);   // no bound on the count
     pa.overflow = nullptr;
     launch_preprocess_map(pa, s);
-    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs, e->offsets, n2, s);   // projection order: only the total matters here
+    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs, e->n_vis, e->offsets, n2, s);   // projection order: only the total matters here
     uint32_t h[2] = {0, 0};
     GSEVT_CUDA_OK(cudaMemcpyAsync(&h[0], e->offsets + ((size_t)n2 - 1), 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaMemcpyAsync(&h[1], e->n_vis, 4, cudaMemcpyDeviceToHost, s));
@@ -1132,7 +1132,7 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // see gsevt_engine_status
     GSEVT_CUDA_OK(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
     GSEVT_CUDA_OK(cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), s));
-    launch_workload_counters(e->map->P, e->radii, e->grad8, L.W * L.H, e->n_contrib, d, s);
+    launch_workload_counters(e->map->P, e->rect_raw, e->grad8, L.W * L.H, e->n_contrib, d, s);
     unsigned long long h[8];
     uint32_t offs[2] = {0, 0};
     GSEVT_CUDA_OK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s));

@@ -212,19 +212,23 @@ __host__ __device__ __forceinline__ uint32_t rect_area(uint32_t r) {
 }
 struct PairArea {
     const uint64_t* pairs;
-    __host__ __device__ __forceinline__ uint32_t operator()(int i) const { return rect_area((uint32_t)(pairs[i] >> 32)); }
+    const uint32_t* n_live;   // entries at and past *n_live are padding (whatever they hold): area 0
+    __host__ __device__ __forceinline__ uint32_t operator()(int i) const {
+        return (uint32_t)i < *n_live ? rect_area((uint32_t)(pairs[i] >> 32)) : 0u;
+    }
 };
 }  // namespace
 size_t scan_gather_temp_bytes(int n) {
     size_t bytes = 0;
-    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), PairArea{nullptr});
+    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), PairArea{nullptr, nullptr});
     cub::DeviceScan::InclusiveSum(nullptr, bytes, it, (uint32_t*)nullptr, n > 0 ? n : 1);
     return bytes;
 }
 // offsets[i] = inclusive sum of the tile-rect areas of pairs[0..i] (pairs in emission order)
-void launch_scan_gather(void* temp, size_t temp_bytes, const uint64_t* pairs, uint32_t* offsets, int n, cudaStream_t s) {
+void launch_scan_gather(void* temp, size_t temp_bytes, const uint64_t* pairs, const uint32_t* n_live, uint32_t* offsets, int n,
+                        cudaStream_t s) {
     if (n <= 0) return;
-    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), PairArea{pairs});
+    auto it = thrust::make_transform_iterator(thrust::counting_iterator<int>(0), PairArea{pairs, n_live});
     cub::DeviceScan::InclusiveSum(temp, temp_bytes, it, offsets, n, s);
 }
 

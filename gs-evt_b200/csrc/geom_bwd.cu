@@ -414,7 +414,7 @@ void launch_geom_bwd_map(const GeomBwdArgs& a, cudaStream_t s) {
 // slice of the pairs, collects its hits in shared memory and reserves its part of the list with ONE global atomic
 // (a warp-aggregated atomic per hit warp serialises tens of thousands of adds on a single L2 address).
 constexpr int GC_PER_CTA = 2048;
-__global__ void __launch_bounds__(256) geom_compact_kernel(int n, int per_cta, const int* __restrict__ radii,
+__global__ void __launch_bounds__(256) geom_compact_kernel(int n, int per_cta, const uint32_t* __restrict__ rect_raw,
                                                            const float4* __restrict__ grad8, uint32_t* __restrict__ list,
                                                            uint32_t* __restrict__ count, const EngineCtl* __restrict__ ctl) {
     if (ctl && ctl->level_done) return;
@@ -425,24 +425,25 @@ __global__ void __launch_bounds__(256) geom_compact_kernel(int n, int per_cta, c
     const int lane = threadIdx.x & 31;
     const int first = blockIdx.x * per_cta;
     for (int k0 = 0; k0 < per_cta; k0 += 4 * 256) {
-        int gid[4], rad[4];
+        int gid[4];
+        uint32_t rad[4];   // tile rect of the pair, 0 = not visible
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             gid[u] = first + k0 + u * 256 + threadIdx.x;
-            rad[u] = (k0 + u * 256 < per_cta && gid[u] < n) ? __ldg(radii + gid[u]) : 0;
+            rad[u] = (k0 + u * 256 < per_cta && gid[u] < n) ? __ldg(rect_raw + gid[u]) : 0u;
         }
         float4 g0[4];
         float2 g1[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            if (rad[u] > 0) {
+            if (rad[u] != 0u) {
                 g0[u] = __ldg(grad8 + 2 * (size_t)gid[u]);
                 g1[u] = __ldg(reinterpret_cast<const float2*>(grad8 + 2 * (size_t)gid[u] + 1));
             }
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const bool active = rad[u] > 0 && (g0[u].x != 0.f || g0[u].y != 0.f || g0[u].z != 0.f || g0[u].w != 0.f ||
+            const bool active = rad[u] != 0u && (g0[u].x != 0.f || g0[u].y != 0.f || g0[u].z != 0.f || g0[u].w != 0.f ||
                                                g1[u].x != 0.f || g1[u].y != 0.f);
             const unsigned bal = __ballot_sync(0xffffffffu, active);
             if (bal) {
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(256) geom_compact_kernel(int n, int per_cta, c
     const uint32_t base = s_base;
     for (uint32_t i = threadIdx.x; i < cnt; i += 256) list[base + i] = s_list[i];
 }
-void launch_geom_compact(int n_pairs, const int* radii, const float4* grad8, uint32_t* list, uint32_t* count, const EngineCtl* ctl,
+void launch_geom_compact(int n_pairs, const uint32_t* rect_raw, const float4* grad8, uint32_t* list, uint32_t* count, const EngineCtl* ctl,
                          cudaStream_t s) {
     if (n_pairs <= 0) return;
     // slices of <= GC_PER_CTA pairs, at least ~4 CTAs per SM
@@ -469,7 +470,7 @@ void launch_geom_compact(int n_pairs, const int* radii, const float4* grad8, uin
     per = (per + 255) / 256 * 256;
     if (per > GC_PER_CTA) per = GC_PER_CTA;
     const int blocks = (n_pairs + per - 1) / per;
-    geom_compact_kernel<<<blocks, 256, 0, s>>>(n_pairs, per, radii, grad8, list, count, ctl);
+    geom_compact_kernel<<<blocks, 256, 0, s>>>(n_pairs, per, rect_raw, grad8, list, count, ctl);
 }
 
 // partials[12][nblocks] -> out12, fixed summation order, double accumulation.

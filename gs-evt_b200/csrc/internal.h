@@ -102,22 +102,24 @@ struct PreMapArgs {
     const float4* cov3D_a;
     const float2* cov3D_b;
     const float* sh_planar;   // [48][P]
-    int* radii;               // [2P]
-    uint32_t* tiles_touched;  // [2P]
+    // per pair in index order (padded to preprocess_map_raw_items): tile rect x0 | y0<<8 | x1<<16 | y1<<24, 0 = not visible
+    // (culled, or outside this engine's strip), and the float bits of the view depth
+    uint32_t* rect_raw;
+    uint32_t* depth_raw;
     uint8_t* clamped;         // [2P]
-    // visible pairs only, compacted in index order per view (see preprocess.cu): entries [0, *n_vis)
-    uint32_t* depth_key;      // [2P] float bits of the view depth
-    uint64_t* pairs;          // [2P] {packed tile rect x0 | y0<<8 | x1<<16 | y1<<24} << 32 | pair id (= view * P + Gaussian)
-    unsigned long long* comp_state;   // chained-scan state, preprocess_map_state_bytes(P); the last word is the tile counter
-    uint32_t* tile_counter;   // = (uint32_t*)(comp_state + number of CTAs + 1)
+    // visible pairs only, compacted in index order per view (compact_pairs_kernel): entries [0, *n_vis)
+    uint32_t* depth_key;      // float bits of the view depth
+    uint64_t* pairs;          // {tile rect} << 32 | pair id (= view * P + Gaussian)
+    unsigned long long* comp_state;   // chained-scan state, preprocess_map_state_bytes(P)
     uint32_t* n_vis;          // out: number of visible pairs
-    int vis_cap;              // slots the depth sort covers: [*n_vis, vis_cap) are filled with sentinels after the projection
+    int vis_cap;              // slots the depth sort covers: [*n_vis, vis_cap) are filled with sentinels
     int* overflow;            // set when *n_vis > vis_cap (may be NULL)
     float4* rec;              // [2][2P]
     float4* grad8;            // [2][2P]
 };
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s);
 size_t preprocess_map_state_bytes(int P);
+size_t preprocess_map_raw_items(int P);
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s);
 void launch_pack_map(int P, int M, const float* xyz, const float* scales, const float* rots, const float* opac,
                      const float* shs, float mod, float4* xyz_opacity, float4* cov_a, float2* cov_b, float* sh_planar,
@@ -150,8 +152,10 @@ void launch_sort_pairs32(void* temp, size_t temp_bytes, const uint32_t* keys_in,
                          const uint64_t* vals_in, uint64_t* vals_out, int n, cudaStream_t s);
 void launch_sort_pairs16(void* temp, size_t temp_bytes, const uint16_t* keys_in, uint16_t* keys_out,
                          const uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit, cudaStream_t s);
-// offsets = inclusive sum of the tile-rect areas of `pairs` ({rect (high 32) | pair id (low 32)}), in array order
-void launch_scan_gather(void* temp, size_t temp_bytes, const uint64_t* pairs, uint32_t* offsets, int n, cudaStream_t s);
+// offsets = inclusive sum of the tile-rect areas of `pairs` ({rect (high 32) | pair id (low 32)}), in array order;
+// entries at and past *n_live count as empty
+void launch_scan_gather(void* temp, size_t temp_bytes, const uint64_t* pairs, const uint32_t* n_live, uint32_t* offsets, int n,
+                        cudaStream_t s);
 void launch_emit_tiles(int P, int n_pairs, int grid_x, int tiles_per_view, const uint64_t* pairs, const uint32_t* offsets,
                        uint16_t* keys, uint32_t* values, int cap, int* overflow, const EngineCtl* ctl, cudaStream_t s);
 // ---- tile binning without instance records (tilebin.cu) ----------------------------------------
@@ -264,7 +268,7 @@ int geom_bwd_blocks(int P, int nviews);
 void launch_geom_bwd_aos(const GeomBwdArgs& a, cudaStream_t s);
 void launch_geom_bwd_map(const GeomBwdArgs& a, cudaStream_t s);
 // engine: list of pairs with radius > 0 and a non-zero blend gradient (count must be zero on entry)
-void launch_geom_compact(int n_pairs, const int* radii, const float4* grad8, uint32_t* list, uint32_t* count, const EngineCtl* ctl,
+void launch_geom_compact(int n_pairs, const uint32_t* rect_raw, const float4* grad8, uint32_t* list, uint32_t* count, const EngineCtl* ctl,
                          cudaStream_t s);
 void launch_reduce_partials(const float* partials, int nblocks, float* out12, cudaStream_t s);
 
@@ -287,7 +291,7 @@ void launch_event_accumulate(const int16_t* x, const int16_t* y, const uint8_t* 
 void launch_event_frame(const int* counts, const int* map_ix, const int* map_iy, int W, int H, int levels,
                         float* sign_out, float* unsign_out, float* scratch, double* dscratch, cudaStream_t s);
 
-void launch_workload_counters(int P, const int* radii, const float4* grad8, int HW, const uint32_t* n_contrib,
+void launch_workload_counters(int P, const uint32_t* rect_raw, const float4* grad8, int HW, const uint32_t* n_contrib,
                               unsigned long long* out, cudaStream_t s);
 
 void set_error(const char* fmt, ...);

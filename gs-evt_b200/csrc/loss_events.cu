@@ -245,12 +245,12 @@ void launch_loss_stats(const float* gray, const float* event_frame, int HW, int 
 // out[0], out[1]: Gaussians with radius > 0 per view; out[2], out[3]: sum of n_contrib per view (the
 // number of (pixel, instance) pairs a pixel walks before it terminates); out[4]: (view, Gaussian) pairs
 // whose blend gradient is non-zero.
-__global__ void workload_counters_kernel(int P, const int* __restrict__ radii, const float4* __restrict__ grad8, int HW,
+__global__ void workload_counters_kernel(int P, const uint32_t* __restrict__ rect_raw, const float4* __restrict__ grad8, int HW,
                                          const uint32_t* __restrict__ n_contrib, unsigned long long* __restrict__ out) {
     unsigned long long c[5] = {0, 0, 0, 0, 0};
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2LL * P; i += stride) {
-        if (radii[i] > 0) {
+        if (rect_raw[i] != 0u) {
             c[i >= P ? 1 : 0]++;
             const float4 a = grad8[2 * i], b = grad8[2 * i + 1];
             if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f || b.x != 0.f || b.y != 0.f) c[4]++;
@@ -266,9 +266,9 @@ __global__ void workload_counters_kernel(int P, const int* __restrict__ radii, c
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + k, v);
     }
 }
-void launch_workload_counters(int P, const int* radii, const float4* grad8, int HW, const uint32_t* n_contrib,
+void launch_workload_counters(int P, const uint32_t* rect_raw, const float4* grad8, int HW, const uint32_t* n_contrib,
                               unsigned long long* out, cudaStream_t s) {
-    workload_counters_kernel<<<296, 256, 0, s>>>(P, radii, grad8, HW, n_contrib, out);
+    workload_counters_kernel<<<296, 256, 0, s>>>(P, rect_raw, grad8, HW, n_contrib, out);
 }
 
 }  // namespace gsevt

@@ -136,83 +136,24 @@ void launch_preprocess_aos(const PreAosArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Engine path: packed map, two views per thread.
 // ------------------------------------------------------------------------------------------------
-// Compaction of the visible (view, Gaussian) pairs, in index order, inside the projection kernel: a chained scan
-// with decoupled look-back over the CTAs' visible counts (one 64-bit state word per CTA: flag << 32 | value; flags
-// 1 = this CTA's count, 2 = inclusive prefix).  CTAs take their tile of 256 Gaussians from an atomic counter, so a
-// CTA can only wait for CTAs that already run.  Within a CTA view-0 pairs come first, then view-1 pairs, each in
-// index order: within a view the compact order is the index order — which is all the stable depth sort needs
-// to reproduce the reference's (depth, index) tie-break; pairs of different views never meet in a tile list.
-// The depth sort / scan / emission then run over ~the visible pairs instead of all 2P (and, under the screen-tile
-// split, over this rank's strip only).
-// Called by all 32 lanes of warp 0; returns (to every lane) the number of visible pairs in all lower tiles.  The
-// look-back reads 32 predecessors per step, so a CTA never walks a long chain one L2 round trip at a time.
-__device__ __forceinline__ uint32_t compact_base(unsigned long long* state, uint32_t tile, uint32_t count) {
-    const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (tile > 0) {
-        if (lane == 0) atomicExch(state + tile, (1ull << 32) | count);
-        int t = (int)tile - 1 - lane;   // this lane's predecessor in the current window of 32
-        while (true) {
-            unsigned long long w = 2ull << 32;   // lanes before tile 0: an (empty) inclusive prefix
-            if (t >= 0) {
-                do {
-                    w = *reinterpret_cast<volatile unsigned long long*>(state + t);
-                } while ((w >> 32) == 0ull);
-            }
-            const unsigned incl = __ballot_sync(0xffffffffu, (w >> 32) == 2ull);
-            const int stop = incl ? __ffs(incl) - 1 : 31;   // nearest predecessor that already holds a prefix
-            uint32_t v = lane <= stop ? (uint32_t)w : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            base += v;
-            if (incl) break;
-            t -= 32;
-        }
-    }
-    if (lane == 0) {
-        __threadfence();
-        atomicExch(state + tile, (2ull << 32) | (unsigned long long)(base + count));
-    }
-    return base;
-}
-
-// After the projection: sentinels behind the visible pairs (key 0xFFFFFFFF sorts last, rect 0 emits nothing) so that
-// the fixed-size depth sort over `cap` slots is well defined whatever the count, and the chained-scan state back to
-// zero for the next launch.
-__global__ void __launch_bounds__(256) compact_finish_kernel(const uint32_t* __restrict__ n_vis, int cap, uint32_t* __restrict__ depth_key,
-                                                             uint64_t* __restrict__ pairs, unsigned long long* __restrict__ state,
-                                                             int state_words) {
-    const int tid = blockIdx.x * 256 + threadIdx.x, stride = gridDim.x * 256;
-    for (int i = (int)*n_vis + tid; i < cap; i += stride) {
-        depth_key[i] = 0xFFFFFFFFu;
-        pairs[i] = 0ull;
-    }
-    for (int i = tid; i < state_words; i += stride) state[i] = 0ull;
-}
-
-template <int D, int MINB>
-__global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a) {
+template <int D>
+__global__ void __launch_bounds__(256, 3) preprocess_map_kernel(PreMapArgs a) {
     if (a.ctl && a.ctl->level_done) return;
     __shared__ ViewParams s_vp[2];
-    __shared__ uint32_t s_tile, s_base;
-    __shared__ uint32_t s_cnt[2][8];
-    if (threadIdx.x == 0) s_tile = atomicAdd(a.tile_counter, 1u);
-    load_views(s_vp, a.views, 2);   // (barrier inside)
-    const uint32_t tile = s_tile;
-    const int idx = (int)tile * 256 + threadIdx.x;
-    const bool live = idx < a.P;
-    const int idc = live ? idx : a.P - 1;
-    const float4 xo = __ldg(a.xyz_opacity + idc);
+    load_views(s_vp, a.views, 2);
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= a.P) return;
+    const float4 xo = __ldg(a.xyz_opacity + idx);
     float cov[6];
     {
-        const float4 c0 = __ldg(a.cov3D_a + idc);
-        const float2 c1 = __ldg(a.cov3D_b + idc);
+        const float4 c0 = __ldg(a.cov3D_a + idx);
+        const float2 c1 = __ldg(a.cov3D_b + idx);
         cov[0] = c0.x; cov[1] = c0.y; cov[2] = c0.z; cov[3] = c0.w; cov[4] = c1.x; cov[5] = c1.y;
     }
     ProjOut o[2];
     bool ok[2];
 #pragma unroll
-    for (int v = 0; v < 2; v++) ok[v] = project_geometry(s_vp[v], xo.x, xo.y, xo.z, cov, o[v]) && live;
+    for (int v = 0; v < 2; v++) ok[v] = project_geometry(s_vp[v], xo.x, xo.y, xo.z, cov, o[v]);
     if (a.ctl) {
         // screen-tile split: keep only the part of the tile rect inside this engine's strip of tile rows
         // (the whole grid unless split, where this changes nothing)
@@ -225,119 +166,185 @@ __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a)
             o[v].rect = (r & 0x00FF00FFu) | (y0 << 8) | (y1 << 24);
         }
     }
-    if (live) {
-        a.radii[idx] = ok[0] ? o[0].radius : 0;
-        a.radii[(size_t)a.P + idx] = ok[1] ? o[1].radius : 0;
+    // per pair, in index order: the tile rect (0 = not visible here) and the depth bits; compact_pairs_kernel squeezes
+    // the visible ones together for the depth sort
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+        const size_t j = (size_t)v * a.P + idx;
+        a.rect_raw[j] = ok[v] ? o[v].rect : 0u;
+        a.depth_raw[j] = __float_as_uint(o[v].depth);
     }
+    if (!ok[0] && !ok[1]) return;
     // SH -> RGB for both views from ONE pass over the planar coefficients (coalesced 128-byte lines).  The degree
     // is a template parameter so that all (D+1)^2 * 3 loads are issued back to back, unconditionally.
-    const bool any_view = ok[0] || ok[1];
+    const float* sh = a.sh_planar + idx;
     const size_t P = (size_t)a.P;
     constexpr int NB = (D + 1) * (D + 1);
     float coef[NB * 3];
-    if (any_view) {
-        const float* sh = a.sh_planar + idx;
 #pragma unroll
-        for (int k = 0; k < NB * 3; k++) coef[k] = __ldg(sh + (size_t)k * P);
+    for (int k = 0; k < NB * 3; k++) coef[k] = __ldg(sh + (size_t)k * P);
+    float basis[2][16];
+#pragma unroll
+    for (int v = 0; v < 2; v++)
+        sh_basis(D, xo.x - s_vp[v].campos[0], xo.y - s_vp[v].campos[1], xo.z - s_vp[v].campos[2], basis[v]);
+    float rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            rgb[0][ch] += basis[0][k] * coef[k * 3 + ch];
+            rgb[1][ch] += basis[1][k] * coef[k * 3 + ch];
+        }
     }
-    // ---- compaction: rank of this thread's pairs inside the CTA, CTA base from the chained scan — done by warp 0
-    // while the coefficient loads of the whole CTA are in flight, so the look-back latency is not exposed
+#pragma unroll
+    for (int v = 0; v < 2; v++) {
+        if (!ok[v]) continue;
+        unsigned clampbits = 0;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float c = rgb[v][ch] + 0.5f;
+            if (c < 0.0f) clampbits |= 1u << ch;
+            rgb[v][ch] = fmaxf(c, 0.0f);
+        }
+        const float gray = GSEVT_GRAY_R * rgb[v][0] + GSEVT_GRAY_G * rgb[v][1] + GSEVT_GRAY_B * rgb[v][2];
+        const size_t j = (size_t)v * P + idx;
+        a.clamped[j] = (uint8_t)clampbits;
+        a.rec[2 * j] = make_float4(o[v].mx, o[v].my, o[v].A, o[v].B);
+        a.rec[2 * j + 1] = make_float4(o[v].C, xo.w, gray, o[v].depth);
+        // (the blend-backward accumulators grad8 are all-zero here: geom_bwd clears what it consumes)
+    }
+}
+
+// Compaction of the visible (view, Gaussian) pairs, in index order — a stream pass of its own between the projection
+// and the depth sort (done inside the projection kernel, the chained scan's barriers and look-back cost the heavy
+// kernel 30 us; here they hide behind 64 resident warps and the pass moves 32 B per pair).  Within a view the compact
+// order is the index order, which is all the stable depth sort needs to reproduce the reference's (depth, index)
+// tie-break; pairs of different views never meet in a tile list.  The depth sort / scan / tile binning then run over
+// the visible pairs instead of all 2P (and, under the screen-tile split, over this rank's strip only).
+//
+// Chained scan with decoupled look-back over the CTAs' visible counts.  One 64-bit state word per CTA:
+// epoch << 34 | flag << 32 | value, flag 1 = this CTA's count, 2 = inclusive prefix.  The epoch (a device counter the
+// last CTA bumps when it is done) makes words of earlier launches read as "not published": no reset pass.  CTAs are
+// dispatched in blockIdx order, so a CTA only ever waits for CTAs that already run.
+constexpr int CP_ITEMS = 8;
+constexpr int CP_TILE = 256 * CP_ITEMS;
+__device__ __forceinline__ uint32_t compact_base(unsigned long long* state, uint32_t tile, uint32_t count, uint32_t epoch) {
+    // called by all 32 lanes of warp 0; returns (to every lane) the number of visible pairs in all lower tiles
+    const int lane = threadIdx.x & 31;
+    const unsigned long long tag = (unsigned long long)epoch << 34;
+    uint32_t base = 0;
+    if (tile > 0) {
+        if (lane == 0) atomicExch(state + tile, tag | (1ull << 32) | count);
+        int t = (int)tile - 1 - lane;   // this lane's predecessor in the current window of 32
+        while (true) {
+            unsigned long long w = tag | (2ull << 32);   // lanes before tile 0: an (empty) inclusive prefix
+            if (t >= 0) {
+                do {
+                    w = *reinterpret_cast<volatile unsigned long long*>(state + t);
+                } while ((w >> 34) != (unsigned long long)epoch);
+            }
+            const unsigned incl = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == 2ull);
+            const int stop = incl ? __ffs(incl) - 1 : 31;   // nearest predecessor that already holds a prefix
+            uint32_t v = lane <= stop ? (uint32_t)w : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            base += v;
+            if (incl) break;
+            t -= 32;
+        }
+    }
+    if (lane == 0) {
+        __threadfence();
+        atomicExch(state + tile, tag | (2ull << 32) | (unsigned long long)(base + count));
+    }
+    return base;
+}
+
+__global__ void __launch_bounds__(256) compact_pairs_kernel(int n2, const uint32_t* __restrict__ rect_raw,
+                                                            const uint32_t* __restrict__ depth_raw,
+                                                            unsigned long long* __restrict__ state, uint32_t* __restrict__ depth_key,
+                                                            uint64_t* __restrict__ pairs, uint32_t* __restrict__ n_vis, int vis_cap,
+                                                            int* __restrict__ overflow, const EngineCtl* __restrict__ ctl) {
+    if (ctl && ctl->level_done) return;
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    uint32_t* epoch_ctr = reinterpret_cast<uint32_t*>(state + gridDim.x);
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(epoch_ctr) + 1u;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t i0 = tile * (uint32_t)CP_TILE + threadIdx.x * (uint32_t)CP_ITEMS;   // the arrays are padded to whole tiles
+    uint32_t rect[CP_ITEMS], key[CP_ITEMS];
+    {
+        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rect_raw + i0)), r1 = __ldg(reinterpret_cast<const uint4*>(rect_raw + i0) + 1);
+        const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(depth_raw + i0)), k1 = __ldg(reinterpret_cast<const uint4*>(depth_raw + i0) + 1);
+        rect[0] = r0.x; rect[1] = r0.y; rect[2] = r0.z; rect[3] = r0.w; rect[4] = r1.x; rect[5] = r1.y; rect[6] = r1.z; rect[7] = r1.w;
+        key[0] = k0.x; key[1] = k0.y; key[2] = k0.z; key[3] = k0.w; key[4] = k1.x; key[5] = k1.y; key[6] = k1.z; key[7] = k1.w;
+    }
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; k++) {
+        if (i0 + k >= (uint32_t)n2) rect[k] = 0u;
+        cnt += rect[k] != 0u;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned b0 = __ballot_sync(0xffffffffu, ok[0]), b1 = __ballot_sync(0xffffffffu, ok[1]);
-    if (lane == 0) { s_cnt[0][warp] = __popc(b0); s_cnt[1][warp] = __popc(b1); }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    uint32_t before[2] = {0, 0}, total[2] = {0, 0};
+    uint32_t before = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
-        const uint32_t c0 = s_cnt[0][w], c1 = s_cnt[1][w];
-        if (w < warp) { before[0] += c0; before[1] += c1; }
-        total[0] += c0; total[1] += c1;
+        const uint32_t c = s_warp[w];
+        if (w < warp) before += c;
+        total += c;
     }
     if (warp == 0) {
-        const uint32_t count = total[0] + total[1];
-        const uint32_t base = compact_base(a.comp_state, tile, count);
-        if (lane == 0) {
-            s_base = base;
-            if (tile == gridDim.x - 1) {
-                // all pairs counted: publish the total, check it against the slots the depth sort covers
-                const uint32_t n_vis = base + count;
-                *a.n_vis = n_vis;
-                if (a.overflow && n_vis > (uint32_t)a.vis_cap) *a.overflow = 1;
-            }
-        }
-    }
-    if (any_view) {
-        float basis[2][16];
-#pragma unroll
-        for (int v = 0; v < 2; v++)
-            sh_basis(D, xo.x - s_vp[v].campos[0], xo.y - s_vp[v].campos[1], xo.z - s_vp[v].campos[2], basis[v]);
-        float rgb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-#pragma unroll
-        for (int k = 0; k < NB; k++) {
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                rgb[0][ch] += basis[0][k] * coef[k * 3 + ch];
-                rgb[1][ch] += basis[1][k] * coef[k * 3 + ch];
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < 2; v++) {
-            if (!ok[v]) continue;
-            unsigned clampbits = 0;
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) {
-                const float c = rgb[v][ch] + 0.5f;
-                if (c < 0.0f) clampbits |= 1u << ch;
-                rgb[v][ch] = fmaxf(c, 0.0f);
-            }
-            const float gray = GSEVT_GRAY_R * rgb[v][0] + GSEVT_GRAY_G * rgb[v][1] + GSEVT_GRAY_B * rgb[v][2];
-            const size_t j = (size_t)v * P + idx;
-            a.clamped[j] = (uint8_t)clampbits;
-            a.rec[2 * j] = make_float4(o[v].mx, o[v].my, o[v].A, o[v].B);
-            a.rec[2 * j + 1] = make_float4(o[v].C, xo.w, gray, o[v].depth);
-            // (the blend-backward accumulators grad8 are all-zero here: geom_bwd clears what it consumes)
-        }
+        const uint32_t base = compact_base(state, tile, total, epoch);
+        if (lane == 0) s_base = base;
     }
     __syncthreads();
-    const unsigned lt = (1u << lane) - 1u;
-    const uint32_t slot[2] = {s_base + before[0] + __popc(b0 & lt), s_base + total[0] + before[1] + __popc(b1 & lt)};
-    if (live) {
+    uint32_t slot = s_base + before + incl - cnt;
 #pragma unroll
-        for (int v = 0; v < 2; v++) {
-            const size_t j = (size_t)v * a.P + idx;
-            if (ok[v]) {
-                a.depth_key[slot[v]] = __float_as_uint(o[v].depth);
-                a.pairs[slot[v]] = ((uint64_t)o[v].rect << 32) | (uint64_t)j;
-            }
+    for (int k = 0; k < CP_ITEMS; k++) {
+        if (rect[k] != 0u) {
+            depth_key[slot] = key[k];
+            pairs[slot] = ((uint64_t)rect[k] << 32) | (uint64_t)(i0 + k);
+            slot++;
+        }
+    }
+    if (tile == gridDim.x - 1) {
+        // all pairs counted: publish the total, sentinel keys behind it (0xFFFFFFFF sorts last) so
+        // that the fixed-size depth sort over vis_cap slots is well defined whatever the count, then open the next epoch
+        const uint32_t nv = s_base + total;
+        // (only the keys: the offsets scan treats every entry past *n_vis as empty, see PairArea in binning.cu)
+        for (uint32_t i = nv + threadIdx.x; i < (uint32_t)vis_cap; i += 256) depth_key[i] = 0xFFFFFFFFu;
+        if (threadIdx.x == 0) {
+            *n_vis = nv;
+            if (overflow && nv > (uint32_t)vis_cap) *overflow = 1;
+            __threadfence();
+            *epoch_ctr = epoch;
         }
     }
 }
 
-size_t preprocess_map_state_bytes(int P) { return ((size_t)(P + 255) / 256 + 2) * sizeof(unsigned long long); }
+size_t preprocess_map_state_bytes(int P) { return ((size_t)(2 * (size_t)P + CP_TILE - 1) / CP_TILE + 2) * sizeof(unsigned long long); }
+size_t preprocess_map_raw_items(int P) { return (2 * (size_t)P + CP_TILE - 1) / CP_TILE * CP_TILE; }
 
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
     const int blocks = (a.P + 255) / 256;
-    // comp_state (chained-scan words + tile counter) is zero on entry: zeroed at allocation and by every finish kernel
-    // GSEVT_PRE_MINB=3: 80 registers (88 B of spills at SH degree 3), three CTAs per SM; default 2: 105 registers, no spills
-    static const int minb = [] { const char* v = getenv("GSEVT_PRE_MINB"); return v && atoi(v) == 3 ? 3 : 2; }();
-    if (minb == 3) {
-        switch (a.D) {
-            case 0: preprocess_map_kernel<0, 3><<<blocks, 256, 0, s>>>(a); break;
-            case 1: preprocess_map_kernel<1, 3><<<blocks, 256, 0, s>>>(a); break;
-            case 2: preprocess_map_kernel<2, 3><<<blocks, 256, 0, s>>>(a); break;
-            default: preprocess_map_kernel<3, 3><<<blocks, 256, 0, s>>>(a); break;
-        }
-    } else {
-        switch (a.D) {
-            case 0: preprocess_map_kernel<0, 2><<<blocks, 256, 0, s>>>(a); break;
-            case 1: preprocess_map_kernel<1, 2><<<blocks, 256, 0, s>>>(a); break;
-            case 2: preprocess_map_kernel<2, 2><<<blocks, 256, 0, s>>>(a); break;
-            default: preprocess_map_kernel<3, 2><<<blocks, 256, 0, s>>>(a); break;
-        }
+    switch (a.D) {
+        case 0: preprocess_map_kernel<0><<<blocks, 256, 0, s>>>(a); break;
+        case 1: preprocess_map_kernel<1><<<blocks, 256, 0, s>>>(a); break;
+        case 2: preprocess_map_kernel<2><<<blocks, 256, 0, s>>>(a); break;
+        default: preprocess_map_kernel<3><<<blocks, 256, 0, s>>>(a); break;
     }
-    compact_finish_kernel<<<148, 256, 0, s>>>(a.n_vis, a.vis_cap, a.depth_key, a.pairs, a.comp_state,
-                                              (int)(preprocess_map_state_bytes(a.P) / sizeof(unsigned long long)));
+    const int n2 = 2 * a.P;
+    compact_pairs_kernel<<<(n2 + CP_TILE - 1) / CP_TILE, 256, 0, s>>>(n2, a.rect_raw, a.depth_raw, a.comp_state, a.depth_key, a.pairs,
+                                                                    a.n_vis, a.vis_cap, a.overflow, a.ctl);
 }
 
 // checkFrustum (rasterizer_impl.cu:54-66)

@@ -20,6 +20,7 @@
 // slice in order, 32 instances per step, ranking equal tiles inside a step with match.any (lower lane = earlier
 // instance).  Traffic: the pairs twice (12 B each), hist/base once each way, 4 B per instance out — against
 // (6 B + 2 x 12 B + 2 B) per instance for emit + two radix passes + range scan.
+#include <cstdlib>
 #include "internal.h"
 
 namespace gsevt {
@@ -93,7 +94,7 @@ __device__ __forceinline__ PairWork load_pair(const uint64_t* __restrict__ pairs
 // Visits every instance of the warp's 32 pairs: f(local_instance, tile, Gaussian).  A lane walks its own rect when it
 // has at most TB_SMALL instances in the chunk; larger ones are walked by the whole warp, 32 instances per step, so no
 // lane ever loops over a screen-filling Gaussian alone.
-constexpr uint32_t TB_SMALL = 12;
+__constant__ uint32_t TB_SMALL = 32;   // set once from GSEVT_TB_SMALL (tuning knob)
 template <typename F>
 __device__ __forceinline__ void visit_pair(const PairWork& w, uint32_t begin, int gx, F f) {
     const bool big = w.t1 - w.t0 > TB_SMALL;
@@ -121,20 +122,14 @@ __device__ __forceinline__ void visit_pair(const PairWork& w, uint32_t begin, in
     }
 }
 
-// All pairs [p_lo, p_hi] of a chunk, 256 per round, four rounds' loads in flight together.
+// All pairs [p_lo, p_hi] of a chunk, 256 per round.  (Keeping several rounds' loads in flight costs more in registers and
+// code size than the latency it hides: measured 25 -> 47 us for the count kernel.)
 template <typename F>
 __device__ __forceinline__ void visit_chunk(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ off, uint32_t p_lo,
                                             uint32_t p_hi, uint32_t begin, uint32_t end, int P, int gx, int tiles_per_view, F f) {
-    for (uint32_t p0 = p_lo; p0 <= p_hi; p0 += 4u * TB_THREADS) {
-        PairWork w[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            w[u] = load_pair(pairs, off, p0 + (uint32_t)u * TB_THREADS + threadIdx.x, p_hi, begin, end, P, gx, tiles_per_view);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (p0 + (uint32_t)u * TB_THREADS > p_hi) break;   // uniform
-            visit_pair(w[u], begin, gx, f);
-        }
+    for (uint32_t p0 = p_lo; p0 <= p_hi; p0 += TB_THREADS) {
+        const PairWork w = load_pair(pairs, off, p0 + threadIdx.x, p_hi, begin, end, P, gx, tiles_per_view);
+        visit_pair(w, begin, gx, f);
     }
 }
 
@@ -341,6 +336,10 @@ size_t tilebin_base_bytes(int cap, int tiles_per_view) {
 size_t tilebin_chunk_bytes(int cap) { return (size_t)((cap + TB_CH - 1) / TB_CH) * sizeof(uint2); }
 
 int tilebin_configure(int max_tiles_per_view) {
+    if (const char* v = getenv("GSEVT_TB_SMALL")) {
+        const uint32_t k = (uint32_t)atoi(v);
+        if (k >= 1 && k <= 65536) cudaMemcpyToSymbol(TB_SMALL, &k, sizeof(k));
+    }
     const size_t smem = (size_t)2 * max_tiles_per_view * 5 * sizeof(uint32_t);
     if (smem + TB_CH * 6 + 64 > 227 * 1024) return -1;
     cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
