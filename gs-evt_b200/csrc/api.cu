@@ -414,6 +414,13 @@ struct GsevtEngine {
     void* sortA_temp = nullptr; size_t sortA_bytes = 0;
     // tile binning (tilebin.cu): per-chunk tile counts, their prefix over the chunks, chunk pair ranges, per-tile totals
     uint16_t* tb_hist = nullptr; uint32_t* tb_base = nullptr; uint2* tb_chunks = nullptr; uint32_t* tb_total = nullptr;
+    size_t tb_items = 0, tb_rows = 0;    // allocated hist / base elements, chunk rows
+    // radix fallback when the strip has more tiles than the counting kernels bin in shared memory (binning.cu):
+    // (u16 tile key, u32 id) records, double-buffered for a CUB sort
+    int bin_path = 0;                    // 0 tile binning by counting, 1 emit + radix sort + range scan
+    uint16_t *keys_u = nullptr, *keys = nullptr;
+    uint32_t* vals_u = nullptr;
+    void* sort_temp = nullptr; size_t sort_bytes = 0; long long radix_cap = 0;
     uint32_t* vals = nullptr;            // per-tile lists: Gaussian index per slot
     uint2* ranges = nullptr;
     uint32_t* hitmask = nullptr; size_t hitmask_stride = 0;   // forward -> backward: what each warp blended
@@ -485,18 +492,56 @@ static int ensure_capacity(GsevtEngine* e, long long slots, cudaStream_t s) {
     cudaStreamSynchronize(s);
     if (e->graph_stream && e->graph_stream != s) cudaStreamSynchronize(e->graph_stream);
     if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
-    dev_free(e, e->vals); dev_free(e, e->tb_hist); dev_free(e, e->tb_base); dev_free(e, e->tb_chunks);
+    dev_free(e, e->vals);
     dev_free(e, e->hitmask);
-    e->vals = nullptr; e->tb_hist = nullptr; e->tb_base = nullptr; e->tb_chunks = nullptr; e->hitmask = nullptr;
+    e->vals = nullptr; e->hitmask = nullptr;
     e->cap = (int)cap;
     e->hitmask_stride = hitmask_stride_for(e, e->cap);
-    const int tiles0 = e->lv[0].gx * e->lv[0].gy;
     int rc = 0;
     rc |= dev_alloc(e, &e->hitmask, 8 * e->hitmask_stride);
     rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
-    rc |= dev_alloc(e, (char**)&e->tb_hist, tilebin_hist_bytes(e->cap, tiles0));
-    rc |= dev_alloc(e, (char**)&e->tb_base, tilebin_base_bytes(e->cap, tiles0));
-    rc |= dev_alloc(e, (char**)&e->tb_chunks, tilebin_chunk_bytes(e->cap));
+    return rc ? GSEVT_ECUDA : 0;
+}
+
+// The tile-binning kernels keep 5 words per bin in shared memory: above this many bins (2 x tiles of the strip) a CTA
+// no longer shares an SM and the per-bin bookkeeping outweighs the 4096 instances of a chunk — measured at 2 x 3600
+// tiles (1280x720 unsplit): 1.5 ms against 0.77 ms for emit + radix sort, which is then used instead.
+#define GSEVT_TILEBIN_MAX_BINS 4096
+
+// Picks the binning path for the current level / strip and (re)sizes its work buffers for e->sort_n instance slots
+// (never inside a captured graph).
+static int ensure_binning(GsevtEngine* e, cudaStream_t s) {
+    const LevelInfo& L = e->lv[e->cur_level];
+    const int bins = 2 * (e->strip_y1 - e->strip_y0) * L.gx;
+    e->bin_path = bins <= GSEVT_TILEBIN_MAX_BINS ? 0 : 1;
+    auto quiesce = [&]() {
+        cudaStreamSynchronize(s);
+        if (e->graph_stream && e->graph_stream != s) cudaStreamSynchronize(e->graph_stream);
+        if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+    };
+    int rc = 0;
+    if (e->bin_path == 0) {
+        const size_t rows = tilebin_chunks(e->sort_n), items = rows * (size_t)bins;
+        if (items > e->tb_items || rows > e->tb_rows) {
+            quiesce();
+            dev_free(e, e->tb_hist); dev_free(e, e->tb_base); dev_free(e, e->tb_chunks);
+            e->tb_hist = nullptr; e->tb_base = nullptr; e->tb_chunks = nullptr;
+            e->tb_items = items + items / 4; e->tb_rows = rows + rows / 4;
+            rc |= dev_alloc(e, &e->tb_hist, e->tb_items);
+            rc |= dev_alloc(e, &e->tb_base, e->tb_items);
+            rc |= dev_alloc(e, &e->tb_chunks, e->tb_rows);
+        }
+    } else if ((long long)e->sort_n > e->radix_cap) {
+        quiesce();
+        dev_free(e, e->keys_u); dev_free(e, e->keys); dev_free(e, e->vals_u); dev_free(e, e->sort_temp);
+        e->keys_u = e->keys = nullptr; e->vals_u = nullptr; e->sort_temp = nullptr;
+        e->radix_cap = (long long)e->sort_n + e->sort_n / 4;
+        e->sort_bytes = sort16_temp_bytes((int)e->radix_cap);
+        rc |= dev_alloc(e, &e->keys_u, (size_t)e->radix_cap);
+        rc |= dev_alloc(e, &e->keys, (size_t)e->radix_cap);
+        rc |= dev_alloc(e, &e->vals_u, (size_t)e->radix_cap);
+        rc |= dev_alloc(e, (char**)&e->sort_temp, e->sort_bytes);
+    }
     return rc ? GSEVT_ECUDA : 0;
 }
 
@@ -556,17 +601,29 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs_sorted, e->n_vis, e->offsets, nv, s);
     mark();
     const int tiles = L.gx * L.gy;
-    TileBinArgs tb;
-    tb.P = P; tb.n_pairs = nv; tb.grid_x = L.gx; tb.tiles_per_view = tiles;
-    tb.pairs = e->pairs_sorted; tb.offsets = e->offsets; tb.hist = e->tb_hist; tb.base = e->tb_base; tb.chunk_pairs = e->tb_chunks;
-    tb.tile_total = e->tb_total; tb.ranges = e->ranges; tb.values = e->vals; tb.cap = e->sort_n; tb.overflow = e->overflow;
-    tb.ctl = e->ctl;
-    launch_tile_count(tb, s);
-    mark();
-    launch_tile_scan(tb, s);
-    mark();
-    launch_tile_scatter(tb, s);
-    mark();
+    if (e->bin_path == 0) {
+        TileBinArgs tb;
+        tb.P = P; tb.n_pairs = nv; tb.grid_x = L.gx;
+        tb.tiles_per_view = (e->strip_y1 - e->strip_y0) * L.gx; tb.row0 = e->strip_y0; tb.tiles_global = tiles;
+        tb.pairs = e->pairs_sorted; tb.offsets = e->offsets; tb.hist = e->tb_hist; tb.base = e->tb_base; tb.chunk_pairs = e->tb_chunks;
+        tb.tile_total = e->tb_total; tb.ranges = e->ranges; tb.values = e->vals; tb.cap = e->sort_n; tb.overflow = e->overflow;
+        tb.ctl = e->ctl;
+        launch_tile_count(tb, s);
+        mark();
+        launch_tile_scan(tb, s);
+        mark();
+        launch_tile_scatter(tb, s);
+        mark();
+    } else {
+        // radix fallback (same three stage slots): emit (tile key, id) records, stable sort on the tile key, range scan
+        launch_emit_tiles(P, nv, L.gx, tiles, e->pairs_sorted, e->offsets, e->keys_u, e->vals_u, e->sort_n, e->overflow, e->ctl, s);
+        mark();
+        const int bit = (int)higher_msb((uint32_t)(2 * tiles));
+        launch_sort_pairs16(e->sort_temp, e->sort_bytes, e->keys_u, e->keys, e->vals_u, e->vals, e->sort_n, bit, s);
+        mark();
+        launch_identify_ranges16(e->keys, e->ranges, 2 * tiles, e->offsets + (nv - 1), e->sort_n, s);
+        mark();
+    }
     BlendFwdArgs f;
     memset(&f, 0, sizeof(f));
     f.W = L.W; f.H = L.H; f.grid_x = L.gx; f.grid_y = L.gy; f.nviews = 2;
@@ -622,6 +679,8 @@ static int upload_strip(GsevtEngine* e, int y0, int y1, cudaStream_t s) {
     struct { int y0, y1; } h = {y0, y1};
     static_assert(offsetof(EngineCtl, strip_y1) - offsetof(EngineCtl, strip_y0) == 4, "EngineCtl strip layout");
     GSEVT_CUDA_OK(cudaMemcpyAsync((char*)e->ctl + offsetof(EngineCtl, strip_y0), &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    // tiles outside the strip are never binned or blended by this engine: their ranges read as empty
+    GSEVT_CUDA_OK(cudaMemsetAsync(e->ranges, 0, 2 * (size_t)e->lv[0].gx * e->lv[0].gy * sizeof(uint2), s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // h is a stack buffer
     return 0;
 }
@@ -725,12 +784,9 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->pairs_sorted, p2);
     rc |= dev_alloc(e, (char**)&e->sortA_temp, e->sortA_bytes);
     rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
-    rc |= dev_alloc(e, (char**)&e->tb_hist, tilebin_hist_bytes(e->cap, L0.gx * L0.gy));
-    rc |= dev_alloc(e, (char**)&e->tb_base, tilebin_base_bytes(e->cap, L0.gx * L0.gy));
-    rc |= dev_alloc(e, (char**)&e->tb_chunks, tilebin_chunk_bytes(e->cap));
     rc |= dev_alloc(e, &e->tb_total, 2 * (size_t)L0.gx * L0.gy);
     rc |= dev_alloc(e, &e->ranges, 2 * (size_t)L0.gx * L0.gy);
-    if (tilebin_configure(L0.gx * L0.gy)) { set_error("image too large for the tile binning kernels"); gsevt_engine_destroy(e); return GSEVT_EINVAL; }
+    if (tilebin_configure(GSEVT_TILEBIN_MAX_BINS / 2)) { set_error("image too large for the tile binning kernels"); gsevt_engine_destroy(e); return GSEVT_EINVAL; }
     e->hitmask_stride = hitmask_stride_for(e, e->cap);
     rc |= dev_alloc(e, &e->hitmask, 8 * e->hitmask_stride);
     rc |= dev_alloc(e, &e->gray, 2 * hw);
@@ -885,6 +941,7 @@ static int size_level(GsevtEngine* e, cudaStream_t s, bool rebalance, int slack_
     const long long want = slots_for((long long)total + (slack_div > 0 ? total / slack_div : 0));
     if ((rc = ensure_capacity(e, want, s))) return rc;
     e->sort_n = (int)want;
+    if ((rc = ensure_binning(e, s))) return rc;
     // visible pairs: the count moves while the pose is optimised; above the cap the device voids the iteration and pauses
     long long vslack = (long long)n_vis / 16 + 8192;
     if (slack_div > 0) vslack += n_vis / slack_div;
@@ -1080,7 +1137,7 @@ GSEVT_API int gsevt_engine_binning(GsevtEngine* e, int32_t view, uint64_t* keys_
     for (int t = 0; t < tiles; t++) { n0 += r[t].y - r[t].x; n1 += r[tiles + t].y - r[tiles + t].x; }
     const uint32_t first = view == 0 ? 0u : n0, count = view == 0 ? n0 : n1;
     if ((int64_t)count > (int64_t)capacity) { set_error("capacity %d < %u instances", capacity, count); return GSEVT_ENOMEM; }
-    uint16_t* tile_keys = nullptr;   // tile id per slot, as the high word of the reference's sorted keys holds it
+    uint16_t* tile_keys = nullptr;   // tile id per slot, as the high word of the reference's sorted keys holds it (both paths)
     GSEVT_CUDA_OK(cudaMalloc(&tile_keys, ((size_t)n0 + n1 + 1) * sizeof(uint16_t)));
     launch_keys_from_ranges(2 * tiles, e->ranges, tile_keys, s);
     launch_rebuild_keys(tile_keys, e->vals, e->rec + 2 * (size_t)view * e->map->P, (uint32_t)(view * tiles), first, count, keys_out,
@@ -1248,11 +1305,10 @@ GSEVT_API int gsevt_engine_split_info(GsevtEngine* e, int32_t out6[6], void* str
 }
 
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e) {
-    (void)e;
-    // preprocess, compact_finish, tile_count, tile_scan, tile_starts, tile_scatter, blend_fwd, loss_stats, blend_bwd,
-    // geom_compact, geom_bwd, update = 12 of ours; plus CUB: one radix sort (histogram + exclusive sum + four onesweep
-    // passes) and a scan.
-    return 12;
+    // preprocess_map, compact_pairs, {tile_count, tile_scan, tile_starts, tile_scatter | emit_tiles, identify_ranges16},
+    // blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, engine_update; plus CUB library kernels: the depth sort
+    // (histogram + exclusive sum + four onesweep passes), the offsets scan, and on the radix path the 16-bit tile sort.
+    return e && e->bin_path == 1 ? 10 : 12;
 }
 
 }  // extern "C"

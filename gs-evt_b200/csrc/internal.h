@@ -160,7 +160,9 @@ void launch_emit_tiles(int P, int n_pairs, int grid_x, int tiles_per_view, const
                        uint16_t* keys, uint32_t* values, int cap, int* overflow, const EngineCtl* ctl, cudaStream_t s);
 // ---- tile binning without instance records (tilebin.cu) ----------------------------------------
 struct TileBinArgs {
-    int P, n_pairs, grid_x, tiles_per_view;
+    int P, n_pairs, grid_x;
+    int tiles_per_view;         // bins per view: the tiles of this engine's strip of tile rows (the whole grid unless split)
+    int row0, tiles_global;     // first tile row of the strip; tiles per view of the whole grid (ranges are indexed globally)
     const uint64_t* pairs;      // depth-sorted {rect | pair id}, n_pairs entries (sentinels with rect 0 at the end)
     const uint32_t* offsets;    // inclusive sum of the rect areas
     uint16_t* hist;             // [chunks][2 * tiles_per_view]
@@ -174,9 +176,7 @@ struct TileBinArgs {
     const EngineCtl* ctl;
 };
 int tilebin_chunk();
-size_t tilebin_hist_bytes(int cap, int tiles_per_view);
-size_t tilebin_base_bytes(int cap, int tiles_per_view);
-size_t tilebin_chunk_bytes(int cap);
+size_t tilebin_chunks(int cap);   // chunk CTAs (= rows of hist / base) for `cap` instance slots
 int tilebin_configure(int max_tiles_per_view);
 void launch_tile_count(const TileBinArgs& a, cudaStream_t s);
 void launch_tile_scan(const TileBinArgs& a, cudaStream_t s);

@@ -74,7 +74,7 @@ __device__ __forceinline__ void chunk_pair_range(const uint32_t* __restrict__ of
 struct PairWork { uint32_t excl, t0, t1, tbase, wd, id; };
 
 __device__ __forceinline__ PairWork load_pair(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ off, uint32_t p,
-                                              uint32_t p_hi, uint32_t begin, uint32_t end, int P, int gx, int tiles_per_view) {
+                                              uint32_t p_hi, uint32_t begin, uint32_t end, int P, int gx, int tiles_per_view, int row0) {
     PairWork w = {0u, 0u, 0u, 0u, 1u, 0u};
     if (p <= p_hi) {
         const uint64_t pr = __ldg(pairs + p);
@@ -86,7 +86,7 @@ __device__ __forceinline__ PairWork load_pair(const uint64_t* __restrict__ pairs
         w.t1 = (incl < end ? incl : end) - w.excl;
         if (w.t1 < w.t0) w.t1 = w.t0;
         w.wd = (rect >> 16 & 255u) - (rect & 255u);
-        w.tbase = ((uint32_t)pr >= (uint32_t)P ? (uint32_t)tiles_per_view : 0u) + (rect >> 8 & 255u) * (uint32_t)gx + (rect & 255u);
+        w.tbase = ((uint32_t)pr >= (uint32_t)P ? (uint32_t)tiles_per_view : 0u) + ((rect >> 8 & 255u) - (uint32_t)row0) * (uint32_t)gx + (rect & 255u);
     }
     return w;
 }
@@ -126,9 +126,9 @@ __device__ __forceinline__ void visit_pair(const PairWork& w, uint32_t begin, in
 // code size than the latency it hides: measured 25 -> 47 us for the count kernel.)
 template <typename F>
 __device__ __forceinline__ void visit_chunk(const uint64_t* __restrict__ pairs, const uint32_t* __restrict__ off, uint32_t p_lo,
-                                            uint32_t p_hi, uint32_t begin, uint32_t end, int P, int gx, int tiles_per_view, F f) {
+                                            uint32_t p_hi, uint32_t begin, uint32_t end, int P, int gx, int tiles_per_view, int row0, F f) {
     for (uint32_t p0 = p_lo; p0 <= p_hi; p0 += TB_THREADS) {
-        const PairWork w = load_pair(pairs, off, p0 + threadIdx.x, p_hi, begin, end, P, gx, tiles_per_view);
+        const PairWork w = load_pair(pairs, off, p0 + threadIdx.x, p_hi, begin, end, P, gx, tiles_per_view, row0);
         visit_pair(w, begin, gx, f);
     }
 }
@@ -136,7 +136,7 @@ __device__ __forceinline__ void visit_chunk(const uint64_t* __restrict__ pairs, 
 }  // namespace
 
 // ---- 1. counts per (chunk, tile) ------------------------------------------------------------------
-__global__ void __launch_bounds__(TB_THREADS) tile_count_kernel(int P, int n_pairs, int gx, int tiles_per_view,
+__global__ void __launch_bounds__(TB_THREADS) tile_count_kernel(int P, int n_pairs, int gx, int tiles_per_view, int row0,
                                                                  const uint64_t* __restrict__ pairs,
                                                                  const uint32_t* __restrict__ off, uint16_t* __restrict__ hist,
                                                                  uint2* __restrict__ chunk_pairs, int cap, int* __restrict__ overflow,
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_count_kernel(int P, int n_pai
     __syncthreads();
     const uint32_t p_lo = s_p[0], p_hi = s_p[1];
     if (threadIdx.x == 0) chunk_pairs[blockIdx.x] = make_uint2(p_lo, p_hi);
-    visit_chunk(pairs, off, p_lo, p_hi, begin, end, P, gx, tiles_per_view,
+    visit_chunk(pairs, off, p_lo, p_hi, begin, end, P, gx, tiles_per_view, row0,
                 [&](uint32_t, uint32_t tile, uint32_t) { atomicAdd(&s_hist[tile], 1u); });
     __syncthreads();
     uint16_t* row = hist + (size_t)blockIdx.x * nt;
@@ -217,8 +217,9 @@ __global__ void __launch_bounds__(TS_COLS * TS_GROUPS) tile_scan_kernel(int nt, 
 }
 
 // ---- 3. prefix over the tiles: the tile ranges ----------------------------------------------------
-__global__ void __launch_bounds__(1024) tile_starts_kernel(int nt, const uint32_t* __restrict__ tile_total,
-                                                            uint2* __restrict__ ranges, const EngineCtl* __restrict__ ctl) {
+__global__ void __launch_bounds__(1024) tile_starts_kernel(int nt, int tiles_local, int tiles_global, int tile_origin,
+                                                            const uint32_t* __restrict__ tile_total, uint2* __restrict__ ranges,
+                                                            const EngineCtl* __restrict__ ctl) {
     if (ctl && ctl->level_done) return;
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
@@ -248,7 +249,10 @@ __global__ void __launch_bounds__(1024) tile_starts_kernel(int nt, const uint32_
         __syncthreads();
         const uint32_t carry = s_carry;
         const uint32_t start = carry + s_warp[warp] + x - v;
-        if (t < nt) ranges[t] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);
+        if (t < nt) {
+            const int view = t >= tiles_local ? 1 : 0;   // bins are strip-local; the ranges are indexed by the global tile id
+            ranges[view * tiles_global + tile_origin + (t - view * tiles_local)] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);
+        }
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = start + v;
         __syncthreads();
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(1024) tile_starts_kernel(int nt, const uint32_
 }
 
 // ---- 4. stable scatter ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(int P, int n_pairs, int gx, int tiles_per_view,
+__global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(int P, int n_pairs, int gx, int tiles_per_view, int row0, int tiles_global,
                                                                    const uint64_t* __restrict__ pairs,
                                                                    const uint32_t* __restrict__ off,
                                                                    const uint2* __restrict__ chunk_pairs,
@@ -278,13 +282,14 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(int P, int n_p
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t* brow = base + (size_t)blockIdx.x * nt;
     for (int t = threadIdx.x; t < nt; t += TB_THREADS) {
-        s_gbase[t] = __ldg(&ranges[t].x) + __ldg(brow + t);
+        const int view = t >= tiles_per_view ? 1 : 0;
+        s_gbase[t] = __ldg(&ranges[view * tiles_global + row0 * gx + (t - view * tiles_per_view)].x) + __ldg(brow + t);
         s_cnt[t] = 0; s_cnt[nt + t] = 0; s_cnt[2 * nt + t] = 0; s_cnt[3 * nt + t] = 0;
     }
     const uint2 pr = chunk_pairs[blockIdx.x];
     __syncthreads();
     // regenerate the chunk's instances: (tile, id) per local instance index, plus the per-slice counts
-    visit_chunk(pairs, off, pr.x, pr.y, begin, end, P, gx, tiles_per_view, [&](uint32_t li, uint32_t tile, uint32_t id) {
+    visit_chunk(pairs, off, pr.x, pr.y, begin, end, P, gx, tiles_per_view, row0, [&](uint32_t li, uint32_t tile, uint32_t id) {
         s_tile[li] = (uint16_t)tile;
         s_id[li] = id;
         const uint32_t slice = li / TB_SLICE;
@@ -327,13 +332,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(int P, int n_p
 
 // ---- host side -----------------------------------------------------------------------------------
 int tilebin_chunk() { return TB_CH; }
-size_t tilebin_hist_bytes(int cap, int tiles_per_view) {
-    return (size_t)((cap + TB_CH - 1) / TB_CH) * 2 * (size_t)tiles_per_view * sizeof(uint16_t);
-}
-size_t tilebin_base_bytes(int cap, int tiles_per_view) {
-    return (size_t)((cap + TB_CH - 1) / TB_CH) * 2 * (size_t)tiles_per_view * sizeof(uint32_t);
-}
-size_t tilebin_chunk_bytes(int cap) { return (size_t)((cap + TB_CH - 1) / TB_CH) * sizeof(uint2); }
+size_t tilebin_chunks(int cap) { return (size_t)((cap + TB_CH - 1) / TB_CH); }
 
 int tilebin_configure(int max_tiles_per_view) {
     if (const char* v = getenv("GSEVT_TB_SMALL")) {
@@ -352,7 +351,7 @@ void launch_tile_count(const TileBinArgs& a, cudaStream_t s) {
     const int chunks = (a.cap + TB_CH - 1) / TB_CH;
     if (chunks <= 0 || a.n_pairs <= 0) return;
     tile_count_kernel<<<chunks, TB_THREADS, (size_t)2 * a.tiles_per_view * 4, s>>>(
-        a.P, a.n_pairs, a.grid_x, a.tiles_per_view, a.pairs, a.offsets, a.hist, a.chunk_pairs, a.cap, a.overflow, a.ctl);
+        a.P, a.n_pairs, a.grid_x, a.tiles_per_view, a.row0, a.pairs, a.offsets, a.hist, a.chunk_pairs, a.cap, a.overflow, a.ctl);
 }
 void launch_tile_scan(const TileBinArgs& a, cudaStream_t s) {
     const int nt = 2 * a.tiles_per_view;
@@ -361,13 +360,14 @@ void launch_tile_scan(const TileBinArgs& a, cudaStream_t s) {
     const int rows_cached = chunks < 4096 ? chunks : 4096;   // 32 B per cached row: <= 128 KB
     tile_scan_kernel<<<(nt + TS_COLS - 1) / TS_COLS, TS_COLS * TS_GROUPS, (size_t)rows_cached * TS_COLS * 2, s>>>(
         nt, a.offsets + (a.n_pairs - 1), a.cap, a.hist, a.base, a.tile_total, rows_cached, a.ctl);
-    tile_starts_kernel<<<1, 1024, 0, s>>>(nt, a.tile_total, a.ranges, a.ctl);
+    tile_starts_kernel<<<1, 1024, 0, s>>>(nt, a.tiles_per_view, a.tiles_global, a.row0 * a.grid_x, a.tile_total, a.ranges, a.ctl);
 }
 void launch_tile_scatter(const TileBinArgs& a, cudaStream_t s) {
     const int chunks = (a.cap + TB_CH - 1) / TB_CH;
     if (chunks <= 0 || a.n_pairs <= 0) return;
     tile_scatter_kernel<<<chunks, TB_THREADS, (size_t)2 * a.tiles_per_view * 5 * 4, s>>>(
-        a.P, a.n_pairs, a.grid_x, a.tiles_per_view, a.pairs, a.offsets, a.chunk_pairs, a.base, a.ranges, a.values, a.cap, a.ctl);
+        a.P, a.n_pairs, a.grid_x, a.tiles_per_view, a.row0, a.tiles_global, a.pairs, a.offsets, a.chunk_pairs, a.base, a.ranges, a.values,
+        a.cap, a.ctl);
 }
 
 // Parity-test helper: tile id of every slot of the per-tile lists (what the sorted keys of the reference hold in
