@@ -413,14 +413,14 @@ struct GsevtEngine {
     uint64_t *pairs = nullptr, *pairs_sorted = nullptr;   // {tile rect | pair id}: projection order / depth order
     void* sortA_temp = nullptr; size_t sortA_bytes = 0;
     // tile binning (tilebin.cu): per-chunk tile counts, their prefix over the chunks, chunk pair ranges, per-tile totals
-    uint16_t* tb_hist = nullptr; uint32_t* tb_base = nullptr; uint2* tb_chunks = nullptr; uint32_t* tb_total = nullptr;
+    uint16_t* tb_hist = nullptr; uint32_t* tb_base = nullptr; uint32_t* tb_total = nullptr;
     size_t tb_items = 0, tb_rows = 0;    // allocated hist / base elements, chunk rows
     // radix fallback when the strip has more tiles than the counting kernels bin in shared memory (binning.cu):
     // (u16 tile key, u32 id) records, double-buffered for a CUB sort
     int bin_path = 0;                    // 0 tile binning by counting, 1 emit + radix sort + range scan
     uint16_t *keys_u = nullptr, *keys = nullptr;
     uint32_t* vals_u = nullptr;
-    void* sort_temp = nullptr; size_t sort_bytes = 0; long long radix_cap = 0;
+    void* sort_temp = nullptr; size_t sort_bytes = 0; long long radix_cap = 0, inst_cap = 0;
     uint32_t* vals = nullptr;            // per-tile lists: Gaussian index per slot
     uint2* ranges = nullptr;
     uint32_t* hitmask = nullptr; size_t hitmask_stride = 0;   // forward -> backward: what each warp blended
@@ -503,16 +503,15 @@ static int ensure_capacity(GsevtEngine* e, long long slots, cudaStream_t s) {
     return rc ? GSEVT_ECUDA : 0;
 }
 
-// The tile-binning kernels keep 5 words per bin in shared memory: above this many bins (2 x tiles of the strip) a CTA
-// no longer shares an SM and the per-bin bookkeeping outweighs the 4096 instances of a chunk — measured at 2 x 3600
-// tiles (1280x720 unsplit): 1.5 ms against 0.77 ms for emit + radix sort, which is then used instead.
+// The tile-binning kernels keep 5 words per bin (= tile of the strip, one view) in shared memory; above this many bins
+// the per-bin bookkeeping outweighs the 4096 instances of a chunk and emit + radix sort is used instead.
 #define GSEVT_TILEBIN_MAX_BINS 4096
 
 // Picks the binning path for the current level / strip and (re)sizes its work buffers for e->sort_n instance slots
 // (never inside a captured graph).
 static int ensure_binning(GsevtEngine* e, cudaStream_t s) {
     const LevelInfo& L = e->lv[e->cur_level];
-    const int bins = 2 * (e->strip_y1 - e->strip_y0) * L.gx;
+    const int bins = (e->strip_y1 - e->strip_y0) * L.gx;   // per view: a chunk of the tile binning holds one view
     e->bin_path = bins <= GSEVT_TILEBIN_MAX_BINS ? 0 : 1;
     auto quiesce = [&]() {
         cudaStreamSynchronize(s);
@@ -520,26 +519,31 @@ static int ensure_binning(GsevtEngine* e, cudaStream_t s) {
         if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
     };
     int rc = 0;
+    if ((long long)e->sort_n > e->inst_cap) {   // (tile, id) per instance: both paths
+        quiesce();
+        dev_free(e, e->keys_u); dev_free(e, e->vals_u);
+        e->keys_u = nullptr; e->vals_u = nullptr;
+        e->inst_cap = (long long)e->sort_n + e->sort_n / 4;
+        rc |= dev_alloc(e, &e->keys_u, (size_t)e->inst_cap);
+        rc |= dev_alloc(e, &e->vals_u, (size_t)e->inst_cap);
+    }
     if (e->bin_path == 0) {
-        const size_t rows = tilebin_chunks(e->sort_n), items = rows * (size_t)bins;
+        const size_t rows = tilebin_chunks(e->sort_n) + 1, items = rows * (size_t)bins;
         if (items > e->tb_items || rows > e->tb_rows) {
             quiesce();
-            dev_free(e, e->tb_hist); dev_free(e, e->tb_base); dev_free(e, e->tb_chunks);
-            e->tb_hist = nullptr; e->tb_base = nullptr; e->tb_chunks = nullptr;
+            dev_free(e, e->tb_hist); dev_free(e, e->tb_base);
+            e->tb_hist = nullptr; e->tb_base = nullptr;
             e->tb_items = items + items / 4; e->tb_rows = rows + rows / 4;
             rc |= dev_alloc(e, &e->tb_hist, e->tb_items);
             rc |= dev_alloc(e, &e->tb_base, e->tb_items);
-            rc |= dev_alloc(e, &e->tb_chunks, e->tb_rows);
         }
     } else if ((long long)e->sort_n > e->radix_cap) {
         quiesce();
-        dev_free(e, e->keys_u); dev_free(e, e->keys); dev_free(e, e->vals_u); dev_free(e, e->sort_temp);
-        e->keys_u = e->keys = nullptr; e->vals_u = nullptr; e->sort_temp = nullptr;
+        dev_free(e, e->keys); dev_free(e, e->sort_temp);
+        e->keys = nullptr; e->sort_temp = nullptr;
         e->radix_cap = (long long)e->sort_n + e->sort_n / 4;
         e->sort_bytes = sort16_temp_bytes((int)e->radix_cap);
-        rc |= dev_alloc(e, &e->keys_u, (size_t)e->radix_cap);
         rc |= dev_alloc(e, &e->keys, (size_t)e->radix_cap);
-        rc |= dev_alloc(e, &e->vals_u, (size_t)e->radix_cap);
         rc |= dev_alloc(e, (char**)&e->sort_temp, e->sort_bytes);
     }
     return rc ? GSEVT_ECUDA : 0;
@@ -605,7 +609,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
         TileBinArgs tb;
         tb.P = P; tb.n_pairs = nv; tb.grid_x = L.gx;
         tb.tiles_per_view = (e->strip_y1 - e->strip_y0) * L.gx; tb.row0 = e->strip_y0; tb.tiles_global = tiles;
-        tb.pairs = e->pairs_sorted; tb.offsets = e->offsets; tb.hist = e->tb_hist; tb.base = e->tb_base; tb.chunk_pairs = e->tb_chunks;
+        tb.pairs = e->pairs_sorted; tb.offsets = e->offsets; tb.n_vis = e->n_vis; tb.hist = e->tb_hist; tb.base = e->tb_base; tb.inst_tile = e->keys_u; tb.inst_id = e->vals_u;
         tb.tile_total = e->tb_total; tb.ranges = e->ranges; tb.values = e->vals; tb.cap = e->sort_n; tb.overflow = e->overflow;
         tb.ctl = e->ctl;
         launch_tile_count(tb, s);
@@ -777,7 +781,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->active_count, 1);
     rc |= dev_alloc(e, (char**)&e->scan_temp, e->scan_bytes);
     rc |= dev_alloc(e, (char**)&e->comp_state, preprocess_map_state_bytes(P));
-    rc |= dev_alloc(e, &e->n_vis, 1);
+    rc |= dev_alloc(e, &e->n_vis, 2);
     rc |= dev_alloc(e, &e->depth_key, p2);
     rc |= dev_alloc(e, &e->depth_sorted, p2);
     rc |= dev_alloc(e, &e->pairs, p2);
@@ -786,7 +790,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
     rc |= dev_alloc(e, &e->tb_total, 2 * (size_t)L0.gx * L0.gy);
     rc |= dev_alloc(e, &e->ranges, 2 * (size_t)L0.gx * L0.gy);
-    if (tilebin_configure(GSEVT_TILEBIN_MAX_BINS / 2)) { set_error("image too large for the tile binning kernels"); gsevt_engine_destroy(e); return GSEVT_EINVAL; }
+    if (tilebin_configure(GSEVT_TILEBIN_MAX_BINS)) { set_error("image too large for the tile binning kernels"); gsevt_engine_destroy(e); return GSEVT_EINVAL; }
     e->hitmask_stride = hitmask_stride_for(e, e->cap);
     rc |= dev_alloc(e, &e->hitmask, 8 * e->hitmask_stride);
     rc |= dev_alloc(e, &e->gray, 2 * hw);

@@ -175,6 +175,82 @@ __device__ void adam_group(EngineCtl* c, int group, const float* grad, double lr
     }
 }
 
+// Optimiser step, convergence test, pose / velocity update and stage logic of one iteration (single thread).  `c` points
+// at a copy of the control block WITHOUT the loss history (shared memory); the history stays in global memory.
+__device__ void engine_control(EngineCtl* c, float* losses, const float* s_g, int* host_flag, ViewParams* views,
+                               const float* bg3) {
+    for (int k = 0; k < GSEVT_NPART; k++) c->grads[k] = s_g[k];
+    if (c->eval_only) {
+        c->level_done = 1;   // one-shot
+        return;
+    }
+    c->iters_executed += 1;
+    if (c->n_losses < GSEVT_MAX_LOSSES) losses[c->n_losses] = c->last_loss;
+    c->n_losses += 1;
+
+    // learning rates (tracker.py:161-170,188-202)
+    double lr[4] = {c->lr_base[0], c->lr_base[1], c->lr_base[2], c->lr_base[3]};
+    if (c->opt_vel) {
+        const int k = c->optim_iter - c->start_vel_opt_iter;
+        const double fraction_num = c->max_optim_iter / 2.0;
+        const double fraction = (k >= 1 && (double)k <= fraction_num) ? (double)k / fraction_num : 1.0;
+        lr[0] *= fraction; lr[1] *= fraction; lr[2] *= (1.0 - fraction); lr[3] *= (1.0 - fraction);
+    }
+    // gradient slots: grads[0:3] rho -> cam_trans_delta, [3:6] theta -> cam_rot_delta,
+    //                 [6:9] v -> cam_v_delta, [9:12] w -> cam_w_delta
+    float d_rot[3] = {0, 0, 0}, d_trans[3] = {0, 0, 0}, d_w[3] = {0, 0, 0}, d_v[3] = {0, 0, 0};
+    adam_group(c, 0, c->grads + 3, lr[0], d_rot);
+    adam_group(c, 1, c->grads + 0, lr[1], d_trans);
+    if (c->opt_vel) {
+        adam_group(c, 2, c->grads + 9, lr[2], d_w);
+        adam_group(c, 3, c->grads + 6, lr[3], d_v);
+    }
+    // check_convergence (tracker.py:65-76): mean |diff| of the last 11 losses, in double
+    bool converged = false;
+    if (c->n_losses > 10 && c->n_losses <= GSEVT_MAX_LOSSES) {
+        double acc = 0.0;
+        for (int i = c->n_losses - 10; i < c->n_losses; i++) acc += fabs((double)losses[i] - (double)losses[i - 1]);
+        converged = (acc / 10.0) < (double)c->converged_threshold;
+    }
+    // update_vwRT / update_pose (camera.py:129-155)
+    if (c->opt_vel) {
+        for (int i = 0; i < 3; i++) {
+            c->ang_vel[i] += d_w[i];
+            c->lin_vel[i] += d_v[i];
+        }
+    }
+    {
+        const float xi[6] = {d_trans[0], d_trans[1], d_trans[2], d_rot[0], d_rot[1], d_rot[2]};
+        const SE3f nw = se3_mul(se3_exp(xi), load_pose(c));
+        store_pose(c, nw);
+    }
+    // stage logic (tracker.py:224-240)
+    bool done = false;
+    if (converged) {
+        if (!c->opt_vel) {
+            c->opt_vel = 1;
+            c->start_vel_opt_iter = c->optim_iter;
+        } else {
+            done = true;
+        }
+    }
+    if (!done) {
+        if (!c->opt_vel) {
+            if (c->optim_iter >= c->max_optim_iter) done = true;
+        } else if (c->optim_iter >= c->start_vel_opt_iter + c->max_optim_iter) {
+            done = true;
+        }
+    }
+    if (done) {
+        c->level_done = 1;
+        if (host_flag) *host_flag = 1;
+        __threadfence_system();
+    } else {
+        c->optim_iter += 1;
+        pose_setup_device(c, views, bg3);   // the next iteration's two views
+    }
+}
+
 __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineCtl* ctl,
                                                                           const float* __restrict__ partials,
                                                                           int nblocks, int* host_flag,
@@ -231,79 +307,18 @@ __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineC
         }
         return;
     }
-    if (threadIdx.x != 0) return;
-    EngineCtl* c = ctl;
-    for (int k = 0; k < GSEVT_NPART; k++) c->grads[k] = s_g[k];
-    if (c->eval_only) {
-        c->level_done = 1;   // one-shot
-        return;
-    }
-    c->iters_executed += 1;
-    if (c->n_losses < GSEVT_MAX_LOSSES) c->losses[c->n_losses] = c->last_loss;
-    c->n_losses += 1;
-
-    // learning rates (tracker.py:161-170,188-202)
-    double lr[4] = {c->lr_base[0], c->lr_base[1], c->lr_base[2], c->lr_base[3]};
-    if (c->opt_vel) {
-        const int k = c->optim_iter - c->start_vel_opt_iter;
-        const double fraction_num = c->max_optim_iter / 2.0;
-        const double fraction = (k >= 1 && (double)k <= fraction_num) ? (double)k / fraction_num : 1.0;
-        lr[0] *= fraction; lr[1] *= fraction; lr[2] *= (1.0 - fraction); lr[3] *= (1.0 - fraction);
-    }
-    // gradient slots: grads[0:3] rho -> cam_trans_delta, [3:6] theta -> cam_rot_delta,
-    //                 [6:9] v -> cam_v_delta, [9:12] w -> cam_w_delta
-    float d_rot[3] = {0, 0, 0}, d_trans[3] = {0, 0, 0}, d_w[3] = {0, 0, 0}, d_v[3] = {0, 0, 0};
-    adam_group(c, 0, c->grads + 3, lr[0], d_rot);
-    adam_group(c, 1, c->grads + 0, lr[1], d_trans);
-    if (c->opt_vel) {
-        adam_group(c, 2, c->grads + 9, lr[2], d_w);
-        adam_group(c, 3, c->grads + 6, lr[3], d_v);
-    }
-    // check_convergence (tracker.py:65-76): mean |diff| of the last 11 losses, in double
-    bool converged = false;
-    if (c->n_losses > 10 && c->n_losses <= GSEVT_MAX_LOSSES) {
-        double acc = 0.0;
-        for (int i = c->n_losses - 10; i < c->n_losses; i++) acc += fabs((double)c->losses[i] - (double)c->losses[i - 1]);
-        converged = (acc / 10.0) < (double)c->converged_threshold;
-    }
-    // update_vwRT / update_pose (camera.py:129-155)
-    if (c->opt_vel) {
-        for (int i = 0; i < 3; i++) {
-            c->ang_vel[i] += d_w[i];
-            c->lin_vel[i] += d_v[i];
-        }
-    }
-    {
-        const float xi[6] = {d_trans[0], d_trans[1], d_trans[2], d_rot[0], d_rot[1], d_rot[2]};
-        const SE3f nw = se3_mul(se3_exp(xi), load_pose(c));
-        store_pose(c, nw);
-    }
-    // stage logic (tracker.py:224-240)
-    bool done = false;
-    if (converged) {
-        if (!c->opt_vel) {
-            c->opt_vel = 1;
-            c->start_vel_opt_iter = c->optim_iter;
-        } else {
-            done = true;
-        }
-    }
-    if (!done) {
-        if (!c->opt_vel) {
-            if (c->optim_iter >= c->max_optim_iter) done = true;
-        } else if (c->optim_iter >= c->start_vel_opt_iter + c->max_optim_iter) {
-            done = true;
-        }
-    }
-    if (done) {
-        c->level_done = 1;
-        if (host_flag) *host_flag = 1;
-        __threadfence_system();
-    } else {
-        c->optim_iter += 1;
-        pose_setup_device(c, views, bg3);   // the next iteration's two views
-    }
+    // The control block (everything before the loss history) is staged in shared memory: the serial control code
+    // below makes ~200 dependent accesses to it, each an L2 round trip when made in place.  All threads copy it in,
+    // thread 0 runs the control logic on the copy, all threads copy it back.
+    constexpr int HOT_WORDS = (int)(offsetof(EngineCtl, losses) / 4);
+    __shared__ __align__(16) uint32_t s_ctl[HOT_WORDS];
+    for (int i = threadIdx.x; i < HOT_WORDS; i += blockDim.x) s_ctl[i] = reinterpret_cast<const uint32_t*>(ctl)[i];
+    __syncthreads();
+    if (threadIdx.x == 0) engine_control(reinterpret_cast<EngineCtl*>(s_ctl), ctl->losses, s_g, host_flag, views, bg3);
+    __syncthreads();
+    for (int i = threadIdx.x; i < HOT_WORDS; i += blockDim.x) reinterpret_cast<uint32_t*>(ctl)[i] = s_ctl[i];
 }
+
 void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, const int* overflow,
                           ViewParams* views, const float* bg3, SplitComm* comm, cudaStream_t s) {
     engine_update_kernel<<<1, 32 * GSEVT_NPART, 0, s>>>(ctl, partials, nblocks, host_flag, overflow, views, bg3, comm);

@@ -111,7 +111,7 @@ struct PreMapArgs {
     uint32_t* depth_key;      // float bits of the view depth
     uint64_t* pairs;          // {tile rect} << 32 | pair id (= view * P + Gaussian)
     unsigned long long* comp_state;   // chained-scan state, preprocess_map_state_bytes(P)
-    uint32_t* n_vis;          // out: number of visible pairs
+    uint32_t* n_vis;          // out: [0] number of visible pairs, [1] number of visible pairs of view 0
     int vis_cap;              // slots the depth sort covers: [*n_vis, vis_cap) are filled with sentinels
     int* overflow;            // set when *n_vis > vis_cap (may be NULL)
     float4* rec;              // [2][2P]
@@ -165,9 +165,11 @@ struct TileBinArgs {
     int row0, tiles_global;     // first tile row of the strip; tiles per view of the whole grid (ranges are indexed globally)
     const uint64_t* pairs;      // depth-sorted {rect | pair id}, n_pairs entries (sentinels with rect 0 at the end)
     const uint32_t* offsets;    // inclusive sum of the rect areas
-    uint16_t* hist;             // [chunks][2 * tiles_per_view]
-    uint32_t* base;             // [chunks][2 * tiles_per_view]
-    uint2* chunk_pairs;         // [chunks] first / last pair of every chunk
+    const uint32_t* n_vis;      // [0] visible pairs, [1] those of view 0 (they come first: the sort key carries the view)
+    uint16_t* hist;             // [chunks + 1][tiles_per_view]: a chunk holds instances of ONE view
+    uint32_t* base;             // [chunks + 1][tiles_per_view]
+    uint16_t* inst_tile;        // [cap] bin of every instance, in sequence order (count -> scatter)
+    uint32_t* inst_id;          // [cap] Gaussian index of every instance, in sequence order
     uint32_t* tile_total;       // [2 * tiles_per_view]
     uint2* ranges;              // [2 * tiles_per_view] out
     uint32_t* values;           // [cap] out: Gaussian index per slot of the per-tile lists

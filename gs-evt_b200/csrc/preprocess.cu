@@ -263,7 +263,7 @@ __device__ __forceinline__ uint32_t compact_base(unsigned long long* state, uint
 __global__ void __launch_bounds__(256) compact_pairs_kernel(int n2, const uint32_t* __restrict__ rect_raw,
                                                             const uint32_t* __restrict__ depth_raw,
                                                             unsigned long long* __restrict__ state, uint32_t* __restrict__ depth_key,
-                                                            uint64_t* __restrict__ pairs, uint32_t* __restrict__ n_vis, int vis_cap,
+                                                            uint64_t* __restrict__ pairs, uint32_t* n_vis, int vis_cap,
                                                             int* __restrict__ overflow, const EngineCtl* __restrict__ ctl) {
     if (ctl && ctl->level_done) return;
     __shared__ uint32_t s_warp[8];
@@ -306,11 +306,16 @@ __global__ void __launch_bounds__(256) compact_pairs_kernel(int n2, const uint32
         if (lane == 0) s_base = base;
     }
     __syncthreads();
+    // Sort key: view << 31 | depth bits (depths are positive floats: bit 31 is free).  The depth sort then also separates
+    // the two views — pairs of different views never meet in a tile list, so the order inside every list is unchanged —
+    // and the tile binning works on one view (half the bins) at a time.  n_vis[1] = number of visible view-0 pairs.
+    const uint32_t Pu = (uint32_t)n2 >> 1;
     uint32_t slot = s_base + before + incl - cnt;
 #pragma unroll
     for (int k = 0; k < CP_ITEMS; k++) {
+        if (i0 + k == Pu) n_vis[1] = slot;
         if (rect[k] != 0u) {
-            depth_key[slot] = key[k];
+            depth_key[slot] = key[k] | (i0 + k >= Pu ? 0x80000000u : 0u);
             pairs[slot] = ((uint64_t)rect[k] << 32) | (uint64_t)(i0 + k);
             slot++;
         }

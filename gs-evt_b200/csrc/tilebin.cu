@@ -7,19 +7,20 @@
 // PARTITION of the instance sequence by tile id — a one-pass counting sort over <= 65535 bins — and the instance
 // records never have to exist in memory:
 //
-//   tile_count    chunk c = instances [c*CH, (c+1)*CH) of the sequence, regenerated from the pairs' tile rects;
-//                 counts per (chunk, tile) in shared memory -> hist[c][tile] (u16)
+//   tile_count    chunk c = instances [c*CH, (c+1)*CH) of the sequence, generated from the pairs' tile rects;
+//                 counts per (chunk, tile) in shared memory -> hist[c][tile] (u16); (tile, id) per instance -> memory
 //   tile_scan     per tile: exclusive prefix of the counts over the chunks -> base[c][tile]; totals per tile
 //   tile_starts   exclusive prefix of the totals over the tiles -> ranges[tile] (untouched tiles stay (0,0) as in
 //                 the reference)
-//   tile_scatter  chunk c again: every instance gets slot ranges[tile].x + base[c][tile] + (its rank among the
-//                 chunk's earlier instances of the same tile) and stores its Gaussian index there.
+//   tile_scatter  chunk c again (coalesced read of its instances): every instance gets slot ranges[tile].x +
+//                 base[c][tile] + (its rank among the chunk's earlier instances of the same tile) and stores its
+//                 Gaussian index there.
 //
 // Stability inside a chunk: the chunk is cut into 8 slices in sequence order, one per warp; a first pass counts per
 // (slice, tile), the prefix over the slices gives every warp its own cursor per tile, and each warp then walks its
 // slice in order, 32 instances per step, ranking equal tiles inside a step with match.any (lower lane = earlier
-// instance).  Traffic: the pairs twice (12 B each), hist/base once each way, 4 B per instance out — against
-// (6 B + 2 x 12 B + 2 B) per instance for emit + two radix passes + range scan.
+// instance).  Traffic: the pairs once (12 B each), hist/base once each way, per instance 6 B out + 6 B in + 4 B out,
+// all but the last coalesced — against (6 B + 2 x 12 B + 2 B) per instance for emit + two radix passes + range scan.
 #include <cstdlib>
 #include "internal.h"
 
@@ -34,6 +35,31 @@ constexpr int TB_SLICE = TB_CH / 8;               // instances per warp slice
 
 __device__ __forceinline__ uint32_t rect_area_d(uint32_t r) {
     return ((r >> 16 & 255u) - (r & 255u)) * ((r >> 24) - (r >> 8 & 255u));
+}
+
+// Chunk b of the instance sequence.  The depth-sorted pairs hold view 0 first (the sort key carries the view in bit 31),
+// so instances [0, N0) belong to view 0 and [N0, total) to view 1; chunks never straddle the boundary: rows [0, R0) of
+// hist / base cut view 0 into pieces of TB_CH instances, rows [R0, R0 + R1) view 1.  A chunk therefore bins one view's
+// tiles only — half the shared memory and half the per-chunk bookkeeping of binning both views at once.
+struct ChunkRange { uint32_t begin, end, view, rows0, rows1; bool active, overflow; };
+__device__ __forceinline__ ChunkRange chunk_range(const uint32_t* __restrict__ off, const uint32_t* __restrict__ n_vis, int n_pairs,
+                                                  int cap, uint32_t b) {
+    ChunkRange c;
+    const uint32_t total = __ldg(off + n_pairs - 1);
+    const uint32_t nv0 = __ldg(n_vis + 1);
+    const uint32_t N0 = nv0 ? __ldg(off + nv0 - 1) : 0u;
+    c.overflow = total > (uint32_t)cap;
+    c.rows0 = (N0 + TB_CH - 1) / TB_CH;
+    c.rows1 = (total - N0 + TB_CH - 1) / TB_CH;
+    if (b < c.rows0) {
+        c.view = 0; c.begin = b * (uint32_t)TB_CH; c.end = min(c.begin + (uint32_t)TB_CH, N0);
+        c.active = true;
+    } else {
+        c.view = 1; c.begin = N0 + (b - c.rows0) * (uint32_t)TB_CH; c.end = min(c.begin + (uint32_t)TB_CH, total);
+        c.active = c.begin < total;
+    }
+    if (c.overflow) c.active = false;
+    return c;
 }
 
 // First index p in [0, n) with off[p] > o, for a non-decreasing off[] with off[n-1] > o.  All 32 lanes call it;
@@ -86,7 +112,7 @@ __device__ __forceinline__ PairWork load_pair(const uint64_t* __restrict__ pairs
         w.t1 = (incl < end ? incl : end) - w.excl;
         if (w.t1 < w.t0) w.t1 = w.t0;
         w.wd = (rect >> 16 & 255u) - (rect & 255u);
-        w.tbase = ((uint32_t)pr >= (uint32_t)P ? (uint32_t)tiles_per_view : 0u) + ((rect >> 8 & 255u) - (uint32_t)row0) * (uint32_t)gx + (rect & 255u);
+        w.tbase = ((rect >> 8 & 255u) - (uint32_t)row0) * (uint32_t)gx + (rect & 255u);   // bin = tile of the strip (one view per chunk)
     }
     return w;
 }
@@ -138,31 +164,39 @@ __device__ __forceinline__ void visit_chunk(const uint64_t* __restrict__ pairs, 
 // ---- 1. counts per (chunk, tile) ------------------------------------------------------------------
 __global__ void __launch_bounds__(TB_THREADS) tile_count_kernel(int P, int n_pairs, int gx, int tiles_per_view, int row0,
                                                                  const uint64_t* __restrict__ pairs,
-                                                                 const uint32_t* __restrict__ off, uint16_t* __restrict__ hist,
-                                                                 uint2* __restrict__ chunk_pairs, int cap, int* __restrict__ overflow,
+                                                                 const uint32_t* __restrict__ off, const uint32_t* __restrict__ n_vis,
+                                                                 uint16_t* __restrict__ hist, uint16_t* __restrict__ inst_tile, uint32_t* __restrict__ inst_id,
+                                                                 int cap, int* __restrict__ overflow,
                                                                  const EngineCtl* __restrict__ ctl) {
     if (ctl && ctl->level_done) return;
-    extern __shared__ uint32_t s_hist[];   // [2 * tiles_per_view]
+    extern __shared__ uint32_t s_hist[];   // [tiles_per_view]
     __shared__ uint32_t s_p[2];
-    const uint32_t total = __ldg(off + n_pairs - 1);
-    if (total > (uint32_t)cap) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
-        return;
-    }
-    const uint32_t begin = blockIdx.x * (uint32_t)TB_CH;
-    if (begin >= total) return;
-    const uint32_t end = begin + TB_CH < total ? begin + TB_CH : total;
-    const int nt = 2 * tiles_per_view;
+    __shared__ uint16_t s_tile[TB_CH];     // the chunk's instances in sequence order, staged so that they leave coalesced
+    __shared__ uint32_t s_id[TB_CH];
+    const ChunkRange cr = chunk_range(off, n_vis, n_pairs, cap, blockIdx.x);
+    if (cr.overflow && blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1;
+    if (!cr.active) return;
+    const uint32_t begin = cr.begin, end = cr.end;
+    const int nt = tiles_per_view;
     for (int t = threadIdx.x; t < nt; t += TB_THREADS) s_hist[t] = 0;
     chunk_pair_range(off, (uint32_t)n_pairs, begin, end, s_p);
     __syncthreads();
     const uint32_t p_lo = s_p[0], p_hi = s_p[1];
-    if (threadIdx.x == 0) chunk_pairs[blockIdx.x] = make_uint2(p_lo, p_hi);
-    visit_chunk(pairs, off, p_lo, p_hi, begin, end, P, gx, tiles_per_view, row0,
-                [&](uint32_t, uint32_t tile, uint32_t) { atomicAdd(&s_hist[tile], 1u); });
+    visit_chunk(pairs, off, p_lo, p_hi, begin, end, P, gx, tiles_per_view, row0, [&](uint32_t li, uint32_t tile, uint32_t id) {
+        atomicAdd(&s_hist[tile], 1u);
+        s_tile[li] = (uint16_t)tile;
+        s_id[li] = id;
+    });
     __syncthreads();
     uint16_t* row = hist + (size_t)blockIdx.x * nt;
     for (int t = threadIdx.x; t < nt; t += TB_THREADS) row[t] = (uint16_t)s_hist[t];
+    // (tile, id) of every instance, for the scatter pass: 6 B per instance, written and read once, both coalesced —
+    // cheaper than walking the rects a second time (measured: the walk was 44 % of the scatter kernel's instructions)
+    const uint32_t n_local = end - begin;
+    for (uint32_t li = threadIdx.x; li < n_local; li += TB_THREADS) {
+        inst_tile[begin + li] = s_tile[li];
+        inst_id[begin + li] = s_id[li];
+    }
 }
 
 // ---- 2. prefix over the chunks, per tile ----------------------------------------------------------
@@ -170,7 +204,8 @@ __global__ void __launch_bounds__(TB_THREADS) tile_count_kernel(int P, int n_pai
 // memory (all loads independent, in flight together) and sums them, the groups are scanned through shared memory, then
 // every thread re-walks its rows from shared memory writing the running prefix.  150 CTAs for 2 x 1200 tiles.
 constexpr int TS_COLS = 16, TS_GROUPS = 64;
-__global__ void __launch_bounds__(TS_COLS * TS_GROUPS) tile_scan_kernel(int nt, const uint32_t* __restrict__ total_dev, int cap,
+__global__ void __launch_bounds__(TS_COLS * TS_GROUPS) tile_scan_kernel(int nt, int n_pairs, const uint32_t* __restrict__ off,
+                                                                         const uint32_t* __restrict__ n_vis, int cap,
                                                                          const uint16_t* __restrict__ hist,
                                                                          uint32_t* __restrict__ base,
                                                                          uint32_t* __restrict__ tile_total, int rows_cached,
@@ -178,17 +213,19 @@ __global__ void __launch_bounds__(TS_COLS * TS_GROUPS) tile_scan_kernel(int nt, 
     if (ctl && ctl->level_done) return;
     extern __shared__ uint16_t s_rows[];                 // [rows_cached][TS_COLS]
     __shared__ uint32_t s_part[TS_GROUPS][TS_COLS + 1];
-    const uint32_t total = *total_dev;
+    const int view = blockIdx.y;                         // nt = tiles per view; this view's chunks are rows [row_lo, row_lo + nact)
+    const ChunkRange cr = chunk_range(off, n_vis, n_pairs, cap, 0u);
     const int col = threadIdx.x & (TS_COLS - 1), g = threadIdx.x / TS_COLS;
     const int tile = blockIdx.x * TS_COLS + col;
-    const int nact = total > (uint32_t)cap ? 0 : (int)((total + TB_CH - 1) / TB_CH);
+    const int row_lo = view ? (int)cr.rows0 : 0;
+    const int nact = cr.overflow ? 0 : (int)(view ? cr.rows1 : cr.rows0);
     const int R = (nact + TS_GROUPS - 1) / TS_GROUPS;
     const int r0 = g * R, r1 = min(r0 + R, nact);
     uint32_t sum = 0;
     if (tile < nt) {
 #pragma unroll 8
         for (int r = r0; r < r1; r++) {
-            const uint16_t v = __ldg(hist + (size_t)r * nt + tile);
+            const uint16_t v = __ldg(hist + (size_t)(row_lo + r) * nt + tile);
             if (r < rows_cached) s_rows[r * TS_COLS + col] = v;
             sum += v;
         }
@@ -203,13 +240,13 @@ __global__ void __launch_bounds__(TS_COLS * TS_GROUPS) tile_scan_kernel(int nt, 
             s_part[k][col] = run;
             run += v;
         }
-        if (tile < nt) tile_total[tile] = run;
+        if (tile < nt) tile_total[view * nt + tile] = run;
     }
     __syncthreads();
     if (tile < nt) {
         uint32_t run = s_part[g][col];
         for (int r = r0; r < r1; r++) {
-            const size_t i = (size_t)r * nt + tile;
+            const size_t i = (size_t)(row_lo + r) * nt + tile;
             base[i] = run;
             run += r < rows_cached ? s_rows[r * TS_COLS + col] : __ldg(hist + i);
         }
@@ -260,41 +297,48 @@ __global__ void __launch_bounds__(1024) tile_starts_kernel(int nt, int tiles_loc
 }
 
 // ---- 4. stable scatter ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(int P, int n_pairs, int gx, int tiles_per_view, int row0, int tiles_global,
-                                                                   const uint64_t* __restrict__ pairs,
-                                                                   const uint32_t* __restrict__ off,
-                                                                   const uint2* __restrict__ chunk_pairs,
+__global__ void __launch_bounds__(TB_THREADS, 4) tile_scatter_kernel(int n_pairs, int gx, int tiles_per_view, int row0, int tiles_global,
+                                                                   const uint32_t* __restrict__ off, const uint32_t* __restrict__ n_vis,
+                                                                   const uint16_t* __restrict__ inst_tile,
+                                                                   const uint32_t* __restrict__ inst_id,
                                                                    const uint32_t* __restrict__ base,
                                                                    const uint2* __restrict__ ranges, uint32_t* __restrict__ values,
                                                                    int cap, const EngineCtl* __restrict__ ctl) {
     if (ctl && ctl->level_done) return;
     extern __shared__ uint32_t s_mem[];
-    const int nt = 2 * tiles_per_view;
+    const int nt = tiles_per_view;
     uint32_t* s_gbase = s_mem;                 // [nt]    first slot of (this chunk, tile)
     uint32_t* s_cnt = s_mem + nt;              // [4][nt] per-slice counts, then cursors: slice w in word w & 3, half w >> 2
-    __shared__ uint16_t s_tile[TB_CH];         // tile id of every instance of the chunk
-    __shared__ uint32_t s_id[TB_CH];           // Gaussian index of every instance of the chunk
-    const uint32_t total = __ldg(off + n_pairs - 1);
-    if (total > (uint32_t)cap) return;         // flagged by tile_count_kernel: the iteration is void
-    const uint32_t begin = blockIdx.x * (uint32_t)TB_CH;
-    if (begin >= total) return;
-    const uint32_t end = begin + TB_CH < total ? begin + TB_CH : total;
+    uint32_t* s_lstart = s_mem + 5 * nt;       // [nt]    first position of the tile in the chunk's tile-ordered staging
+    uint16_t* s_stamp = reinterpret_cast<uint16_t*>(s_mem + 6 * nt);   // [nt] scratch of the distinct-tiles test
+    __shared__ uint32_t s_out_id[TB_CH];       // the chunk's instances ordered by (tile, rank): what leaves for tile t is one
+    __shared__ uint16_t s_out_tile[TB_CH];     // contiguous run in shared AND in global memory -> few store sectors per warp
+    __shared__ uint32_t s_wsum[8];
+    const ChunkRange cr = chunk_range(off, n_vis, n_pairs, cap, blockIdx.x);
+    if (!cr.active) return;                    // (an overflow was flagged by tile_count_kernel: the iteration is void)
+    const uint32_t begin = cr.begin, end = cr.end;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // this lane's instances: slice `warp` of the chunk, step st -> local index warp * TB_SLICE + st * 32 + lane
+    constexpr int STEPS = TB_SLICE / 32;
+    const uint32_t first = begin + (uint32_t)warp * TB_SLICE + (uint32_t)lane;
+    uint32_t tile[STEPS], id[STEPS];
+#pragma unroll
+    for (int st = 0; st < STEPS; st++) {
+        const uint32_t o = first + (uint32_t)st * 32u;
+        tile[st] = o < end ? (uint32_t)__ldg(inst_tile + o) : 0xFFFFFFFFu;
+        id[st] = o < end ? __ldg(inst_id + o) : 0u;
+    }
     const uint32_t* brow = base + (size_t)blockIdx.x * nt;
     for (int t = threadIdx.x; t < nt; t += TB_THREADS) {
-        const int view = t >= tiles_per_view ? 1 : 0;
-        s_gbase[t] = __ldg(&ranges[view * tiles_global + row0 * gx + (t - view * tiles_per_view)].x) + __ldg(brow + t);
+        s_gbase[t] = __ldg(&ranges[(int)cr.view * tiles_global + row0 * gx + t].x) + __ldg(brow + t);
         s_cnt[t] = 0; s_cnt[nt + t] = 0; s_cnt[2 * nt + t] = 0; s_cnt[3 * nt + t] = 0;
     }
-    const uint2 pr = chunk_pairs[blockIdx.x];
     __syncthreads();
-    // regenerate the chunk's instances: (tile, id) per local instance index, plus the per-slice counts
-    visit_chunk(pairs, off, pr.x, pr.y, begin, end, P, gx, tiles_per_view, row0, [&](uint32_t li, uint32_t tile, uint32_t id) {
-        s_tile[li] = (uint16_t)tile;
-        s_id[li] = id;
-        const uint32_t slice = li / TB_SLICE;
-        atomicAdd(&s_cnt[(slice & 3u) * nt + tile], 1u << (16u * (slice >> 2)));
-    });
+    const uint32_t shift = 16u * (uint32_t)(warp >> 2);
+    uint32_t* my_cnt = s_cnt + (warp & 3) * nt;
+#pragma unroll
+    for (int st = 0; st < STEPS; st++)
+        if (tile[st] != 0xFFFFFFFFu) atomicAdd(&my_cnt[tile[st]], 1u << shift);
     __syncthreads();
     // counts -> exclusive prefix over the 8 slices, in place
     for (int t = threadIdx.x; t < nt; t += TB_THREADS) {
@@ -305,28 +349,82 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(int P, int n_p
 #pragma unroll
         for (int k = 0; k < 4; k++) { const uint32_t c = w[k] >> 16; w[k] = (w[k] & 0xFFFFu) | (run << 16); run += c; }
         s_cnt[t] = w[0]; s_cnt[nt + t] = w[1]; s_cnt[2 * nt + t] = w[2]; s_cnt[3 * nt + t] = w[3];
+        s_lstart[t] = run;   // the chunk's count for this tile; prefixed over the tiles below
     }
     __syncthreads();
-    // every warp walks its slice in order
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t shift = 16u * (uint32_t)(warp >> 2);
-    uint32_t* my_cnt = s_cnt + (warp & 3) * nt;
-    const uint32_t n_local = end - begin;
-#pragma unroll 4
-    for (int st = 0; st < TB_SLICE / 32; st++) {
-        const uint32_t li = (uint32_t)warp * TB_SLICE + (uint32_t)st * 32u + (uint32_t)lane;
-        const bool valid = li < n_local;
-        if (!__any_sync(0xffffffffu, valid)) break;
-        const uint32_t tile = valid ? (uint32_t)s_tile[li] : 0xFFFFFFFFu;
-        const unsigned m = __match_any_sync(0xffffffffu, tile);
-        const int leader = __ffs(m) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) old = atomicAdd(&my_cnt[tile], (uint32_t)__popc(m) << shift);
-        old = __shfl_sync(0xffffffffu, old, leader);
-        if (valid) {
-            const uint32_t pos = s_gbase[tile] + ((old >> shift) & 0xFFFFu) + (uint32_t)__popc(m & lt);
-            values[pos] = s_id[li];
+    {
+        // exclusive prefix of the per-tile counts over the tiles: where each tile's run starts in the staging arrays
+        const int per = (nt + TB_THREADS - 1) / TB_THREADS, t0 = threadIdx.x * per;
+        uint32_t sum = 0;
+        for (int k = 0; k < per; k++) sum += t0 + k < nt ? s_lstart[t0 + k] : 0u;
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
         }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t run = incl - sum;
+        for (int w = 0; w < warp; w++) run += s_wsum[w];
+        for (int k = 0; k < per; k++) {
+            if (t0 + k < nt) { const uint32_t c = s_lstart[t0 + k]; s_lstart[t0 + k] = run; run += c; }
+        }
+    }
+    __syncthreads();
+    // every warp walks its slice in order: rank among the chunk's instances of the same tile -> staging position.
+    // Two lanes of a step need ranking against each other only when they hit the same tile.  match.any answers that but
+    // runs ~100 cycles per instruction on a shared unit (it bounded this kernel: 64 % unit utilisation at 26 % issue
+    // slots), so a step first tests "all tiles distinct" with a stamp: every lane writes its own id to s_stamp[tile]
+    // and reads it back — if two lanes share a tile at most one reads its own id back.  A foreign warp's stamp can only
+    // produce a false alarm.  Steps with distinct tiles (about two in three at 1200 tiles) take one atomic per lane;
+    // only the others fall back to match.any.  Shared-memory atomics of one warp execute in program order, which is
+    // what keeps the ranks stable across steps.  Software-pipelined in groups of 8 steps.
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint16_t my_stamp = (uint16_t)threadIdx.x;
+    constexpr int GROUP = 8;
+#pragma unroll
+    for (int g0 = 0; g0 < STEPS; g0 += GROUP) {
+        unsigned clash = 0;   // bit k: step g0 + k has two lanes on one tile (or a false alarm)
+        uint32_t old[GROUP];
+#pragma unroll
+        for (int k = 0; k < GROUP; k++)
+            if (tile[g0 + k] != 0xFFFFFFFFu) s_stamp[tile[g0 + k]] = (uint16_t)(my_stamp ^ (k << 8));
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < GROUP; k++) {
+            const bool lost = tile[g0 + k] != 0xFFFFFFFFu && s_stamp[tile[g0 + k]] != (uint16_t)(my_stamp ^ (k << 8));
+            if (__any_sync(0xffffffffu, lost)) clash |= 1u << k;
+        }
+#pragma unroll
+        for (int k = 0; k < GROUP; k++) {
+            const uint32_t t = tile[g0 + k];
+            uint32_t o = 0, rank = 0;
+            if (clash >> k & 1u) {
+                const unsigned m = __match_any_sync(0xffffffffu, t);
+                const int leader = __ffs(m) - 1;
+                if (t != 0xFFFFFFFFu && lane == leader) o = atomicAdd(&my_cnt[t], (uint32_t)__popc(m) << shift);
+                o = __shfl_sync(0xffffffffu, o, leader);
+                rank = (uint32_t)__popc(m & lt);
+            } else if (t != 0xFFFFFFFFu) {
+                o = atomicAdd(&my_cnt[t], 1u << shift);
+            }
+            old[k] = ((o >> shift) & 0xFFFFu) + rank;
+        }
+#pragma unroll
+        for (int k = 0; k < GROUP; k++) {
+            if (tile[g0 + k] != 0xFFFFFFFFu) {
+                const uint32_t pos = s_lstart[tile[g0 + k]] + old[k];
+                s_out_id[pos] = id[g0 + k];
+                s_out_tile[pos] = (uint16_t)tile[g0 + k];
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n_local = end - begin;
+    for (uint32_t i = threadIdx.x; i < n_local; i += TB_THREADS) {
+        const uint32_t t = s_out_tile[i];
+        values[s_gbase[t] + (i - s_lstart[t])] = s_out_id[i];
     }
 }
 
@@ -339,35 +437,36 @@ int tilebin_configure(int max_tiles_per_view) {
         const uint32_t k = (uint32_t)atoi(v);
         if (k >= 1 && k <= 65536) cudaMemcpyToSymbol(TB_SMALL, &k, sizeof(k));
     }
-    const size_t smem = (size_t)2 * max_tiles_per_view * 5 * sizeof(uint32_t);
-    if (smem + TB_CH * 6 + 64 > 227 * 1024) return -1;
+    const size_t smem = (size_t)max_tiles_per_view * 26;
+    if (smem + TB_CH * 6 + 128 > 227 * 1024) return -1;
     cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * max_tiles_per_view * 4));
+    cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)max_tiles_per_view * 4));
     cudaFuncSetAttribute(tile_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * TS_COLS * 2);
     return 0;
 }
 
 void launch_tile_count(const TileBinArgs& a, cudaStream_t s) {
-    const int chunks = (a.cap + TB_CH - 1) / TB_CH;
-    if (chunks <= 0 || a.n_pairs <= 0) return;
-    tile_count_kernel<<<chunks, TB_THREADS, (size_t)2 * a.tiles_per_view * 4, s>>>(
-        a.P, a.n_pairs, a.grid_x, a.tiles_per_view, a.row0, a.pairs, a.offsets, a.hist, a.chunk_pairs, a.cap, a.overflow, a.ctl);
+    const int chunks = (a.cap + TB_CH - 1) / TB_CH + 1;   // + 1: the view boundary may cut one chunk in two
+    if (a.n_pairs <= 0) return;
+    tile_count_kernel<<<chunks, TB_THREADS, (size_t)a.tiles_per_view * 4, s>>>(
+        a.P, a.n_pairs, a.grid_x, a.tiles_per_view, a.row0, a.pairs, a.offsets, a.n_vis, a.hist, a.inst_tile, a.inst_id, a.cap,
+        a.overflow, a.ctl);
 }
 void launch_tile_scan(const TileBinArgs& a, cudaStream_t s) {
-    const int nt = 2 * a.tiles_per_view;
+    const int nt = a.tiles_per_view;
     if (a.n_pairs <= 0) return;
-    const int chunks = (a.cap + TB_CH - 1) / TB_CH;
+    const int chunks = (a.cap + TB_CH - 1) / TB_CH + 1;
     const int rows_cached = chunks < 4096 ? chunks : 4096;   // 32 B per cached row: <= 128 KB
-    tile_scan_kernel<<<(nt + TS_COLS - 1) / TS_COLS, TS_COLS * TS_GROUPS, (size_t)rows_cached * TS_COLS * 2, s>>>(
-        nt, a.offsets + (a.n_pairs - 1), a.cap, a.hist, a.base, a.tile_total, rows_cached, a.ctl);
-    tile_starts_kernel<<<1, 1024, 0, s>>>(nt, a.tiles_per_view, a.tiles_global, a.row0 * a.grid_x, a.tile_total, a.ranges, a.ctl);
+    tile_scan_kernel<<<dim3((nt + TS_COLS - 1) / TS_COLS, 2), TS_COLS * TS_GROUPS, (size_t)rows_cached * TS_COLS * 2, s>>>(
+        nt, a.n_pairs, a.offsets, a.n_vis, a.cap, a.hist, a.base, a.tile_total, rows_cached, a.ctl);
+    tile_starts_kernel<<<1, 1024, 0, s>>>(2 * nt, a.tiles_per_view, a.tiles_global, a.row0 * a.grid_x, a.tile_total, a.ranges, a.ctl);
 }
 void launch_tile_scatter(const TileBinArgs& a, cudaStream_t s) {
-    const int chunks = (a.cap + TB_CH - 1) / TB_CH;
-    if (chunks <= 0 || a.n_pairs <= 0) return;
-    tile_scatter_kernel<<<chunks, TB_THREADS, (size_t)2 * a.tiles_per_view * 5 * 4, s>>>(
-        a.P, a.n_pairs, a.grid_x, a.tiles_per_view, a.row0, a.tiles_global, a.pairs, a.offsets, a.chunk_pairs, a.base, a.ranges, a.values,
-        a.cap, a.ctl);
+    const int chunks = (a.cap + TB_CH - 1) / TB_CH + 1;
+    if (a.n_pairs <= 0) return;
+    tile_scatter_kernel<<<chunks, TB_THREADS, (size_t)a.tiles_per_view * 26, s>>>(
+        a.n_pairs, a.grid_x, a.tiles_per_view, a.row0, a.tiles_global, a.offsets, a.n_vis, a.inst_tile, a.inst_id, a.base, a.ranges,
+        a.values, a.cap, a.ctl);
 }
 
 // Parity-test helper: tile id of every slot of the per-tile lists (what the sorted keys of the reference hold in
