@@ -418,6 +418,7 @@ struct GsevtEngine {
     // radix fallback when the strip has more tiles than the counting kernels bin in shared memory (binning.cu):
     // (u16 tile key, u32 id) records, double-buffered for a CUB sort
     int bin_path = 0;                    // 0 tile binning by counting, 1 emit + radix sort + range scan
+    int bin_mode = 0;                    // gsevt_engine_set_binning: 0 automatic, 1 counting, 2 radix
     uint16_t *keys_u = nullptr, *keys = nullptr;
     uint32_t* vals_u = nullptr;
     void* sort_temp = nullptr; size_t sort_bytes = 0; long long radix_cap = 0, inst_cap = 0;
@@ -512,7 +513,7 @@ static int ensure_capacity(GsevtEngine* e, long long slots, cudaStream_t s) {
 static int ensure_binning(GsevtEngine* e, cudaStream_t s) {
     const LevelInfo& L = e->lv[e->cur_level];
     const int bins = (e->strip_y1 - e->strip_y0) * L.gx;   // per view: a chunk of the tile binning holds one view
-    e->bin_path = bins <= GSEVT_TILEBIN_MAX_BINS ? 0 : 1;
+    e->bin_path = e->bin_mode == 2 ? 1 : (bins <= GSEVT_TILEBIN_MAX_BINS ? 0 : 1);
     auto quiesce = [&]() {
         cudaStreamSynchronize(s);
         if (e->graph_stream && e->graph_stream != s) cudaStreamSynchronize(e->graph_stream);
@@ -610,7 +611,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
         tb.P = P; tb.n_pairs = nv; tb.grid_x = L.gx;
         tb.tiles_per_view = (e->strip_y1 - e->strip_y0) * L.gx; tb.row0 = e->strip_y0; tb.tiles_global = tiles;
         tb.pairs = e->pairs_sorted; tb.offsets = e->offsets; tb.n_vis = e->n_vis; tb.hist = e->tb_hist; tb.base = e->tb_base; tb.inst_tile = e->keys_u; tb.inst_id = e->vals_u;
-        tb.tile_total = e->tb_total; tb.ranges = e->ranges; tb.values = e->vals; tb.cap = e->sort_n; tb.overflow = e->overflow;
+        tb.tile_total = e->tb_total; tb.ticket = e->tb_total + 2 * (size_t)e->lv[0].gx * e->lv[0].gy; tb.ranges = e->ranges; tb.values = e->vals; tb.cap = e->sort_n; tb.overflow = e->overflow;
         tb.ctl = e->ctl;
         launch_tile_count(tb, s);
         mark();
@@ -788,7 +789,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->pairs_sorted, p2);
     rc |= dev_alloc(e, (char**)&e->sortA_temp, e->sortA_bytes);
     rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
-    rc |= dev_alloc(e, &e->tb_total, 2 * (size_t)L0.gx * L0.gy);
+    rc |= dev_alloc(e, &e->tb_total, 2 * (size_t)L0.gx * L0.gy + 4);   // per-tile totals + the tile_scan ticket word
     rc |= dev_alloc(e, &e->ranges, 2 * (size_t)L0.gx * L0.gy);
     if (tilebin_configure(GSEVT_TILEBIN_MAX_BINS)) { set_error("image too large for the tile binning kernels"); gsevt_engine_destroy(e); return GSEVT_EINVAL; }
     e->hitmask_stride = hitmask_stride_for(e, e->cap);
@@ -820,6 +821,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     float bg[4] = {cfg->background[0], cfg->background[1], cfg->background[2], 0.f};
     cudaMemcpy(e->bg3, bg, sizeof(bg), cudaMemcpyHostToDevice);
     cudaMemset(e->overflow, 0, 4);
+    cudaMemset(e->tb_total, 0, (2 * (size_t)L0.gx * L0.gy + 4) * 4);
     cudaMemset(e->comp_state, 0, preprocess_map_state_bytes(P));   // epoch 0: nothing published (compact_pairs_kernel)
     cudaMemset(e->loss_partials, 0, ((size_t)e->loss_nb * 3 + 2) * 8);
     cudaMemset(e->grad8, 0, 2 * p2 * 16);
@@ -1308,11 +1310,21 @@ GSEVT_API int gsevt_engine_split_info(GsevtEngine* e, int32_t out6[6], void* str
     return 0;
 }
 
+GSEVT_API int gsevt_engine_set_binning(GsevtEngine* e, int32_t mode) {
+    if (!e || mode < 0 || mode > 2) { set_error("set_binning: bad arguments"); return GSEVT_EINVAL; }
+    if (mode == 1 && e->lv[0].gx * e->lv[0].gy > GSEVT_TILEBIN_MAX_BINS) {
+        set_error("set_binning: %d tiles per view exceed the counting kernels' %d bins", e->lv[0].gx * e->lv[0].gy, GSEVT_TILEBIN_MAX_BINS);
+        return GSEVT_EINVAL;
+    }
+    e->bin_mode = mode;
+    return 0;
+}
+
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e) {
-    // preprocess_map, compact_pairs, {tile_count, tile_scan, tile_starts, tile_scatter | emit_tiles, identify_ranges16},
+    // preprocess_map, compact_pairs, {tile_count, tile_scan, tile_scatter | emit_tiles, identify_ranges16},
     // blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, engine_update; plus CUB library kernels: the depth sort
     // (histogram + exclusive sum + four onesweep passes), the offsets scan, and on the radix path the 16-bit tile sort.
-    return e && e->bin_path == 1 ? 10 : 12;
+    return e && e->bin_path == 1 ? 10 : 11;
 }
 
 }  // extern "C"

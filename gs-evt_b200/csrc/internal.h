@@ -171,6 +171,7 @@ struct TileBinArgs {
     uint16_t* inst_tile;        // [cap] bin of every instance, in sequence order (count -> scatter)
     uint32_t* inst_id;          // [cap] Gaussian index of every instance, in sequence order
     uint32_t* tile_total;       // [2 * tiles_per_view]
+    uint32_t* ticket;           // one zero-initialised word: CTAs of tile_scan done (the last one computes the ranges and resets it)
     uint2* ranges;              // [2 * tiles_per_view] out
     uint32_t* values;           // [cap] out: Gaussian index per slot of the per-tile lists
     int cap;                    // instance slots available; more live instances -> *overflow = 1, nothing written

@@ -226,8 +226,11 @@ __global__ void __launch_bounds__(256, 3) preprocess_map_kernel(PreMapArgs a) {
 // epoch << 34 | flag << 32 | value, flag 1 = this CTA's count, 2 = inclusive prefix.  The epoch (a device counter the
 // last CTA bumps when it is done) makes words of earlier launches read as "not published": no reset pass.  CTAs are
 // dispatched in blockIdx order, so a CTA only ever waits for CTAs that already run.
-constexpr int CP_ITEMS = 8;
-constexpr int CP_TILE = 256 * CP_ITEMS;
+// 512 threads x 16 pairs: few, large tiles keep the look-back short (a resident wave of N CTAs that publish at the same
+// time looks back over up to N / 32 windows of one L2 round trip each: 2048-pair tiles measured 28 us for this pass)
+constexpr int CP_ITEMS = 16;
+constexpr int CP_THREADS = 512;
+constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
 __device__ __forceinline__ uint32_t compact_base(unsigned long long* state, uint32_t tile, uint32_t count, uint32_t epoch) {
     // called by all 32 lanes of warp 0; returns (to every lane) the number of visible pairs in all lower tiles
     const int lane = threadIdx.x & 31;
@@ -260,24 +263,28 @@ __device__ __forceinline__ uint32_t compact_base(unsigned long long* state, uint
     return base;
 }
 
-__global__ void __launch_bounds__(256) compact_pairs_kernel(int n2, const uint32_t* __restrict__ rect_raw,
+__global__ void __launch_bounds__(CP_THREADS, 2) compact_pairs_kernel(int n2, const uint32_t* __restrict__ rect_raw,
                                                             const uint32_t* __restrict__ depth_raw,
                                                             unsigned long long* __restrict__ state, uint32_t* __restrict__ depth_key,
                                                             uint64_t* __restrict__ pairs, uint32_t* n_vis, int vis_cap,
                                                             int* __restrict__ overflow, const EngineCtl* __restrict__ ctl) {
     if (ctl && ctl->level_done) return;
-    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_warp[CP_THREADS / 32];
     __shared__ uint32_t s_base;
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    uint64_t* s_pair = reinterpret_cast<uint64_t*>(s_dyn);                   // [CP_TILE]
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(s_dyn + CP_TILE * 8);      // [CP_TILE]
     uint32_t* epoch_ctr = reinterpret_cast<uint32_t*>(state + gridDim.x);
     const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(epoch_ctr) + 1u;
     const uint32_t tile = blockIdx.x;
     const uint32_t i0 = tile * (uint32_t)CP_TILE + threadIdx.x * (uint32_t)CP_ITEMS;   // the arrays are padded to whole tiles
     uint32_t rect[CP_ITEMS], key[CP_ITEMS];
-    {
-        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rect_raw + i0)), r1 = __ldg(reinterpret_cast<const uint4*>(rect_raw + i0) + 1);
-        const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(depth_raw + i0)), k1 = __ldg(reinterpret_cast<const uint4*>(depth_raw + i0) + 1);
-        rect[0] = r0.x; rect[1] = r0.y; rect[2] = r0.z; rect[3] = r0.w; rect[4] = r1.x; rect[5] = r1.y; rect[6] = r1.z; rect[7] = r1.w;
-        key[0] = k0.x; key[1] = k0.y; key[2] = k0.z; key[3] = k0.w; key[4] = k1.x; key[5] = k1.y; key[6] = k1.z; key[7] = k1.w;
+#pragma unroll
+    for (int q = 0; q < CP_ITEMS / 4; q++) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(rect_raw + i0) + q);
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(depth_raw + i0) + q);
+        rect[4 * q] = r.x; rect[4 * q + 1] = r.y; rect[4 * q + 2] = r.z; rect[4 * q + 3] = r.w;
+        key[4 * q] = d.x; key[4 * q + 1] = d.y; key[4 * q + 2] = d.z; key[4 * q + 3] = d.w;
     }
     uint32_t cnt = 0;
 #pragma unroll
@@ -296,36 +303,44 @@ __global__ void __launch_bounds__(256) compact_pairs_kernel(int n2, const uint32
     __syncthreads();
     uint32_t before = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
+    for (int w = 0; w < CP_THREADS / 32; w++) {
         const uint32_t c = s_warp[w];
         if (w < warp) before += c;
         total += c;
+    }
+    // Sort key: view << 31 | depth bits (depths are positive floats: bit 31 is free).  The depth sort then also separates
+    // the two views — pairs of different views never meet in a tile list, so the order inside every list is unchanged —
+    // and the tile binning works on one view (half the bins) at a time.  n_vis[1] = number of visible view-0 pairs.
+    // The CTA's survivors are squeezed together in shared memory first (while warp 0 looks back for the CTA's base) and
+    // leave with unit-stride stores: written straight from the registers every store instruction hits 32 sectors.
+    const uint32_t Pu = (uint32_t)n2 >> 1;
+    uint32_t local = before + incl - cnt;
+    int boundary = -1;   // position (within the CTA's survivors) in front of pair index P, if this thread holds it
+#pragma unroll
+    for (int k = 0; k < CP_ITEMS; k++) {
+        if (i0 + k == Pu) boundary = (int)local;
+        if (rect[k] != 0u) {
+            s_key[local] = key[k] | (i0 + k >= Pu ? 0x80000000u : 0u);
+            s_pair[local] = ((uint64_t)rect[k] << 32) | (uint64_t)(i0 + k);
+            local++;
+        }
     }
     if (warp == 0) {
         const uint32_t base = compact_base(state, tile, total, epoch);
         if (lane == 0) s_base = base;
     }
     __syncthreads();
-    // Sort key: view << 31 | depth bits (depths are positive floats: bit 31 is free).  The depth sort then also separates
-    // the two views — pairs of different views never meet in a tile list, so the order inside every list is unchanged —
-    // and the tile binning works on one view (half the bins) at a time.  n_vis[1] = number of visible view-0 pairs.
-    const uint32_t Pu = (uint32_t)n2 >> 1;
-    uint32_t slot = s_base + before + incl - cnt;
-#pragma unroll
-    for (int k = 0; k < CP_ITEMS; k++) {
-        if (i0 + k == Pu) n_vis[1] = slot;
-        if (rect[k] != 0u) {
-            depth_key[slot] = key[k] | (i0 + k >= Pu ? 0x80000000u : 0u);
-            pairs[slot] = ((uint64_t)rect[k] << 32) | (uint64_t)(i0 + k);
-            slot++;
-        }
+    if (boundary >= 0) n_vis[1] = s_base + (uint32_t)boundary;
+    for (uint32_t i = threadIdx.x; i < total; i += CP_THREADS) {
+        depth_key[s_base + i] = s_key[i];
+        pairs[s_base + i] = s_pair[i];
     }
     if (tile == gridDim.x - 1) {
         // all pairs counted: publish the total, sentinel keys behind it (0xFFFFFFFF sorts last) so
         // that the fixed-size depth sort over vis_cap slots is well defined whatever the count, then open the next epoch
         const uint32_t nv = s_base + total;
         // (only the keys: the offsets scan treats every entry past *n_vis as empty, see PairArea in binning.cu)
-        for (uint32_t i = nv + threadIdx.x; i < (uint32_t)vis_cap; i += 256) depth_key[i] = 0xFFFFFFFFu;
+        for (uint32_t i = nv + threadIdx.x; i < (uint32_t)vis_cap; i += CP_THREADS) depth_key[i] = 0xFFFFFFFFu;
         if (threadIdx.x == 0) {
             *n_vis = nv;
             if (overflow && nv > (uint32_t)vis_cap) *overflow = 1;
@@ -348,7 +363,12 @@ void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
         default: preprocess_map_kernel<3><<<blocks, 256, 0, s>>>(a); break;
     }
     const int n2 = 2 * a.P;
-    compact_pairs_kernel<<<(n2 + CP_TILE - 1) / CP_TILE, 256, 0, s>>>(n2, a.rect_raw, a.depth_raw, a.comp_state, a.depth_key, a.pairs,
+    static const bool configured = [] {
+        cudaFuncSetAttribute(compact_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_TILE * 12);
+        return true;
+    }();
+    (void)configured;
+    compact_pairs_kernel<<<(n2 + CP_TILE - 1) / CP_TILE, CP_THREADS, CP_TILE * 12, s>>>(n2, a.rect_raw, a.depth_raw, a.comp_state, a.depth_key, a.pairs,
                                                                     a.n_vis, a.vis_cap, a.overflow, a.ctl);
 }
 

@@ -10,7 +10,7 @@
 //   tile_count    chunk c = instances [c*CH, (c+1)*CH) of the sequence, generated from the pairs' tile rects;
 //                 counts per (chunk, tile) in shared memory -> hist[c][tile] (u16); (tile, id) per instance -> memory
 //   tile_scan     per tile: exclusive prefix of the counts over the chunks -> base[c][tile]; totals per tile
-//   tile_starts   exclusive prefix of the totals over the tiles -> ranges[tile] (untouched tiles stay (0,0) as in
+//   (tile_starts) exclusive prefix of the totals over the tiles, by the last tile_scan CTA -> ranges[tile] (untouched tiles stay (0,0) as in
 //                 the reference)
 //   tile_scatter  chunk c again (coalesced read of its instances): every instance gets slot ranges[tile].x +
 //                 base[c][tile] + (its rank among the chunk's earlier instances of the same tile) and stores its
@@ -199,6 +199,48 @@ __global__ void __launch_bounds__(TB_THREADS) tile_count_kernel(int P, int n_pai
     }
 }
 
+// ---- 3. prefix over the tiles: the tile ranges ----------------------------------------------------
+// Run by the 1024 threads of the LAST tile_scan CTA to finish (ticket below): no launch of its own.
+__device__ void tile_starts(int nt, int tiles_local, int tiles_global, int tile_origin, const uint32_t* tile_total,
+                            uint2* __restrict__ ranges) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < nt; t0 += 1024) {
+        const int t = t0 + threadIdx.x;
+        const uint32_t v = t < nt ? __ldcg(tile_total + t) : 0u;   // written by other CTAs of this launch: L2, not L1
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], xs = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+                if (lane >= o) xs += y;
+            }
+            s_warp[lane] = xs - w;   // exclusive
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t start = carry + s_warp[warp] + x - v;
+        if (t < nt) {
+            const int view = t >= tiles_local ? 1 : 0;   // bins are strip-local; the ranges are indexed by the global tile id
+            ranges[view * tiles_global + tile_origin + (t - view * tiles_local)] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = start + v;
+        __syncthreads();
+    }
+}
+
 // ---- 2. prefix over the chunks, per tile ----------------------------------------------------------
 // CTA = 16 tile columns (one 32-byte sector per hist row) x 64 row groups: thread (col, g) loads its rows into shared
 // memory (all loads independent, in flight together) and sums them, the groups are scanned through shared memory, then
@@ -208,10 +250,12 @@ __global__ void __launch_bounds__(TS_COLS * TS_GROUPS) tile_scan_kernel(int nt, 
                                                                          const uint32_t* __restrict__ n_vis, int cap,
                                                                          const uint16_t* __restrict__ hist,
                                                                          uint32_t* __restrict__ base,
-                                                                         uint32_t* __restrict__ tile_total, int rows_cached,
+                                                                         uint32_t* tile_total, uint32_t* ticket, int rows_cached,
+                                                                         int tiles_global, int tile_origin, uint2* __restrict__ ranges,
                                                                          const EngineCtl* __restrict__ ctl) {
     if (ctl && ctl->level_done) return;
     extern __shared__ uint16_t s_rows[];                 // [rows_cached][TS_COLS]
+    __shared__ bool s_last;
     __shared__ uint32_t s_part[TS_GROUPS][TS_COLS + 1];
     const int view = blockIdx.y;                         // nt = tiles per view; this view's chunks are rows [row_lo, row_lo + nact)
     const ChunkRange cr = chunk_range(off, n_vis, n_pairs, cap, 0u);
@@ -251,49 +295,15 @@ __global__ void __launch_bounds__(TS_COLS * TS_GROUPS) tile_scan_kernel(int nt, 
             run += r < rows_cached ? s_rows[r * TS_COLS + col] : __ldg(hist + i);
         }
     }
-}
-
-// ---- 3. prefix over the tiles: the tile ranges ----------------------------------------------------
-__global__ void __launch_bounds__(1024) tile_starts_kernel(int nt, int tiles_local, int tiles_global, int tile_origin,
-                                                            const uint32_t* __restrict__ tile_total, uint2* __restrict__ ranges,
-                                                            const EngineCtl* __restrict__ ctl) {
-    if (ctl && ctl->level_done) return;
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    // the last CTA to get here turns the per-tile totals into the tile ranges
+    __threadfence();
     __syncthreads();
-    for (int t0 = 0; t0 < nt; t0 += 1024) {
-        const int t = t0 + threadIdx.x;
-        const uint32_t v = t < nt ? tile_total[t] : 0u;
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = s_warp[lane], xs = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
-                if (lane >= o) xs += y;
-            }
-            s_warp[lane] = xs - w;   // exclusive
-        }
-        __syncthreads();
-        const uint32_t carry = s_carry;
-        const uint32_t start = carry + s_warp[warp] + x - v;
-        if (t < nt) {
-            const int view = t >= tiles_local ? 1 : 0;   // bins are strip-local; the ranges are indexed by the global tile id
-            ranges[view * tiles_global + tile_origin + (t - view * tiles_local)] = v ? make_uint2(start, start + v) : make_uint2(0u, 0u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = start + v;
-        __syncthreads();
-    }
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0u;
+    tile_starts(2 * nt, nt, tiles_global, tile_origin, tile_total, ranges);
 }
 
 // ---- 4. stable scatter ---------------------------------------------------------------------------
@@ -458,8 +468,8 @@ void launch_tile_scan(const TileBinArgs& a, cudaStream_t s) {
     const int chunks = (a.cap + TB_CH - 1) / TB_CH + 1;
     const int rows_cached = chunks < 4096 ? chunks : 4096;   // 32 B per cached row: <= 128 KB
     tile_scan_kernel<<<dim3((nt + TS_COLS - 1) / TS_COLS, 2), TS_COLS * TS_GROUPS, (size_t)rows_cached * TS_COLS * 2, s>>>(
-        nt, a.n_pairs, a.offsets, a.n_vis, a.cap, a.hist, a.base, a.tile_total, rows_cached, a.ctl);
-    tile_starts_kernel<<<1, 1024, 0, s>>>(2 * nt, a.tiles_per_view, a.tiles_global, a.row0 * a.grid_x, a.tile_total, a.ranges, a.ctl);
+        nt, a.n_pairs, a.offsets, a.n_vis, a.cap, a.hist, a.base, a.tile_total, a.ticket, rows_cached, a.tiles_global, a.row0 * a.grid_x, a.ranges,
+        a.ctl);
 }
 void launch_tile_scatter(const TileBinArgs& a, cudaStream_t s) {
     const int chunks = (a.cap + TB_CH - 1) / TB_CH + 1;
