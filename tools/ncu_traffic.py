@@ -15,7 +15,7 @@ import json
 import os
 
 STAGE_OF = [  # (substring of the kernel name, stage); CUB kernels are attributed by position, see below
-    ("preprocess_map_kernel", "preprocess_map"), ("compact_finish_kernel", "preprocess_map"),
+    ("preprocess_map_kernel", "preprocess_map"), ("compact_pairs_kernel", "preprocess_map"),
     ("tile_count_kernel", "tile_count"), ("tile_scan_kernel", "tile_scan"), ("tile_starts_kernel", "tile_scan"),
     ("tile_scatter_kernel", "tile_scatter"),
     ("blend_fwd_kernel", "blend_fwd_gray"), ("loss_stats_kernel", "loss_stats"), ("blend_bwd_kernel", "blend_bwd_gray"),
@@ -37,7 +37,15 @@ def main():
     per = collections.defaultdict(lambda: [0.0, 0.0, 0])   # bytes, us, iterations seen
     seen_in_iter = collections.defaultdict(int)
     after = None   # last non-CUB stage seen: CUB kernels after preprocess belong to the depth sort / scan, after emit to the tile sort
-    for row in rows[2:]:
+    # only complete iterations: from a projection kernel to the next update kernel
+    body = rows[2:]
+    starts = [i for i, row in enumerate(body) if "preprocess_map_kernel" in row[k]]
+    keep = []
+    for si in starts:
+        end = next((j for j in range(si, len(body)) if "engine_update_kernel" in body[j][k]), None)
+        if end is not None:
+            keep.extend(body[si:end + 1])
+    for row in keep:
         name = row[k]
         stage = next((s for sub, s in STAGE_OF if sub in name), None)
         if stage is None and "cub::" in name:
