@@ -295,9 +295,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": round(status_bytes * frames_run / args.steps, 1),
                     "frames": frames_run, "note": "per frame: events pinned-host->device, GPU event frame, iterations, loss+pose read-back"},
             "gpu_launches": eng.launches_per_iteration * args.steps,
-            "gpu_launches_note": "our own kernels per iteration (preprocess_map, compact_finish, tile_count, tile_scan, tile_starts, "
-                                 "tile_scatter, blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, engine_update) x steps; plus CUB "
-                                 "library kernels (one radix sort over the visible pairs, one scan), all inside one CUDA graph launch",
+            "gpu_launches_note": "our own kernels per iteration (preprocess_map, compact_pairs, tile_count, tile_scan, tile_scatter, "
+                                 "blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, engine_update) x steps; plus CUB library "
+                                 "kernels (one radix sort over the visible pairs, one scan), all inside one CUDA graph launch",
             "roofline": roof,
             "stages_ms": stage_table,
             "workload_counters": wl,

@@ -3,24 +3,26 @@
 // What it replaces.  The reference writes one (tile << 32 | depth, id) record per tile instance and radix-sorts
 // all of them (rasterizer_impl.cu:70-111, 303-311), then finds the tile boundaries in the sorted keys (:116-138).
 // The order inside a tile is (depth bits, Gaussian index).  The engine already holds the pairs in exactly that
-// order (stable depth sort of the index-ordered compact list, binning.cu), so the per-tile lists are a STABLE
-// PARTITION of the instance sequence by tile id — a one-pass counting sort over <= 65535 bins — and the instance
-// records never have to exist in memory:
+// order (stable depth sort of the index-ordered compact list; view 0 in front of view 1 because the sort key carries
+// the view in bit 31), so the per-tile lists are a STABLE PARTITION of the instance sequence by tile id — a one-pass
+// counting sort over the tiles of one view — instead of a sort of 12-byte records:
 //
-//   tile_count    chunk c = instances [c*CH, (c+1)*CH) of the sequence, generated from the pairs' tile rects;
-//                 counts per (chunk, tile) in shared memory -> hist[c][tile] (u16); (tile, id) per instance -> memory
-//   tile_scan     per tile: exclusive prefix of the counts over the chunks -> base[c][tile]; totals per tile
-//   (tile_starts) exclusive prefix of the totals over the tiles, by the last tile_scan CTA -> ranges[tile] (untouched tiles stay (0,0) as in
-//                 the reference)
-//   tile_scatter  chunk c again (coalesced read of its instances): every instance gets slot ranges[tile].x +
-//                 base[c][tile] + (its rank among the chunk's earlier instances of the same tile) and stores its
-//                 Gaussian index there.
+//   tile_count    chunk = 4096 consecutive instances of ONE view, generated from the pairs' tile rects; counts per
+//                 (chunk, tile) in shared memory -> hist[chunk][tile] (u16); (u16 tile, u32 id) per instance staged
+//                 in shared memory and written out coalesced
+//   tile_scan     per tile: exclusive prefix of the counts over the view's chunks -> base[chunk][tile]; totals per
+//                 tile; the LAST CTA to finish prefixes the totals over the tiles -> ranges[tile] (untouched tiles
+//                 stay (0,0) as in the reference)
+//   tile_scatter  chunk again (coalesced read of its instances): every instance gets slot ranges[tile].x +
+//                 base[chunk][tile] + (its rank among the chunk's earlier instances of the same tile) and stores
+//                 its Gaussian index there.
 //
 // Stability inside a chunk: the chunk is cut into 8 slices in sequence order, one per warp; a first pass counts per
 // (slice, tile), the prefix over the slices gives every warp its own cursor per tile, and each warp then walks its
-// slice in order, 32 instances per step, ranking equal tiles inside a step with match.any (lower lane = earlier
-// instance).  Traffic: the pairs once (12 B each), hist/base once each way, per instance 6 B out + 6 B in + 4 B out,
-// all but the last coalesced — against (6 B + 2 x 12 B + 2 B) per instance for emit + two radix passes + range scan.
+// slice in order, 32 instances per step (shared-memory atomics of one warp execute in program order); equal tiles
+// inside a step are ranked by lane with match.any, which a stamp test skips when the 32 tiles are all different.
+// Traffic: the pairs once (12 B each), hist/base once each way, per instance 6 B out + 6 B in + 4 B out — against
+// (6 B + 2 x 12 B + 2 B) per instance for emit + two radix passes + range scan (the fallback above 4096 tiles per view).
 #include <cstdlib>
 #include "internal.h"
 
