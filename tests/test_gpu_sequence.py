@@ -110,6 +110,8 @@ def sequence_report(dev, work, P=40000, W=320, H=240, n_frames=8, n_events=12000
            "ate_ours": ate.ate(ours, gt), "ate_reference": ate.ate(ref, gt),
            "unaligned_ours_vs_gt": {k: v for k, v in ate.compare(ours, gt).items() if "per_frame" not in k},
            "unaligned_reference_vs_gt": {k: v for k, v in ate.compare(ref, gt).items() if "per_frame" not in k},
+           "ours_vs_gt_trans_m": [round(x, 5) for x in ate.compare(ours, gt)["trans_per_frame_m"]],
+           "reference_vs_gt_trans_m": [round(x, 5) for x in ate.compare(ref, gt)["trans_per_frame_m"]],
            "iterations_ours": it_o.tolist(), "iterations_reference": it_r.tolist(),
            "optimisation_seconds": {"ours": round(s_o, 3), "reference": round(s_r, 3)}}
     return rep
@@ -117,39 +119,36 @@ def sequence_report(dev, work, P=40000, W=320, H=240, n_frames=8, n_events=12000
 
 @pytest.mark.gpu
 def test_sequence_tracking_matches_reference_tracker(built, cuda_dev, tmp_path):
-    """Whole pipeline, both implementations, same files in.  What is gated and what is only reported:
+    """Whole pipeline, both implementations, same files in (map.ply, events.txt, config.yaml -> Tracker.tracking()):
+    BASELINE.json configs[1] in small — 300 k Gaussians, 640x480, 30 000 events per frame, the desk yaml's own
+    velocities, 4 event frames, three pyramid levels and both stages per frame with the reference's stopping rule.
 
-    * frame 0 (three pyramid levels, both stages, ~200 Adam steps from the yaml start): the two trackers must end in
-      the same basin (5 cm / 0.5 deg); the distance is printed against north_star's 1 mm / 0.05 deg, which the
-      reference does not hold against ITSELF here because its stop iterations jitter (see the comment at the assert);
-    * later frames: the reference's velocity hand-over (cal_weighted_velocity over a first frame that only moved half
-      a frame span, camera.py:157-201) leaves BOTH trackers outside the narrow basin of this noise-textured synthetic
-      map, every level then runs into the iteration cap and the pose performs an Adam random walk — in the reference
-      itself (its metres of error against ground truth are printed next to ours).  Two chaotic walks cannot be
-      compared pose by pose, so for those frames the test checks the machinery (every frame tracked, iteration counts
-      inside the reference's caps, finite well-formed TUM output) and prints ATE of both against ground truth."""
+    Gate: north_star's 1 mm / 0.05 deg between the two trackers' poses on frames 0-2 (measured over repeated runs:
+    0.19-0.34 mm, 0.003-0.008 deg — profiles/r1_sequence_22f_300k_v30.json and the v31 repeats); every frame in the
+    same basin (5 cm / 0.5 deg).  Frame 3 is where a level first runs into the 200-iteration cap in BOTH trackers; from
+    there the stop iteration jitters with the atomics order (0.9 mm in one run, 3.9 mm in the next), and a few frames
+    later both lose the noise-textured synthetic map for good — the reference at frame 6-8, ours at frame 14 in the
+    22-frame run — so later frames are reported, not gated.  (On the smaller, faster-rotating 40 k / 320x240 scene this
+    test used before, the unmodified reference does not even reproduce its own frame-0 stop iterations:
+    profiles/r1_seq_ab_v11.log.)"""
     from oracle import ref_runner
     if not ref_runner.available():
         pytest.skip("oracle/_ref did not travel with this snapshot")
-    rep = sequence_report(cuda_dev, str(tmp_path))
+    rep = sequence_report(cuda_dev, str(tmp_path), P=300000, W=640, H=480, n_frames=4, n_events=30000, ang_scale=1.0, lin_scale=1.0)
     print(json.dumps(rep))
     c = rep["ours_vs_reference"]
-    assert c["pairs"] == rep["frames"]
-    # Frame 0: both trackers stop each level on check_convergence (tracker.py:65-76), a threshold on the mean |loss
-    # step| of the last 10 iterations — on the plateau a rounding-level difference moves the stop by tens of iterations.
-    # The UNMODIFIED reference run repeatedly on the SAME files stopped frame 0 at [66, 73, 66], [66, 96, 147],
-    # [66, 112, 200] and [65, 97, 107] iterations per level (profiles/r1_seq_ab_v11.log; its backward uses float
-    # atomics), i.e. its own frame-0 pose moves by centimetres between runs.  So the 1 mm / 0.05 deg gate lives where it
-    # can hold — fixed iteration counts, test_engine_iterations_match_reference_pipeline — and here frame 0 is gated on
-    # "same basin" and reported against north_star's numbers.
-    print("frame 0: ours vs reference %.2e m, %.4f deg (north_star 1e-3 m / 0.05 deg holds where the stop iterations agree)"
-          % (rep["per_frame_trans_m"][0], rep["per_frame_rot_deg"][0]))
-    assert rep["per_frame_trans_m"][0] < 0.05 and rep["per_frame_rot_deg"][0] < 0.5, (rep["per_frame_trans_m"], rep["per_frame_rot_deg"])
+    assert c["pairs"] == rep["frames"] == 4
+    dt, dr = rep["per_frame_trans_m"], rep["per_frame_rot_deg"]
+    print("ours vs reference per frame: %s m, %s deg; optimisation %s s" % (dt, dr, rep["optimisation_seconds"]))
+    assert max(dt[:3]) < 1e-3 and max(dr[:3]) < 0.05, (dt, dr)
+    assert max(dt) < 0.05 and max(dr) < 0.5, (dt, dr)
+    # both trackers actually track these frames (a few centimetres from the synthetic ground truth at most)
+    assert max(rep["ours_vs_gt_trans_m"]) < 0.05 and max(rep["reference_vs_gt_trans_m"]) < 0.05
     it_o, it_r = np.array(rep["iterations_ours"]), np.array(rep["iterations_reference"])
     assert it_o.shape == it_r.shape == (rep["frames"], 3)
     cap = 2 * 200 + 1                                  # coarse + fine stage caps of tracker.py:224-240
     assert it_o.min() >= 1 and it_o.max() <= cap and it_r.max() <= cap
-    # frame 0: the coarsest level (descending from the same start, far from the plateau) stops at the same iteration
+    # frame 0: the coarsest level (descending from the same start, far from the plateau) stops at about the same iteration
     assert abs(int(it_o[0][0]) - int(it_r[0][0])) <= 15, (it_o[0], it_r[0])
     for k in ("ate_ours", "ate_reference"):
         assert all(np.isfinite(v) for v in rep[k].values() if isinstance(v, float)), rep[k]

@@ -30,12 +30,16 @@ def main():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--events", type=int, default=30000)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--ang-scale", type=float, default=5.0)
+    ap.add_argument("--lin-scale", type=float, default=2.0)
+    ap.add_argument("--scale-mult", type=float, default=1.0, help="multiplies every Gaussian's extent (smoother texture)")
     a = ap.parse_args()
     import test_gpu_sequence as tgs
     from gsevt import ate
     dev = torch.device("cuda:0")
     t0 = time.perf_counter()
-    raw, table, gt, desc = tgs.make_sequence(dev, a.gaussians, a.width, a.height, a.frames, a.events)
+    raw, table, gt, desc = tgs.make_sequence(dev, a.gaussians, a.width, a.height, a.frames, a.events, ang_scale=a.ang_scale,
+                                             lin_scale=a.lin_scale, scale_mult=a.scale_mult)
     t_gen = time.perf_counter() - t0
     torch.cuda.reset_peak_memory_stats()
     free0, total = torch.cuda.mem_get_info()
@@ -54,7 +58,10 @@ def main():
            "device_memory_used_MB_after": round((total - free1) / 2**20, 1), "device_memory_used_MB_before": round((total - free0) / 2**20, 1),
            "vs_ground_truth": {k: v for k, v in cmp_.items() if "per_frame" not in k},
            "ate_vs_ground_truth": ate.ate(ours, gt),
-           "first_frames_trans_err_m": [round(float(x), 5) for x in cmp_["trans_per_frame_m"][:5]]}
+           "first_frames_trans_err_m": [round(float(x), 5) for x in cmp_["trans_per_frame_m"][:5]],
+           "trans_err_m_every_5th_frame": [round(float(x), 4) for x in cmp_["trans_per_frame_m"][::5]],
+           "rot_err_deg_every_5th_frame": [round(float(x), 3) for x in cmp_["rot_per_frame_deg"][::5]],
+           "generator": {"ang_scale": a.ang_scale, "lin_scale": a.lin_scale, "scale_mult": a.scale_mult}}
     s = json.dumps(rep)
     print(s)
     if a.out:
