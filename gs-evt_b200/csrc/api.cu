@@ -406,7 +406,7 @@ struct GsevtEngine {
     uint32_t* active_list = nullptr;   // [2P] compacted pairs with a gradient
     uint32_t* active_count = nullptr;
     void* scan_temp = nullptr; size_t scan_bytes = 0;
-    unsigned long long* comp_state = nullptr;            // projection kernel: chained-scan state + tile counter
+    uint32_t* comp_state = nullptr;                      // compaction: per-CTA visible counts (zero between launches) + their prefix
     uint32_t* n_vis = nullptr;                           // device: visible (view, Gaussian) pairs of the last projection
     int vis_cap = 0;                                     // slots the depth sort covers: upper bound on n_vis the current level's graph was sized for
     uint32_t *depth_key = nullptr, *depth_sorted = nullptr;
@@ -575,7 +575,7 @@ static PreMapArgs premap_args(GsevtEngine* e, int vis_cap) {
     pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
     pa.rect_raw = e->rect_raw; pa.depth_raw = e->depth_raw; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.pairs = e->pairs;
     pa.rec = e->rec; pa.grad8 = e->grad8;
-    pa.comp_state = e->comp_state;
+    pa.cta_count = e->comp_state;
     pa.n_vis = e->n_vis; pa.vis_cap = vis_cap; pa.overflow = e->overflow;
     return pa;
 }
@@ -822,7 +822,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     cudaMemcpy(e->bg3, bg, sizeof(bg), cudaMemcpyHostToDevice);
     cudaMemset(e->overflow, 0, 4);
     cudaMemset(e->tb_total, 0, (2 * (size_t)L0.gx * L0.gy + 4) * 4);
-    cudaMemset(e->comp_state, 0, preprocess_map_state_bytes(P));   // epoch 0: nothing published (compact_pairs_kernel)
+    cudaMemset(e->comp_state, 0, preprocess_map_state_bytes(P));   // the counters start from zero; compact_scan_kernel clears what it reads
     cudaMemset(e->loss_partials, 0, ((size_t)e->loss_nb * 3 + 2) * 8);
     cudaMemset(e->grad8, 0, 2 * p2 * 16);
     cudaMemset(e->rect_raw, 0, preprocess_map_raw_items(P) * 4);

@@ -110,7 +110,8 @@ struct PreMapArgs {
     // visible pairs only, compacted in index order per view (compact_pairs_kernel): entries [0, *n_vis)
     uint32_t* depth_key;      // float bits of the view depth
     uint64_t* pairs;          // {tile rect} << 32 | pair id (= view * P + Gaussian)
-    unsigned long long* comp_state;   // chained-scan state, preprocess_map_state_bytes(P)
+    uint32_t* cta_count;      // [2][P / 256] visible pairs per projection CTA and view (zero between launches), followed by
+                              // their exclusive prefix [2][P / 256]: preprocess_map_state_bytes(P) in all
     uint32_t* n_vis;          // out: [0] number of visible pairs, [1] number of visible pairs of view 0
     int vis_cap;              // slots the depth sort covers: [*n_vis, vis_cap) are filled with sentinels
     int* overflow;            // set when *n_vis > vis_cap (may be NULL)

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(256, 3) preprocess_map_kernel(PreMapArgs a) {
     __shared__ ViewParams s_vp[2];
     load_views(s_vp, a.views, 2);
     const int idx = blockIdx.x * 256 + threadIdx.x;
+    const unsigned live_mask = __ballot_sync(0xffffffffu, idx < a.P);   // a prefix of the warp's lanes
     if (idx >= a.P) return;
     const float4 xo = __ldg(a.xyz_opacity + idx);
     float cov[6];
@@ -164,6 +165,15 @@ __global__ void __launch_bounds__(256, 3) preprocess_map_kernel(PreMapArgs a) {
             const uint32_t y0 = max(r >> 8 & 255u, sy0), y1 = min(r >> 24, sy1);
             ok[v] = ok[v] && y1 > y0;
             o[v].rect = (r & 0x00FF00FFu) | (y0 << 8) | (y1 << 24);
+        }
+    }
+    // visible pairs of this CTA per view, for the compaction pass (one fire-and-forget add per warp and view; the
+    // counters are zero on entry: compact_scan_kernel clears what it reads)
+    {
+        const unsigned b0 = __ballot_sync(live_mask, ok[0]), b1 = __ballot_sync(live_mask, ok[1]);
+        if ((threadIdx.x & 31) == 0) {
+            if (b0) atomicAdd(a.cta_count + blockIdx.x, (uint32_t)__popc(b0));
+            if (b1) atomicAdd(a.cta_count + gridDim.x + blockIdx.x, (uint32_t)__popc(b1));
         }
     }
     // per pair, in index order: the tile rect (0 = not visible here) and the depth bits; compact_pairs_kernel squeezes
@@ -215,143 +225,113 @@ __global__ void __launch_bounds__(256, 3) preprocess_map_kernel(PreMapArgs a) {
     }
 }
 
-// Compaction of the visible (view, Gaussian) pairs, in index order — a stream pass of its own between the projection
-// and the depth sort (done inside the projection kernel, the chained scan's barriers and look-back cost the heavy
-// kernel 30 us; here they hide behind 64 resident warps and the pass moves 32 B per pair).  Within a view the compact
-// order is the index order, which is all the stable depth sort needs to reproduce the reference's (depth, index)
-// tie-break; pairs of different views never meet in a tile list.  The depth sort / scan / tile binning then run over
-// the visible pairs instead of all 2P (and, under the screen-tile split, over this rank's strip only).
-//
-// Chained scan with decoupled look-back over the CTAs' visible counts.  One 64-bit state word per CTA:
-// epoch << 34 | flag << 32 | value, flag 1 = this CTA's count, 2 = inclusive prefix.  The epoch (a device counter the
-// last CTA bumps when it is done) makes words of earlier launches read as "not published": no reset pass.  CTAs are
-// dispatched in blockIdx order, so a CTA only ever waits for CTAs that already run.
-// 512 threads x 16 pairs: few, large tiles keep the look-back short (a resident wave of N CTAs that publish at the same
-// time looks back over up to N / 32 windows of one L2 round trip each: 2048-pair tiles measured 28 us for this pass)
-constexpr int CP_ITEMS = 16;
-constexpr int CP_THREADS = 512;
-constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
-__device__ __forceinline__ uint32_t compact_base(unsigned long long* state, uint32_t tile, uint32_t count, uint32_t epoch) {
-    // called by all 32 lanes of warp 0; returns (to every lane) the number of visible pairs in all lower tiles
-    const int lane = threadIdx.x & 31;
-    const unsigned long long tag = (unsigned long long)epoch << 34;
-    uint32_t base = 0;
-    if (tile > 0) {
-        if (lane == 0) atomicExch(state + tile, tag | (1ull << 32) | count);
-        int t = (int)tile - 1 - lane;   // this lane's predecessor in the current window of 32
-        while (true) {
-            unsigned long long w = tag | (2ull << 32);   // lanes before tile 0: an (empty) inclusive prefix
-            if (t >= 0) {
-                do {
-                    w = *reinterpret_cast<volatile unsigned long long*>(state + t);
-                } while ((w >> 34) != (unsigned long long)epoch);
-            }
-            const unsigned incl = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == 2ull);
-            const int stop = incl ? __ffs(incl) - 1 : 31;   // nearest predecessor that already holds a prefix
-            uint32_t v = lane <= stop ? (uint32_t)w : 0u;
+// Compaction of the visible (view, Gaussian) pairs, in index order — two small passes between the projection and the
+// depth sort.  Within a view the compact order is the index order, which is all the stable depth sort needs to reproduce
+// the reference's (depth, index) tie-break; pairs of different views never meet in a tile list.  The depth sort / scan /
+// tile binning then run over the visible pairs instead of all 2P (and, under the screen-tile split, over this rank's
+// strip only).
+//   projection    adds every warp's visible count to its CTA's counter (per view)
+//   compact_scan  one CTA: exclusive prefix over the 2 x (P / 256) counters (view 0 first), clears them, publishes the
+//                 totals (all / view 0) and checks them against the slots the depth sort covers
+//   compact_pairs CTA = the same 256 Gaussians of one view: ballot + 8 warp counts + the CTA's base -> unit-stride
+//                 writes of (key, {rect | id}); a few extra CTAs write the sentinel keys behind the visible pairs
+// No chained scan, no spinning: what was tried before — the scan inside the projection kernel (barriers and look-back
+// cost the heavy kernel 30 us) and a chained-scan pass of its own (25 us, of which the look-back of a resident wave of
+// CTAs was most) — is in the history of this file.
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int nblk, uint32_t* __restrict__ cta_count, uint32_t* __restrict__ cta_base,
+                                                            uint32_t* __restrict__ n_vis, int vis_cap, int* __restrict__ overflow,
+                                                            const EngineCtl* __restrict__ ctl) {
+    if (ctl && ctl->level_done) return;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = 2 * nblk;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < n; t0 += 4096) {
+        const int i = t0 + threadIdx.x * 4;
+        uint32_t v[4];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            base += v;
-            if (incl) break;
-            t -= 32;
+        for (int k = 0; k < 4; k++) {
+            v[k] = i + k < n ? cta_count[i + k] : 0u;
+            if (i + k < n) cta_count[i + k] = 0u;
         }
+        const uint32_t sum = v[0] + v[1] + v[2] + v[3];
+        uint32_t x = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_warp[lane];
+            uint32_t xs = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+                if (lane >= o) xs += y;
+            }
+            s_warp[lane] = xs - w;   // exclusive
+        }
+        __syncthreads();
+        uint32_t run = s_carry + s_warp[warp] + x - sum;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i + k < n) cta_base[i + k] = run;
+            if (i + k == nblk) n_vis[1] = run;   // everything in front of view 1 = the visible pairs of view 0
+            run += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = run;
+        __syncthreads();
     }
-    if (lane == 0) {
-        __threadfence();
-        atomicExch(state + tile, tag | (2ull << 32) | (unsigned long long)(base + count));
+    if (threadIdx.x == 0) {
+        const uint32_t total = s_carry;
+        n_vis[0] = total;
+        if (overflow && total > (uint32_t)vis_cap) *overflow = 1;
     }
-    return base;
 }
 
-__global__ void __launch_bounds__(CP_THREADS, 2) compact_pairs_kernel(int n2, const uint32_t* __restrict__ rect_raw,
+constexpr int CP_FILL_CTAS = 16;
+__global__ void __launch_bounds__(256) compact_pairs_kernel(int P, int nblk, const uint32_t* __restrict__ rect_raw,
                                                             const uint32_t* __restrict__ depth_raw,
-                                                            unsigned long long* __restrict__ state, uint32_t* __restrict__ depth_key,
-                                                            uint64_t* __restrict__ pairs, uint32_t* n_vis, int vis_cap,
-                                                            int* __restrict__ overflow, const EngineCtl* __restrict__ ctl) {
+                                                            const uint32_t* __restrict__ cta_base, const uint32_t* __restrict__ n_vis,
+                                                            uint32_t* __restrict__ depth_key, uint64_t* __restrict__ pairs, int vis_cap,
+                                                            const EngineCtl* __restrict__ ctl) {
     if (ctl && ctl->level_done) return;
-    __shared__ uint32_t s_warp[CP_THREADS / 32];
-    __shared__ uint32_t s_base;
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    uint64_t* s_pair = reinterpret_cast<uint64_t*>(s_dyn);                   // [CP_TILE]
-    uint32_t* s_key = reinterpret_cast<uint32_t*>(s_dyn + CP_TILE * 8);      // [CP_TILE]
-    uint32_t* epoch_ctr = reinterpret_cast<uint32_t*>(state + gridDim.x);
-    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(epoch_ctr) + 1u;
-    const uint32_t tile = blockIdx.x;
-    const uint32_t i0 = tile * (uint32_t)CP_TILE + threadIdx.x * (uint32_t)CP_ITEMS;   // the arrays are padded to whole tiles
-    uint32_t rect[CP_ITEMS], key[CP_ITEMS];
-#pragma unroll
-    for (int q = 0; q < CP_ITEMS / 4; q++) {
-        const uint4 r = __ldg(reinterpret_cast<const uint4*>(rect_raw + i0) + q);
-        const uint4 d = __ldg(reinterpret_cast<const uint4*>(depth_raw + i0) + q);
-        rect[4 * q] = r.x; rect[4 * q + 1] = r.y; rect[4 * q + 2] = r.z; rect[4 * q + 3] = r.w;
-        key[4 * q] = d.x; key[4 * q + 1] = d.y; key[4 * q + 2] = d.z; key[4 * q + 3] = d.w;
+    if ((int)blockIdx.x >= nblk) {
+        // sentinel keys behind the visible pairs (0xFFFFFFFF sorts last; the offsets scan treats entries past *n_vis as
+        // empty, see PairArea in binning.cu): the fixed-size depth sort over vis_cap slots is defined whatever the count
+        if (blockIdx.y) return;
+        for (uint32_t i = n_vis[0] + (blockIdx.x - nblk) * 256u + threadIdx.x; i < (uint32_t)vis_cap; i += CP_FILL_CTAS * 256u)
+            depth_key[i] = 0xFFFFFFFFu;
+        return;
     }
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int k = 0; k < CP_ITEMS; k++) {
-        if (i0 + k >= (uint32_t)n2) rect[k] = 0u;
-        cnt += rect[k] != 0u;
-    }
+    __shared__ uint32_t s_warp[8];
+    const int view = blockIdx.y;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const size_t j = (size_t)view * P + idx;
+    const uint32_t rect = idx < P ? __ldg(rect_raw + j) : 0u;
+    const uint32_t key = idx < P ? __ldg(depth_raw + j) : 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-    }
-    if (lane == 31) s_warp[warp] = incl;
+    const unsigned b = __ballot_sync(0xffffffffu, rect != 0u);
+    if (lane == 0) s_warp[warp] = (uint32_t)__popc(b);
     __syncthreads();
-    uint32_t before = 0, total = 0;
+    if (rect == 0u) return;
+    uint32_t slot = __ldg(cta_base + (size_t)view * nblk + blockIdx.x) + (uint32_t)__popc(b & ((1u << lane) - 1u));
 #pragma unroll
-    for (int w = 0; w < CP_THREADS / 32; w++) {
-        const uint32_t c = s_warp[w];
-        if (w < warp) before += c;
-        total += c;
-    }
+    for (int w = 0; w < 8; w++) slot += w < warp ? s_warp[w] : 0u;
     // Sort key: view << 31 | depth bits (depths are positive floats: bit 31 is free).  The depth sort then also separates
     // the two views — pairs of different views never meet in a tile list, so the order inside every list is unchanged —
-    // and the tile binning works on one view (half the bins) at a time.  n_vis[1] = number of visible view-0 pairs.
-    // The CTA's survivors are squeezed together in shared memory first (while warp 0 looks back for the CTA's base) and
-    // leave with unit-stride stores: written straight from the registers every store instruction hits 32 sectors.
-    const uint32_t Pu = (uint32_t)n2 >> 1;
-    uint32_t local = before + incl - cnt;
-    int boundary = -1;   // position (within the CTA's survivors) in front of pair index P, if this thread holds it
-#pragma unroll
-    for (int k = 0; k < CP_ITEMS; k++) {
-        if (i0 + k == Pu) boundary = (int)local;
-        if (rect[k] != 0u) {
-            s_key[local] = key[k] | (i0 + k >= Pu ? 0x80000000u : 0u);
-            s_pair[local] = ((uint64_t)rect[k] << 32) | (uint64_t)(i0 + k);
-            local++;
-        }
-    }
-    if (warp == 0) {
-        const uint32_t base = compact_base(state, tile, total, epoch);
-        if (lane == 0) s_base = base;
-    }
-    __syncthreads();
-    if (boundary >= 0) n_vis[1] = s_base + (uint32_t)boundary;
-    for (uint32_t i = threadIdx.x; i < total; i += CP_THREADS) {
-        depth_key[s_base + i] = s_key[i];
-        pairs[s_base + i] = s_pair[i];
-    }
-    if (tile == gridDim.x - 1) {
-        // all pairs counted: publish the total, sentinel keys behind it (0xFFFFFFFF sorts last) so
-        // that the fixed-size depth sort over vis_cap slots is well defined whatever the count, then open the next epoch
-        const uint32_t nv = s_base + total;
-        // (only the keys: the offsets scan treats every entry past *n_vis as empty, see PairArea in binning.cu)
-        for (uint32_t i = nv + threadIdx.x; i < (uint32_t)vis_cap; i += CP_THREADS) depth_key[i] = 0xFFFFFFFFu;
-        if (threadIdx.x == 0) {
-            *n_vis = nv;
-            if (overflow && nv > (uint32_t)vis_cap) *overflow = 1;
-            __threadfence();
-            *epoch_ctr = epoch;
-        }
-    }
+    // and the tile binning works on one view (half the bins) at a time.
+    depth_key[slot] = key | ((uint32_t)view << 31);
+    pairs[slot] = ((uint64_t)rect << 32) | (uint64_t)j;
 }
 
-size_t preprocess_map_state_bytes(int P) { return ((size_t)(2 * (size_t)P + CP_TILE - 1) / CP_TILE + 2) * sizeof(unsigned long long); }
-size_t preprocess_map_raw_items(int P) { return (2 * (size_t)P + CP_TILE - 1) / CP_TILE * CP_TILE; }
+size_t preprocess_map_state_bytes(int P) { return ((size_t)(P + 255) / 256 * 4 + 16) * sizeof(uint32_t); }   // counts + bases, 2 views
+size_t preprocess_map_raw_items(int P) { return (2 * (size_t)P + 1023) / 1024 * 1024; }
 
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
@@ -362,14 +342,10 @@ void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
         case 2: preprocess_map_kernel<2><<<blocks, 256, 0, s>>>(a); break;
         default: preprocess_map_kernel<3><<<blocks, 256, 0, s>>>(a); break;
     }
-    const int n2 = 2 * a.P;
-    static const bool configured = [] {
-        cudaFuncSetAttribute(compact_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_TILE * 12);
-        return true;
-    }();
-    (void)configured;
-    compact_pairs_kernel<<<(n2 + CP_TILE - 1) / CP_TILE, CP_THREADS, CP_TILE * 12, s>>>(n2, a.rect_raw, a.depth_raw, a.comp_state, a.depth_key, a.pairs,
-                                                                    a.n_vis, a.vis_cap, a.overflow, a.ctl);
+    uint32_t* cta_base = a.cta_count + 2 * (size_t)blocks;
+    compact_scan_kernel<<<1, 1024, 0, s>>>(blocks, a.cta_count, cta_base, a.n_vis, a.vis_cap, a.overflow, a.ctl);
+    compact_pairs_kernel<<<dim3(blocks + CP_FILL_CTAS, 2), 256, 0, s>>>(a.P, blocks, a.rect_raw, a.depth_raw, cta_base, a.n_vis,
+                                                                       a.depth_key, a.pairs, a.vis_cap, a.ctl);
 }
 
 // checkFrustum (rasterizer_impl.cu:54-66)
