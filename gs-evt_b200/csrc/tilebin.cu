@@ -22,7 +22,7 @@
 // slice in order, 32 instances per step (shared-memory atomics of one warp execute in program order); equal tiles
 // inside a step are ranked by lane with match.any, which a stamp test skips when the 32 tiles are all different.
 // Traffic: the pairs once (12 B each), hist/base once each way, per instance 6 B out + 6 B in + 4 B out — against
-// (6 B + 2 x 12 B + 2 B) per instance for emit + two radix passes + range scan (the fallback above 4096 tiles per view).
+// (6 B + 2 x 12 B + 2 B) per instance for emit + two radix passes + range scan (the fallback above 2048 tiles per view).
 #include <cstdlib>
 #include "internal.h"
 

@@ -279,7 +279,7 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
 /* Number of kernels the engine launches per executed iteration (for bench.py's gpu_launches). */
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e);
 /* Which binning path the engine uses from the next begin_level / eval on: 0 = automatic (tile binning by counting up
- * to 4096 tiles per view and strip, emit + radix sort above), 1 = counting, 2 = radix.  Both produce the reference's
+ * to 2048 tiles per view and strip, emit + radix sort above), 1 = counting, 2 = radix.  Both produce the reference's
  * per-tile lists (rasterizer_impl.cu:70-138) bit for bit; the knob exists so that tests can compare them.
  * Returns GSEVT_EINVAL when `mode` 1 is asked for a grid the counting kernels cannot hold. */
 GSEVT_API int gsevt_engine_set_binning(GsevtEngine* e, int32_t mode);
