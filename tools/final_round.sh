@@ -5,7 +5,7 @@
 set -u
 TAG="${1:-final}"; OUT=gpurun_out; mkdir -p $OUT
 bash tools/gpu_round.sh "$TAG" tests smoke bench ref launches
-REGEX='preprocess_map|compact_pairs|tile_count|tile_scan|tile_scatter|blend_fwd|blend_bwd|geom_compact|geom_bwd|loss_stats|engine_update|Onesweep|Histogram|ExclusiveSum|DeviceScan'
+REGEX='preprocess_map|compact_scan|compact_pairs|tile_count|tile_scan|tile_scatter|blend_fwd|blend_bwd|geom_compact|geom_bwd|loss_stats|engine_update|Onesweep|Histogram|ExclusiveSum|DeviceScan'
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$REGEX" -s "${NCU_SKIP:-100}" -c "${NCU_COUNT:-40}" \
     -o "$OUT/${TAG}_full" -f python bench.py --steps 6 --warmup 3 --no-cpu-baseline > "$OUT/${TAG}_full.log" 2>&1
 tail -2 "$OUT/${TAG}_full.log"

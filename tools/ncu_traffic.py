@@ -15,7 +15,7 @@ import json
 import os
 
 STAGE_OF = [  # (substring of the kernel name, stage); CUB kernels are attributed by position, see below
-    ("preprocess_map_kernel", "preprocess_map"), ("compact_pairs_kernel", "preprocess_map"),
+    ("preprocess_map_kernel", "preprocess_map"), ("compact_pairs_kernel", "preprocess_map"), ("compact_scan_kernel", "preprocess_map"),
     ("tile_count_kernel", "tile_count"), ("tile_scan_kernel", "tile_scan"),
     ("tile_scatter_kernel", "tile_scatter"),
     ("blend_fwd_kernel", "blend_fwd_gray"), ("loss_stats_kernel", "loss_stats"), ("blend_bwd_kernel", "blend_bwd_gray"),
