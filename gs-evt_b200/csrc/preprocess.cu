@@ -136,8 +136,8 @@ void launch_preprocess_aos(const PreAosArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Engine path: packed map, two views per thread.
 // ------------------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(256, 3) preprocess_map_kernel(PreMapArgs a) {
+template <int D, int MINB>
+__global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a) {
     if (a.ctl && a.ctl->level_done) return;
     __shared__ ViewParams s_vp[2];
     load_views(s_vp, a.views, 2);
@@ -336,11 +336,18 @@ size_t preprocess_map_raw_items(int P) { return (2 * (size_t)P + 1023) / 1024 * 
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
     const int blocks = (a.P + 255) / 256;
+    // SH degree 3 needs 105 registers without spills (2 CTAs per SM) or 80 with 56 B of spills (3 CTAs per SM): the
+    // former measured 2.3 us faster (0.0985 vs 0.1008 ms for the stage, A/B/A/B on one box); GSEVT_PRE_MINB=3 selects the
+    // latter for experiments.
+    static const int minb = [] { const char* v = getenv("GSEVT_PRE_MINB"); return v && atoi(v) == 3 ? 3 : 2; }();
     switch (a.D) {
-        case 0: preprocess_map_kernel<0><<<blocks, 256, 0, s>>>(a); break;
-        case 1: preprocess_map_kernel<1><<<blocks, 256, 0, s>>>(a); break;
-        case 2: preprocess_map_kernel<2><<<blocks, 256, 0, s>>>(a); break;
-        default: preprocess_map_kernel<3><<<blocks, 256, 0, s>>>(a); break;
+        case 0: preprocess_map_kernel<0, 3><<<blocks, 256, 0, s>>>(a); break;
+        case 1: preprocess_map_kernel<1, 3><<<blocks, 256, 0, s>>>(a); break;
+        case 2: preprocess_map_kernel<2, 3><<<blocks, 256, 0, s>>>(a); break;
+        default:
+            if (minb == 2) preprocess_map_kernel<3, 2><<<blocks, 256, 0, s>>>(a);
+            else preprocess_map_kernel<3, 3><<<blocks, 256, 0, s>>>(a);
+            break;
     }
     uint32_t* cta_base = a.cta_count + 2 * (size_t)blocks;
     compact_scan_kernel<<<1, 1024, 0, s>>>(blocks, a.cta_count, cta_base, a.n_vis, a.vis_cap, a.overflow, a.ctl);
