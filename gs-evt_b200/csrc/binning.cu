@@ -168,17 +168,19 @@ void launch_build_view_params(ViewParams* out, const float* view, const float* p
 }
 
 // ------------------------------------------------------------------------------------------------
-// Engine path: two-level binning.
+// Engine path: depth sort of the visible pairs, then the per-tile lists.
 //
 // The reference's order inside a tile is (depth bits, Gaussian index) — the second by stability of the
 // radix sort over the emission order (rasterizer_impl.cu:85-109,306-311).  The same total order is
 // produced with far less traffic by
-//   1. sorting the 2P (view, Gaussian) pairs ONCE by their 32-bit depth key (stable: ties keep index order;
-//      culled pairs carry key 0xFFFFFFFF and sink to the end),
-//   2. emitting tile instances in that order with a 16-bit key = tile id (+ tiles per view for view 1),
-//   3. a stable sort on the tile id alone (<= 13 bits: two 8-bit passes instead of six over 64-bit keys).
-// Within a tile the stable tile sort preserves emission order = (depth, index) order, so point lists and
-// tile ranges are identical to the reference's; gsevt_engine_binning() rebuilds the 64-bit keys for the tests.
+//   1. sorting the VISIBLE (view, Gaussian) pairs — compacted in index order by preprocess.cu — ONCE by
+//      view << 31 | depth bits (stable: ties keep index order; sentinel keys 0xFFFFFFFF fill the slack),
+//   2. a stable partition of the instance sequence by tile id: tilebin.cu (counting, the default), or — for
+//      grids with more than 2048 tiles per view and strip — the kernels of this file: tile instances emitted in
+//      that order with a 16-bit key = tile id (+ tiles per view for view 1), a stable CUB sort on the tile id alone
+//      (<= 13 bits: two 8-bit passes instead of six over 64-bit keys), and a range scan.
+// Either way point lists and tile ranges are identical to the reference's; gsevt_engine_binning() rebuilds the
+// 64-bit keys for the tests.
 // ------------------------------------------------------------------------------------------------
 size_t sort32_temp_bytes(int n) {
     size_t bytes = 0;

@@ -145,7 +145,7 @@ void launch_sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, u
 void launch_identify_ranges(const uint64_t* keys, uint2* ranges, int ntiles_total, int n_host, const uint32_t* n_dev,
                             int cap, cudaStream_t s);
 uint32_t higher_msb(uint32_t n);
-// engine: two-level binning (depth sort of (view, Gaussian) pairs, then a stable 16-bit tile sort)
+// engine: depth sort of the visible (view, Gaussian) pairs; radix fallback of the tile binning (stable 16-bit tile sort)
 size_t sort32_temp_bytes(int n);
 size_t sort16_temp_bytes(int n);
 size_t scan_gather_temp_bytes(int n);
