@@ -390,7 +390,9 @@ __global__ void __launch_bounds__(TB_THREADS, 4) tile_scatter_kernel(int n_pairs
     // slots), so a step first tests "all tiles distinct" with a stamp: every lane writes its own id to s_stamp[tile]
     // and reads it back — if two lanes share a tile at most one reads its own id back.  A foreign warp's stamp can only
     // produce a false alarm.  Steps with distinct tiles (about two in three at 1200 tiles) take one atomic per lane;
-    // only the others fall back to match.any.  Shared-memory atomics of one warp execute in program order, which is
+    // only the others fall back to match.any.  (compute-sanitizer racecheck reports exactly these two lines — the race
+    // between warps on s_stamp is the mechanism, see above; nothing else in the library is flagged:
+    // profiles/r1_sanitizer_v38.log.)  Shared-memory atomics of one warp execute in program order, which is
     // what keeps the ranks stable across steps.  Software-pipelined in groups of 8 steps.
     const uint32_t lt = (1u << lane) - 1u;
     const uint16_t my_stamp = (uint16_t)threadIdx.x;
