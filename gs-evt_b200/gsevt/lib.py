@@ -103,6 +103,7 @@ PROTOTYPES = {
     "gsevt_engine_eval": (C.c_int, [c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p, c_void_p]),
     "gsevt_engine_launches_per_iteration": (C.c_int, [c_void_p]),
     "gsevt_engine_set_binning": (C.c_int, [c_void_p, C.c_int32]),
+    "gsevt_parse_int_table": (C.c_int64, [c_void_p, C.c_size_t, c_void_p, C.c_size_t, C.c_int32]),
     "gsevt_engine_binning": (C.c_int, [c_void_p, C.c_int32, c_void_p, c_void_p, c_void_p, C.c_int32, c_void_p]),
     "gsevt_engine_stage_count": (C.c_int, []),
     "gsevt_engine_stage_name": (C.c_char_p, [C.c_int32]),

@@ -155,6 +155,12 @@ GSEVT_API int64_t gsevt_raster_img_offset(const char* name, int32_t width, int32
  *    Tracker.image_pyramid (utils/tracker.py:78-91), which run on the host with numpy + OpenCV.
  * ---------------------------------------------------------------------------------------------- */
 
+/* Text ingestion.  Replaces the parsing half of load_events_from_txt (utils/event_camera/event.py:11-39:
+ * readlines() + split() + int() + one Python object per event, 0.31 M events/s): converts the whitespace-separated
+ * decimal integers of `text[0, len)` into out[0, n), in order, with `threads` host threads (<= 0: all cores).
+ * out == NULL: returns n without converting (size query).  Returns n, GSEVT_EINVAL on a token that is not an integer
+ * (the reference raises ValueError), GSEVT_ENOMEM when n > capacity.  Host pointers; no device involved. */
+GSEVT_API int64_t gsevt_parse_int_table(const char* text, size_t len, int64_t* out, size_t capacity, int32_t threads);
 /* E0: counts[y*W+x] += p ? +1 : -1  (integer scatter-add, bit-exact).  x,y int16, p uint8, device
  * pointers; counts int32[H*W] must be zeroed by the caller (or pass zero_first != 0).  Events with
  * coordinates outside the frame are an error in the reference (IndexError); here they set the
