@@ -295,9 +295,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": round(status_bytes * frames_run / args.steps, 1),
                     "frames": frames_run, "note": "per frame: events pinned-host->device, GPU event frame, iterations, loss+pose read-back"},
             "gpu_launches": eng.launches_per_iteration * args.steps,
-            "gpu_launches_note": "our own kernels per iteration (preprocess_map, compact_pairs, tile_count, tile_scan, tile_scatter, "
-                                 "blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, engine_update) x steps; plus CUB library "
-                                 "kernels (one radix sort over the visible pairs, one scan), all inside one CUDA graph launch",
+            "gpu_launches_note": "kernels per iteration (preprocess_map, bucket_scatter, bucket_sort, blend_fwd, loss_stats, blend_bwd, "
+                                 "geom_compact, geom_bwd, engine_update) x steps: all this library's own, no library kernels, one CUDA "
+                                 "graph launch per iteration",
             "roofline": roof,
             "stages_ms": stage_table,
             "workload_counters": wl,
@@ -416,21 +416,14 @@ def roofline(stages, wl, P, HW, clocks, default_workload=True, tiles=1200):
     traffic, traffic_src = load_traffic() if default_workload else ({}, None)
     Pv, N, S = sum(wl["visible"]), sum(wl["instances"]), sum(wl["pairs_walked"])
     Pg = wl["gaussians_with_grad"]
-    chunks = (N + 4095) // 4096 + 1
     bytes_alg = {
-        # projection: map read once for both views (40 B) + SH for Gaussians visible in >= 1 view (192 B); per pair the tile
-        # rect and depth bits out (8 B); per visible pair the 32-B record and the clamp byte.  Compaction pass: the 8 B per
-        # pair back in, 12 B per visible pair out (depth key, {rect | id}).
-        "preprocess_map": 40 * P + 192 * max(wl["visible"]) + 2 * P * 16 + Pv * (12 + 32 + 1),
-        # visible (u32 depth key, u64 {rect | id}) pairs: histogram read + 4 digit passes of (12 B in + 12 B out)
-        "depth_sort(cub)": Pv * (4 + 4 * 24),
-        "scan(cub)": Pv * 12,
-        # tile binning (csrc/tilebin.cu): chunks of 4096 instances of one view x `tiles` bins.  count: pairs in, u16 counts
-        # and (u16 tile, u32 id) per instance out; scan: counts in, u32 prefixes out; scatter: instances and prefixes in,
-        # 4 B per instance out
-        "tile_count": Pv * 12 + chunks * tiles * 2 + N * 6,
-        "tile_scan": chunks * tiles * (2 + 4),
-        "tile_scatter": N * 6 + chunks * tiles * 4 + N * 4,
+        # projection, SURVEY.md 8(d) row A: 44 B of geometry per Gaussian, 192 B of SH per Gaussian visible in >= 1 view, out
+        # 32 B per visible pair (depth, pixel centre, conic + opacity, gray) and 4 B per Gaussian (tiles touched)
+        "preprocess_map": 44 * P + 192 * max(wl["visible"]) + 32 * Pv + 4 * P,
+        # binning (csrc/bucketbin.cu), irreducible bytes: every visible pair's (rect, depth bits, id) must be read once
+        # (12 B) and every tile instance's id written once (4 B); the bucket keys in between are this design's own traffic
+        "bucket_scatter": 12 * Pv,
+        "bucket_sort": 4 * N,
         # compaction scan (rect word per pair + 24 B of the accumulator per visible pair) + per active pair: list entry
         # out/in, accumulator in and cleared, xyz/opacity + covariance, SH (AoS copy), clamp byte
         "geom_bwd_pose": 2 * P * 4 + Pv * 24 + Pg * (8 + 32 + 32 + 40 + 192 + 1),
@@ -451,9 +444,9 @@ def roofline(stages, wl, P, HW, clocks, default_workload=True, tiles=1200):
         if name in traffic:
             row["traffic_bytes"] = int(traffic[name])
         table[name] = row
-    # the dominant HBM-bound kernel OF OURS carries the contract's `roofline` object (the CUB library stages — depth
-    # sort, offsets scan — are listed with their own fractions in `stages_ms`)
-    hb = max((n for n in table if table[n].get("bound") == "hbm" and "(cub)" not in n), key=lambda n: table[n]["ms"])
+    # the dominant HBM-bound kernel carries the contract's `roofline` object (every stage is listed with its own fraction
+    # in `stages_ms`)
+    hb = max((n for n in table if table[n].get("bound") == "hbm"), key=lambda n: table[n]["ms"])
     top = max(table, key=lambda n: table[n]["ms"])
     r = table[hb]
     roof = {"kernel": hb, "bound": "hbm", "achieved": r["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": r["frac"],

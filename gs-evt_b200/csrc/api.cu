@@ -401,28 +401,21 @@ struct GsevtEngine {
     float4* grad8 = nullptr;
     uint32_t* rect_raw = nullptr;        // [padded 2P] tile rect per (view, Gaussian), 0 = not visible
     uint32_t* depth_raw = nullptr;       // [padded 2P] depth bits per (view, Gaussian)
-    uint32_t* offsets = nullptr;
     uint8_t* clamped = nullptr;
     uint32_t* active_list = nullptr;   // [2P] compacted pairs with a gradient
     uint32_t* active_count = nullptr;
-    void* scan_temp = nullptr; size_t scan_bytes = 0;
-    uint32_t* comp_state = nullptr;                      // compaction: per-CTA visible counts (zero between launches) + their prefix
-    uint32_t* n_vis = nullptr;                           // device: visible (view, Gaussian) pairs of the last projection
-    int vis_cap = 0;                                     // slots the depth sort covers: upper bound on n_vis the current level's graph was sized for
-    uint32_t *depth_key = nullptr, *depth_sorted = nullptr;
-    uint64_t *pairs = nullptr, *pairs_sorted = nullptr;   // {tile rect | pair id}: projection order / depth order
-    void* sortA_temp = nullptr; size_t sortA_bytes = 0;
-    // tile binning (tilebin.cu): per-chunk tile counts, their prefix over the chunks, chunk pair ranges, per-tile totals
-    uint16_t* tb_hist = nullptr; uint32_t* tb_base = nullptr; uint32_t* tb_total = nullptr;
-    size_t tb_items = 0, tb_rows = 0;    // allocated hist / base elements, chunk rows
-    // radix fallback when the strip has more tiles than the counting kernels bin in shared memory (binning.cu):
-    // (u16 tile key, u32 id) records, double-buffered for a CUB sort
-    int bin_path = 0;                    // 0 tile binning by counting, 1 emit + radix sort + range scan
-    int bin_mode = 0;                    // gsevt_engine_set_binning: 0 automatic, 1 counting, 2 radix
-    uint16_t *keys_u = nullptr, *keys = nullptr;
-    uint32_t* vals_u = nullptr;
-    void* sort_temp = nullptr; size_t sort_bytes = 0; long long radix_cap = 0, inst_cap = 0;
+    // binning (bucketbin.cu): bucket grid of the current level / strip, per-bucket segment table, key segments, tile lists
+    int bin_mode = 0;                    // gsevt_engine_set_binning: 0 automatic, 1 buckets of one tile, 2 buckets of 2 x 2 tiles
+    int bk_shift = 0, bk_nbx = 0, bk_nby = 0, bk_by_origin = 0, bk_nb = 0;
+    int bk_max_buckets = 0;              // entries of the three tables below (2 views x tiles of level 0)
+    uint32_t* bk_cursor = nullptr;       // [bk_max_buckets][GSEVT_BK_CURSOR_STRIDE]
+    uint32_t* bk_start = nullptr; uint32_t* bk_cap = nullptr; uint32_t* bk_counts = nullptr;
+    uint64_t *bk_keys = nullptr, *bk_keys2 = nullptr;
+    long long bk_total = 0;              // key slots of the current level (sum of the bucket capacities)
+    long long bk_alloc = 0, vals_alloc = 0;   // allocated key slots (each buffer) / list slots
+    int bk_smem_elems = 8;
     uint32_t* vals = nullptr;            // per-tile lists: Gaussian index per slot
+    uint32_t* hit_base = nullptr;        // [2 tiles]
     uint2* ranges = nullptr;
     uint32_t* hitmask = nullptr; size_t hitmask_stride = 0;   // forward -> backward: what each warp blended
     float* gray = nullptr; float* final_T = nullptr; uint32_t* n_contrib = nullptr;
@@ -433,11 +426,9 @@ struct GsevtEngine {
     int* host_flag = nullptr;   // pinned, mapped
     int* host_flag_dev = nullptr;
     const float* ev_sign = nullptr;
-    int cap = 0;        // allocated instance capacity (both views together)
-    int sort_n = 0;     // number of slots sorted in the current level
     int geom_blocks = 0, loss_nb = 0;
     cudaGraphExec_t graph = nullptr;
-    int graph_level = -1, graph_sort_n = -1, graph_y0 = -1, graph_y1 = -1, graph_vis_cap = -1;
+    int graph_level = -1, graph_y0 = -1, graph_y1 = -1, graph_shift = -1, graph_smem = -1;
     cudaStream_t graph_stream = nullptr;
     // screen-tile split (one engine per rank; strips of tile rows per pyramid level)
     int split_rank = 0, split_n = 1;
@@ -468,86 +459,36 @@ static void dev_free(GsevtEngine* e, void* p) {
     cudaFree(p);
 }
 
-// Slots sorted per iteration for `total` live tile instances: a little slack so that the pose may move inside a
-// level without re-sizing (an overflow is detected on the device, the iteration is voided and the host re-sizes:
-// gsevt_engine_resume), rounded so that small changes do not re-capture the CUDA graph.
-static long long slots_for(long long total) {
-    long long want = total + total / 16 + 16384;
-    return (want + 4095) / 4096 * 4096;
-}
-
-// Words per warp row of the hit-mask table: word (range.x >> 5) + tile index + group, see blend.cu.
-static size_t hitmask_stride_for(const GsevtEngine* e, long long cap) {
-    const LevelInfo& L0 = e->lv[0];
-    return (size_t)(cap / 32 + 2 * (long long)L0.gx * L0.gy + 64);
-}
-
-// Grows the instance buffers (never inside a captured graph).
-static int ensure_capacity(GsevtEngine* e, long long slots, cudaStream_t s) {
-    if (slots <= e->cap) return 0;
-    long long cap = slots + slots / 2;
-    if (cap > 0x3fffffff) cap = 0x3fffffff;
-    if (slots > cap) { set_error("instance count %lld exceeds the supported maximum", slots); return GSEVT_EOVERFLOW; }
+static void quiesce(GsevtEngine* e, cudaStream_t s) {
     // only this engine's own work uses the buffers (a device-wide sync would also wait for the kernels of OTHER
     // engines, which in a one-process tile-split group may be waiting for this rank)
     cudaStreamSynchronize(s);
     if (e->graph_stream && e->graph_stream != s) cudaStreamSynchronize(e->graph_stream);
     if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
-    dev_free(e, e->vals);
-    dev_free(e, e->hitmask);
-    e->vals = nullptr; e->hitmask = nullptr;
-    e->cap = (int)cap;
-    e->hitmask_stride = hitmask_stride_for(e, e->cap);
-    int rc = 0;
-    rc |= dev_alloc(e, &e->hitmask, 8 * e->hitmask_stride);
-    rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
-    return rc ? GSEVT_ECUDA : 0;
 }
 
-// The tile-binning kernels keep 26 bytes per bin (= tile of the strip, one view) in shared memory next to 24 KB of
-// staging; above this many bins a CTA no longer shares an SM and the per-bin bookkeeping outweighs the 4096 instances of
-// a chunk — measured at 3600 bins (1280x720 unsplit): binning 1.13 ms against 0.77 ms for emit + radix sort, which is used
-// instead from here on.
-#define GSEVT_TILEBIN_MAX_BINS 2048
-
-// Picks the binning path for the current level / strip and (re)sizes its work buffers for e->sort_n instance slots
-// (never inside a captured graph).
-static int ensure_binning(GsevtEngine* e, cudaStream_t s) {
-    const LevelInfo& L = e->lv[e->cur_level];
-    const int bins = (e->strip_y1 - e->strip_y0) * L.gx;   // per view: a chunk of the tile binning holds one view
-    e->bin_path = e->bin_mode == 2 ? 1 : (bins <= GSEVT_TILEBIN_MAX_BINS ? 0 : 1);
-    auto quiesce = [&]() {
-        cudaStreamSynchronize(s);
-        if (e->graph_stream && e->graph_stream != s) cudaStreamSynchronize(e->graph_stream);
-        if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
-    };
+// Grows the key segments, the tile lists and the hit-mask table (never inside a captured graph).
+static int ensure_capacity(GsevtEngine* e, long long keys, int shift, cudaStream_t s) {
+    const long long lists = keys << (2 * shift);
+    if (lists > 0x7fffffffLL) { set_error("instance count %lld exceeds the supported maximum", lists); return GSEVT_EOVERFLOW; }
     int rc = 0;
-    if ((long long)e->sort_n > e->inst_cap) {   // (tile, id) per instance: both paths
-        quiesce();
-        dev_free(e, e->keys_u); dev_free(e, e->vals_u);
-        e->keys_u = nullptr; e->vals_u = nullptr;
-        e->inst_cap = (long long)e->sort_n + e->sort_n / 4;
-        rc |= dev_alloc(e, &e->keys_u, (size_t)e->inst_cap);
-        rc |= dev_alloc(e, &e->vals_u, (size_t)e->inst_cap);
+    if (keys > e->bk_alloc) {
+        quiesce(e, s);
+        dev_free(e, e->bk_keys); dev_free(e, e->bk_keys2);
+        e->bk_keys = e->bk_keys2 = nullptr;
+        e->bk_alloc = keys + keys / 4;
+        rc |= dev_alloc(e, &e->bk_keys, (size_t)e->bk_alloc);
+        rc |= dev_alloc(e, &e->bk_keys2, (size_t)e->bk_alloc);
     }
-    if (e->bin_path == 0) {
-        const size_t rows = tilebin_chunks(e->sort_n) + 1, items = rows * (size_t)bins;
-        if (items > e->tb_items || rows > e->tb_rows) {
-            quiesce();
-            dev_free(e, e->tb_hist); dev_free(e, e->tb_base);
-            e->tb_hist = nullptr; e->tb_base = nullptr;
-            e->tb_items = items + items / 4; e->tb_rows = rows + rows / 4;
-            rc |= dev_alloc(e, &e->tb_hist, e->tb_items);
-            rc |= dev_alloc(e, &e->tb_base, e->tb_items);
-        }
-    } else if ((long long)e->sort_n > e->radix_cap) {
-        quiesce();
-        dev_free(e, e->keys); dev_free(e, e->sort_temp);
-        e->keys = nullptr; e->sort_temp = nullptr;
-        e->radix_cap = (long long)e->sort_n + e->sort_n / 4;
-        e->sort_bytes = sort16_temp_bytes((int)e->radix_cap);
-        rc |= dev_alloc(e, &e->keys, (size_t)e->radix_cap);
-        rc |= dev_alloc(e, (char**)&e->sort_temp, e->sort_bytes);
+    if (lists > e->vals_alloc) {
+        quiesce(e, s);
+        dev_free(e, e->vals); dev_free(e, e->hitmask);
+        e->vals = nullptr; e->hitmask = nullptr;
+        e->vals_alloc = lists + lists / 4;
+        // words per warp row of the hit-mask table: (list slot >> 5) + one spare word per tile, see blend.cu / bucketbin.cu
+        e->hitmask_stride = (size_t)(e->vals_alloc / 32 + 4 * (long long)e->bk_max_buckets + 64);
+        rc |= dev_alloc(e, &e->vals, (size_t)e->vals_alloc);
+        rc |= dev_alloc(e, &e->hitmask, 8 * e->hitmask_stride);
     }
     return rc ? GSEVT_ECUDA : 0;
 }
@@ -570,25 +511,34 @@ static void projection_colmajor(double znear, double zfar, double fovX, double f
         for (int r = 0; r < 4; r++) out[4 * c + r] = P[r][c];
 }
 
-static PreMapArgs premap_args(GsevtEngine* e, int vis_cap) {
+static PreMapArgs premap_args(GsevtEngine* e) {
     const GsevtMap* m = e->map;
     PreMapArgs pa;
     pa.P = m->P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
     pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
-    pa.rect_raw = e->rect_raw; pa.depth_raw = e->depth_raw; pa.clamped = e->clamped; pa.depth_key = e->depth_key; pa.pairs = e->pairs;
+    pa.rect_raw = e->rect_raw; pa.depth_raw = e->depth_raw; pa.clamped = e->clamped;
     pa.rec = e->rec; pa.grad8 = e->grad8;
-    pa.cta_count = e->comp_state;
-    pa.n_vis = e->n_vis; pa.vis_cap = vis_cap; pa.overflow = e->overflow;
     return pa;
+}
+
+static BucketArgs bucket_args(GsevtEngine* e) {
+    const LevelInfo& L = e->lv[e->cur_level];
+    BucketArgs b;
+    b.P = e->map->P; b.s = e->bk_shift; b.nbx = e->bk_nbx; b.nby = e->bk_nby; b.by_origin = e->bk_by_origin; b.nb = e->bk_nb;
+    b.gx = L.gx; b.gy = L.gy; b.tiles_global = L.gx * L.gy;
+    b.rect_raw = e->rect_raw; b.depth_raw = e->depth_raw;
+    b.cursor = e->bk_cursor; b.bk_start = e->bk_start; b.bk_cap = e->bk_cap;
+    b.keys = e->bk_keys; b.keys2 = e->bk_keys2; b.vals = e->vals; b.ranges = e->ranges; b.hit_base = e->hit_base;
+    b.smem_elems = e->bk_smem_elems; b.overflow = e->overflow; b.ctl = e->ctl;
+    return b;
 }
 
 // Enqueue one full optimisation iteration (or one evaluation) on stream s.  When `ev` is non-null an
 // event is recorded before every stage and after the last one (GSEVT_NSTAGES + 1 events): used by
 // gsevt_engine_profile for per-stage device times, never inside a captured graph.
-#define GSEVT_NSTAGES 11
+#define GSEVT_NSTAGES 8
 static const char* const kStageNames[GSEVT_NSTAGES] = {
-    "preprocess_map", "depth_sort(cub)", "scan(cub)", "tile_count", "tile_scan", "tile_scatter",
-    "blend_fwd_gray", "loss_stats", "blend_bwd_gray", "geom_bwd_pose", "engine_update"};
+    "preprocess_map", "bucket_scatter", "bucket_sort", "blend_fwd_gray", "loss_stats", "blend_bwd_gray", "geom_bwd_pose", "engine_update"};
 
 static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = nullptr) {
     const GsevtMap* m = e->map;
@@ -597,47 +547,22 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     int stage = 0;
     auto mark = [&]() { if (ev) cudaEventRecord(ev[stage], s); stage++; };
     // the two ViewParams blocks are current on entry: written by the previous iteration's update kernel, or by
-    // the stand-alone pose kernel after any host-side change of state / level (probe_instances, set_state, ...)
+    // the stand-alone pose kernel after any host-side change of state / level (probe_buckets, set_state, ...)
     mark();
-    const PreMapArgs pa = premap_args(e, e->vis_cap);
-    launch_preprocess_map(pa, s);
+    launch_preprocess_map(premap_args(e), s);
     mark();
-    const int nv = e->vis_cap;   // pairs sorted / scanned / emitted: the visible ones + sentinel slack
-    launch_sort_pairs32(e->sortA_temp, e->sortA_bytes, e->depth_key, e->depth_sorted, e->pairs, e->pairs_sorted, nv, s);
+    const BucketArgs ba = bucket_args(e);
+    launch_bucket_scatter(ba, false, s);
     mark();
-    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs_sorted, e->n_vis, e->offsets, nv, s);
+    launch_bucket_sort(ba, s);
     mark();
-    const int tiles = L.gx * L.gy;
-    if (e->bin_path == 0) {
-        TileBinArgs tb;
-        tb.P = P; tb.n_pairs = nv; tb.grid_x = L.gx;
-        tb.tiles_per_view = (e->strip_y1 - e->strip_y0) * L.gx; tb.row0 = e->strip_y0; tb.tiles_global = tiles;
-        tb.pairs = e->pairs_sorted; tb.offsets = e->offsets; tb.n_vis = e->n_vis; tb.hist = e->tb_hist; tb.base = e->tb_base; tb.inst_tile = e->keys_u; tb.inst_id = e->vals_u;
-        tb.tile_total = e->tb_total; tb.ticket = e->tb_total + 2 * (size_t)e->lv[0].gx * e->lv[0].gy; tb.ranges = e->ranges; tb.values = e->vals; tb.cap = e->sort_n; tb.overflow = e->overflow;
-        tb.ctl = e->ctl;
-        launch_tile_count(tb, s);
-        mark();
-        launch_tile_scan(tb, s);
-        mark();
-        launch_tile_scatter(tb, s);
-        mark();
-    } else {
-        // radix fallback (same three stage slots): emit (tile key, id) records, stable sort on the tile key, range scan
-        launch_emit_tiles(P, nv, L.gx, tiles, e->pairs_sorted, e->offsets, e->keys_u, e->vals_u, e->sort_n, e->overflow, e->ctl, s);
-        mark();
-        const int bit = (int)higher_msb((uint32_t)(2 * tiles));
-        launch_sort_pairs16(e->sort_temp, e->sort_bytes, e->keys_u, e->keys, e->vals_u, e->vals, e->sort_n, bit, s);
-        mark();
-        launch_identify_ranges16(e->keys, e->ranges, 2 * tiles, e->offsets + (nv - 1), e->sort_n, s);
-        mark();
-    }
     BlendFwdArgs f;
     memset(&f, 0, sizeof(f));
     f.W = L.W; f.H = L.H; f.grid_x = L.gx; f.grid_y = L.gy; f.nviews = 2;
     f.tile_y0 = e->strip_y0; f.tile_rows = e->strip_y1 - e->strip_y0;
     f.ranges = e->ranges; f.point_list = e->vals; f.rec = e->rec; f.view_stride_gauss = (size_t)P;
     f.views = e->views; f.final_T = e->final_T; f.n_contrib = e->n_contrib; f.out_color = e->gray; f.ctl = e->ctl;
-    f.hitmask = e->hitmask; f.hitmask_stride = e->hitmask_stride;
+    f.hitmask = e->hitmask; f.hitmask_stride = e->hitmask_stride; f.hit_base = e->hit_base;
     launch_blend_fwd_gray(f, s);
     mark();
     const float* evf = e->ev_sign + L.ev_offset;
@@ -655,7 +580,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     b.tile_y0 = e->strip_y0; b.tile_rows = e->strip_y1 - e->strip_y0;
     b.ranges = e->ranges; b.point_list = e->vals; b.rec = e->rec; b.view_stride_gauss = (size_t)P; b.views = e->views;
     b.final_T = e->final_T; b.n_contrib = e->n_contrib; b.gray = e->gray; b.event_frame = evf; b.ctl = e->ctl;
-    b.grad8 = e->grad8; b.hitmask = e->hitmask; b.hitmask_stride = e->hitmask_stride;
+    b.grad8 = e->grad8; b.hitmask = e->hitmask; b.hitmask_stride = e->hitmask_stride; b.hit_base = e->hit_base;
     launch_blend_bwd_gray(b, s);
     mark();
     GeomBwdArgs q;
@@ -758,14 +683,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     }
     const int P = map->P;
     const size_t p2 = 2 * (size_t)P;
-    long long cap = cfg->instance_capacity > 0 ? (long long)cfg->instance_capacity * 2 : (long long)P * 16;   // grows on demand
-    if (cap < (1 << 20)) cap = 1 << 20;
-    if (cap > 0x3fffffff) cap = 0x3fffffff;
-    e->cap = (int)cap;
-    e->sort_n = e->cap;
-    e->scan_bytes = scan_temp_bytes((int)p2);
-    { const size_t g = scan_gather_temp_bytes((int)p2); if (g > e->scan_bytes) e->scan_bytes = g; }
-    e->sortA_bytes = sort32_temp_bytes((int)p2);
+    if ((long long)P >= (1LL << 31) / 2) { set_error("map too large: pair ids are 32-bit"); delete e; return GSEVT_EINVAL; }
     e->geom_blocks = geom_bwd_blocks(P, 2);
     const LevelInfo& L0 = e->lv[0];
     const size_t hw = (size_t)L0.W * L0.H;
@@ -778,24 +696,24 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->grad8, 2 * p2);
     rc |= dev_alloc(e, &e->rect_raw, preprocess_map_raw_items(P));
     rc |= dev_alloc(e, &e->depth_raw, preprocess_map_raw_items(P));
-    rc |= dev_alloc(e, &e->offsets, p2);
     rc |= dev_alloc(e, &e->clamped, p2);
     rc |= dev_alloc(e, &e->active_list, p2);
     rc |= dev_alloc(e, &e->active_count, 1);
-    rc |= dev_alloc(e, (char**)&e->scan_temp, e->scan_bytes);
-    rc |= dev_alloc(e, (char**)&e->comp_state, preprocess_map_state_bytes(P));
-    rc |= dev_alloc(e, &e->n_vis, 2);
-    rc |= dev_alloc(e, &e->depth_key, p2);
-    rc |= dev_alloc(e, &e->depth_sorted, p2);
-    rc |= dev_alloc(e, &e->pairs, p2);
-    rc |= dev_alloc(e, &e->pairs_sorted, p2);
-    rc |= dev_alloc(e, (char**)&e->sortA_temp, e->sortA_bytes);
-    rc |= dev_alloc(e, &e->vals, (size_t)e->cap);
-    rc |= dev_alloc(e, &e->tb_total, 2 * (size_t)L0.gx * L0.gy + 4);   // per-tile totals + the tile_scan ticket word
-    rc |= dev_alloc(e, &e->ranges, 2 * (size_t)L0.gx * L0.gy);
-    if (tilebin_configure(GSEVT_TILEBIN_MAX_BINS)) { set_error("image too large for the tile binning kernels"); gsevt_engine_destroy(e); return GSEVT_EINVAL; }
-    e->hitmask_stride = hitmask_stride_for(e, e->cap);
-    rc |= dev_alloc(e, &e->hitmask, 8 * e->hitmask_stride);
+    e->bk_max_buckets = 2 * L0.gx * L0.gy;
+    rc |= dev_alloc(e, &e->bk_cursor, (size_t)e->bk_max_buckets * GSEVT_BK_CURSOR_STRIDE);
+    rc |= dev_alloc(e, &e->bk_start, (size_t)e->bk_max_buckets);
+    rc |= dev_alloc(e, &e->bk_cap, (size_t)e->bk_max_buckets);
+    rc |= dev_alloc(e, &e->bk_counts, (size_t)e->bk_max_buckets);
+    rc |= dev_alloc(e, &e->ranges, (size_t)e->bk_max_buckets);
+    rc |= dev_alloc(e, &e->hit_base, (size_t)e->bk_max_buckets);
+    if (bucket_sort_configure()) { set_error("bucket_sort: cannot reserve %d bytes of shared memory", GSEVT_BK_SMEM_MAX_ELEMS * 16); gsevt_engine_destroy(e); return GSEVT_ECUDA; }
+    {
+        // first guess of the list memory (grows on demand at begin_level): 16 instances per Gaussian or the caller's hint
+        long long keys = cfg->instance_capacity > 0 ? (long long)cfg->instance_capacity * 2 : (long long)P * 4;
+        if (keys < (1 << 18)) keys = 1 << 18;
+        if (keys > 0x0fffffff) keys = 0x0fffffff;
+        if (!rc) rc |= ensure_capacity(e, keys, 1, nullptr);
+    }
     rc |= dev_alloc(e, &e->gray, 2 * hw);
     rc |= dev_alloc(e, &e->final_T, 2 * hw);
     rc |= dev_alloc(e, &e->n_contrib, 2 * hw);
@@ -806,7 +724,6 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->row_hist, 256);
     if (rc) { gsevt_engine_destroy(e); return GSEVT_ECUDA; }
     e->strip_y0 = 0; e->strip_y1 = e->lv[0].gy;
-    e->vis_cap = (int)p2;
     if (cudaHostAlloc((void**)&e->host_flag, 4, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&e->host_flag_dev, e->host_flag, 0) != cudaSuccess) {
         set_error("pinned flag allocation failed"); gsevt_engine_destroy(e); return GSEVT_ECUDA;
@@ -823,8 +740,9 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     float bg[4] = {cfg->background[0], cfg->background[1], cfg->background[2], 0.f};
     cudaMemcpy(e->bg3, bg, sizeof(bg), cudaMemcpyHostToDevice);
     cudaMemset(e->overflow, 0, 4);
-    cudaMemset(e->tb_total, 0, (2 * (size_t)L0.gx * L0.gy + 4) * 4);
-    cudaMemset(e->comp_state, 0, preprocess_map_state_bytes(P));   // the counters start from zero; compact_scan_kernel clears what it reads
+    cudaMemset(e->bk_cursor, 0, (size_t)e->bk_max_buckets * GSEVT_BK_CURSOR_STRIDE * 4);
+    cudaMemset(e->ranges, 0, (size_t)e->bk_max_buckets * sizeof(uint2));
+    cudaMemset(e->hit_base, 0, (size_t)e->bk_max_buckets * 4);
     cudaMemset(e->loss_partials, 0, ((size_t)e->loss_nb * 3 + 2) * 8);
     cudaMemset(e->grad8, 0, 2 * p2 * 16);
     cudaMemset(e->rect_raw, 0, preprocess_map_raw_items(P) * 4);
@@ -881,23 +799,32 @@ GSEVT_API int gsevt_engine_begin_frame(GsevtEngine* e, double delta_tau, const f
     return 0;
 }
 
-static int probe_instances(GsevtEngine* e, cudaStream_t s, uint32_t* total, uint32_t* n_vis) {
-    // pose_setup + projection + scan only, to size the sorts for this level: tile instances and visible pairs.
-    const GsevtMap* m = e->map;
+// Bucket grid of the current level / strip for bucket edge 1 << shift.
+static void set_bucket_grid(GsevtEngine* e, int shift) {
+    const LevelInfo& L = e->lv[e->cur_level];
+    e->bk_shift = shift;
+    e->bk_nbx = ((L.gx - 1) >> shift) + 1;
+    e->bk_by_origin = e->strip_y0 >> shift;
+    e->bk_nby = e->strip_y1 > e->strip_y0 ? ((e->strip_y1 - 1) >> shift) - e->bk_by_origin + 1 : 0;
+    e->bk_nb = e->bk_nbx * e->bk_nby;
+}
+
+// pose_setup + projection + a count-only run of the bucket scatter at the current state: keys per bucket of the
+// current bucket grid -> counts[2 * bk_nb] (host).  Leaves the cursors at zero.
+static int probe_buckets(GsevtEngine* e, cudaStream_t s, std::vector<uint32_t>& counts) {
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // pending iterations first (see gsevt_engine_status)
     SETF(level_done, (int)0);
     launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, s);
-    const int n2 = 2 * m->P;
-    PreMapArgs pa = premap_args(e, n2);   // no bound on the count
-    pa.overflow = nullptr;
-    launch_preprocess_map(pa, s);
-    launch_scan_gather(e->scan_temp, e->scan_bytes, e->pairs, e->n_vis, e->offsets, n2, s);   // projection order: only the total matters here
-    uint32_t h[2] = {0, 0};
-    GSEVT_CUDA_OK(cudaMemcpyAsync(&h[0], e->offsets + ((size_t)n2 - 1), 4, cudaMemcpyDeviceToHost, s));
-    GSEVT_CUDA_OK(cudaMemcpyAsync(&h[1], e->n_vis, 4, cudaMemcpyDeviceToHost, s));
+    launch_preprocess_map(premap_args(e), s);
+    const int nbt = 2 * e->bk_nb;
+    counts.assign((size_t)(nbt > 0 ? nbt : 1), 0u);
+    if (nbt <= 0) return 0;
+    launch_bucket_scatter(bucket_args(e), true, s);
+    launch_bucket_counts(nbt, e->bk_cursor, e->bk_counts, s);
+    GSEVT_CUDA_OK(cudaMemsetAsync(e->bk_cursor, 0, (size_t)nbt * GSEVT_BK_CURSOR_STRIDE * 4, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // counts is pageable host memory: wait first (see gsevt_engine_status)
+    GSEVT_CUDA_OK(cudaMemcpyAsync(counts.data(), e->bk_counts, (size_t)nbt * 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
-    *total = h[0];
-    if (n_vis) *n_vis = h[1];
     return 0;
 }
 
@@ -927,16 +854,21 @@ void balance_rows(const uint32_t* cost, int rows, int n, int* bounds) {
     bounds[n] = rows;
 }
 
-// Sizes the per-iteration sort of the current level at the current pose; split mode: (re)balances the strips first.
+// Sizes the binning of the current level at the current pose: bucket shape, the segment of every bucket (its key count
+// now + slack: the count moves while the pose is optimised; a bucket that outgrows its segment voids the iteration on the
+// device and the host comes back here through gsevt_engine_resume), list memory, shared memory of the sort kernel.
+// Split mode: (re)balances the strips first.
 static int size_level(GsevtEngine* e, cudaStream_t s, bool rebalance, int slack_div) {
     const LevelInfo& L = e->lv[e->cur_level];
-    uint32_t total = 0, n_vis = 0;
     int rc = 0;
+    std::vector<uint32_t> counts;
     if (e->split_n > 1 && rebalance) {
         if ((rc = upload_strip(e, 0, L.gy, s))) return rc;
-        if ((rc = probe_instances(e, s, &total, &n_vis))) return rc;
-        launch_row_histogram((int)n_vis, e->pairs, e->row_hist, s);
+        set_bucket_grid(e, 0);
+        if ((rc = probe_buckets(e, s, counts))) return rc;   // (only the projection is needed here)
+        launch_row_histogram(2 * e->map->P, e->rect_raw, e->row_hist, s);
         uint32_t h[256];
+        GSEVT_CUDA_OK(cudaStreamSynchronize(s));
         GSEVT_CUDA_OK(cudaMemcpyAsync(h, e->row_hist, sizeof(h), cudaMemcpyDeviceToHost, s));
         GSEVT_CUDA_OK(cudaStreamSynchronize(s));
         int bounds[GSEVT_SPLIT_MAX + 1];
@@ -945,18 +877,41 @@ static int size_level(GsevtEngine* e, cudaStream_t s, bool rebalance, int slack_
     } else if (e->split_n <= 1) {
         if ((rc = upload_strip(e, 0, L.gy, s))) return rc;
     }
-    if ((rc = probe_instances(e, s, &total, &n_vis))) return rc;   // with this engine's strip in force
-    const long long want = slots_for((long long)total + (slack_div > 0 ? total / slack_div : 0));
-    if ((rc = ensure_capacity(e, want, s))) return rc;
-    e->sort_n = (int)want;
-    if ((rc = ensure_binning(e, s))) return rc;
-    // visible pairs: the count moves while the pose is optimised; above the cap the device voids the iteration and pauses
-    long long vslack = (long long)n_vis / 16 + 8192;
-    if (slack_div > 0) vslack += n_vis / slack_div;
-    long long cap = ((long long)n_vis + vslack + 4095) / 4096 * 4096;
-    if (cap > 2LL * e->map->P) cap = 2LL * e->map->P;
-    e->vis_cap = (int)cap;
+    // Bucket edge: 2 x 2 tiles halve the keys to scatter and sort (a rect of 2 x 2 tiles meets 2.5 buckets on average
+    // instead of 4.7 tiles) as long as a bucket still sorts in shared memory; coarse pyramid levels (few tiles, long lists)
+    // and very dense maps fall back to one tile per bucket.
+    const int strip_tiles = (e->strip_y1 - e->strip_y0) * L.gx;
+    int shift = e->bin_mode == 1 ? 0 : (e->bin_mode == 2 ? 1 : (strip_tiles >= 256 ? 1 : 0));
+    uint32_t maxc = 0;
+    for (;;) {
+        set_bucket_grid(e, shift);
+        if ((rc = probe_buckets(e, s, counts))) return rc;   // with this engine's strip in force
+        maxc = 0;
+        for (int b = 0; b < 2 * e->bk_nb; b++) maxc = counts[b] > maxc ? counts[b] : maxc;
+        if (shift == 1 && e->bin_mode == 0 && maxc + maxc / 8 + 64 > GSEVT_BK_SMEM_MAX_ELEMS) { shift = 0; continue; }
+        break;
+    }
+    const int nbt = 2 * e->bk_nb;
+    std::vector<uint32_t> start((size_t)(nbt > 0 ? nbt : 1), 0u), cap((size_t)(nbt > 0 ? nbt : 1), 0u);
+    long long total = 0;
+    uint32_t maxcap = 8;
+    for (int b = 0; b < nbt; b++) {
+        long long c = (long long)counts[b] + counts[b] / 16 + 64;
+        if (slack_div > 0) c += counts[b] / slack_div;
+        c = (c + 7) / 8 * 8;
+        start[b] = (uint32_t)total; cap[b] = (uint32_t)c;
+        total += c;
+        if ((uint32_t)c > maxcap) maxcap = (uint32_t)c;
+    }
+    if ((rc = ensure_capacity(e, total, shift, s))) return rc;
+    e->bk_total = total;
+    e->bk_smem_elems = (int)(maxcap < GSEVT_BK_SMEM_MAX_ELEMS ? maxcap : GSEVT_BK_SMEM_MAX_ELEMS);
+    if (nbt > 0) {
+        GSEVT_CUDA_OK(cudaMemcpyAsync(e->bk_start, start.data(), (size_t)nbt * 4, cudaMemcpyHostToDevice, s));
+        GSEVT_CUDA_OK(cudaMemcpyAsync(e->bk_cap, cap.data(), (size_t)nbt * 4, cudaMemcpyHostToDevice, s));
+    }
     GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // start / cap are stack-frame vectors
     return 0;
 }
 }  // namespace gsevt
@@ -999,9 +954,11 @@ GSEVT_API int gsevt_engine_iterate(GsevtEngine* e, int32_t n, void* stream) {
     if (!e->ev_sign) { set_error("iterate before begin_frame"); return GSEVT_ESTATE; }
     cudaStream_t s = (cudaStream_t)stream;
     const bool can_graph = s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread;
-    if (can_graph && (e->graph == nullptr || e->graph_level != e->cur_level || e->graph_sort_n != e->sort_n || e->graph_stream != s ||
+    // the captured launches carry the bucket grid, the sort kernel's shared-memory size and every buffer pointer by value
+    // (buffers that grow destroy the graph: quiesce())
+    if (can_graph && (e->graph == nullptr || e->graph_level != e->cur_level || e->graph_stream != s ||
                       e->graph_y0 != e->strip_y0 || e->graph_y1 != e->strip_y1 ||
-                      e->graph_vis_cap != e->vis_cap)) {
+                      e->graph_shift != e->bk_shift || e->graph_smem != e->bk_smem_elems)) {
         if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
         cudaGraph_t g = nullptr;
         GSEVT_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
@@ -1011,8 +968,8 @@ GSEVT_API int gsevt_engine_iterate(GsevtEngine* e, int32_t n, void* stream) {
         err = cudaGraphInstantiate(&e->graph, g, 0);
         cudaGraphDestroy(g);
         if (err != cudaSuccess) { e->graph = nullptr; set_error("graph instantiate failed: %s", cudaGetErrorString(err)); return GSEVT_ECUDA; }
-        e->graph_level = e->cur_level; e->graph_sort_n = e->sort_n; e->graph_stream = s;
-        e->graph_y0 = e->strip_y0; e->graph_y1 = e->strip_y1; e->graph_vis_cap = e->vis_cap;
+        e->graph_level = e->cur_level; e->graph_stream = s;
+        e->graph_y0 = e->strip_y0; e->graph_y1 = e->strip_y1; e->graph_shift = e->bk_shift; e->graph_smem = e->bk_smem_elems;
     }
     for (int i = 0; i < n; i++) {
         if (can_graph) GSEVT_CUDA_OK(cudaGraphLaunch(e->graph, s));
@@ -1035,24 +992,20 @@ GSEVT_API int gsevt_engine_status(GsevtEngine* e, GsevtEngineStatus* out, void* 
     // being waited for is a tile-split exchange whose peer is driven by one of those threads.
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     GSEVT_CUDA_OK(cudaMemcpyAsync(&h, e->ctl, offsetof(EngineCtl, losses), cudaMemcpyDeviceToHost, s));
-    // instances of view 0 = start of the first non-empty range of view 1 = number of sorted keys below `tiles`;
-    // read it from the ranges: the first touched tile of view 1 starts where view 0 ends.
-    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[1], e->offsets + ((size_t)e->vis_cap - 1), 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaMemcpyAsync(&ov, e->overflow, 4, cudaMemcpyDeviceToHost, s));
     {
+        // tile instances per view = the lengths of the view's tile lists
         const LevelInfo& L = e->lv[e->cur_level];
         const int tiles = L.gx * L.gy;
         std::vector<uint2> r((size_t)2 * tiles);
         GSEVT_CUDA_OK(cudaMemcpyAsync(r.data(), e->ranges, r.size() * sizeof(uint2), cudaMemcpyDeviceToHost, s));
         GSEVT_CUDA_OK(cudaStreamSynchronize(s));
-        uint32_t v0 = 0;
-        for (int t = 0; t < tiles; t++) v0 += r[t].y - r[t].x;
-        offs[0] = v0;
+        for (int t = 0; t < tiles; t++) { offs[0] += r[t].y - r[t].x; offs[1] += r[tiles + t].y - r[tiles + t].x; }
     }
     memset(out, 0, sizeof(*out));
     out->level_done = h.level_done; out->optim_iter = h.optim_iter; out->start_vel_opt_iter = h.start_vel_opt_iter;
     out->opt_vel = h.opt_vel; out->iters_executed = h.iters_executed; out->overflow = ov;
-    out->num_rendered[0] = (int)offs[0]; out->num_rendered[1] = (int)(offs[1] - offs[0]);
+    out->num_rendered[0] = (int)offs[0]; out->num_rendered[1] = (int)offs[1];
     out->last_loss = h.last_loss;
     memcpy(out->pose_grads, h.grads, sizeof(h.grads));
     return 0;
@@ -1141,25 +1094,24 @@ GSEVT_API int gsevt_engine_binning(GsevtEngine* e, int32_t view, uint64_t* keys_
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // see gsevt_engine_status
     GSEVT_CUDA_OK(cudaMemcpyAsync(r.data(), e->ranges, r.size() * sizeof(uint2), cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
-    uint32_t n0 = 0, n1 = 0;
-    for (int t = 0; t < tiles; t++) { n0 += r[t].y - r[t].x; n1 += r[tiles + t].y - r[tiles + t].x; }
-    const uint32_t first = view == 0 ? 0u : n0, count = view == 0 ? n0 : n1;
-    if ((int64_t)count > (int64_t)capacity) { set_error("capacity %d < %u instances", capacity, count); return GSEVT_ENOMEM; }
-    uint16_t* tile_keys = nullptr;   // tile id per slot, as the high word of the reference's sorted keys holds it (both paths)
-    GSEVT_CUDA_OK(cudaMalloc(&tile_keys, ((size_t)n0 + n1 + 1) * sizeof(uint16_t)));
-    launch_keys_from_ranges(2 * tiles, e->ranges, tile_keys, s);
-    launch_rebuild_keys(tile_keys, e->vals, e->rec + 2 * (size_t)view * e->map->P, (uint32_t)(view * tiles), first, count, keys_out,
-                        list_out, s);
-    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
-    cudaFree(tile_keys);
-    // ranges of this view, rebased to its own list (untouched tiles stay (0,0) like the reference's)
-    std::vector<uint32_t> rr((size_t)2 * tiles, 0u);
+    // the engine's tile lists are not packed back to back (bucketbin.cu); the reference's representation is: lists in
+    // tile order, ranges into that packed list, (0, 0) for untouched tiles
+    std::vector<uint32_t> packed((size_t)tiles, 0u), rr((size_t)2 * tiles, 0u);
+    uint32_t count = 0;
     for (int t = 0; t < tiles; t++) {
         const uint2 q = r[(size_t)view * tiles + t];
-        if (q.y > q.x) { rr[2 * t] = q.x - first; rr[2 * t + 1] = q.y - first; }
+        packed[t] = count;
+        if (q.y > q.x) { rr[2 * t] = count; rr[2 * t + 1] = count + (q.y - q.x); }
+        count += q.y - q.x;
     }
+    if ((int64_t)count > (int64_t)capacity) { set_error("capacity %d < %u instances", capacity, count); return GSEVT_ENOMEM; }
+    uint32_t* packed_dev = nullptr;
+    GSEVT_CUDA_OK(cudaMalloc(&packed_dev, (size_t)tiles * 4));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(packed_dev, packed.data(), (size_t)tiles * 4, cudaMemcpyHostToDevice, s));
+    launch_export_lists(tiles, e->ranges + (size_t)view * tiles, e->vals, e->rec + 2 * (size_t)view * e->map->P, packed_dev, keys_out, list_out, s);
     GSEVT_CUDA_OK(cudaMemcpyAsync(ranges_out, rr.data(), rr.size() * 4, cudaMemcpyHostToDevice, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    cudaFree(packed_dev);
     return (int)count;
 }
 
@@ -1201,7 +1153,6 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
     unsigned long long h[8];
     uint32_t offs[2] = {0, 0};
     GSEVT_CUDA_OK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s));
-    GSEVT_CUDA_OK(cudaMemcpyAsync(&offs[1], e->offsets + ((size_t)e->vis_cap - 1), 4, cudaMemcpyDeviceToHost, s));
     uint32_t n_active = 0;   // length of the last iteration's active list (the accumulators themselves are cleared by geom_bwd)
     GSEVT_CUDA_OK(cudaMemcpyAsync(&n_active, e->active_count, 4, cudaMemcpyDeviceToHost, s));
     {
@@ -1209,14 +1160,14 @@ GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream)
         std::vector<uint2> r((size_t)2 * tiles);
         GSEVT_CUDA_OK(cudaMemcpyAsync(r.data(), e->ranges, r.size() * sizeof(uint2), cudaMemcpyDeviceToHost, s));
         GSEVT_CUDA_OK(cudaStreamSynchronize(s));
-        for (int t = 0; t < tiles; t++) offs[0] += r[t].y - r[t].x;
+        for (int t = 0; t < tiles; t++) { offs[0] += r[t].y - r[t].x; offs[1] += r[tiles + t].y - r[tiles + t].x; }
     }
     cudaFree(d);
     out8[0] = (int64_t)h[0]; out8[1] = (int64_t)h[1];              // visible Gaussians per view
-    out8[2] = (int64_t)offs[0]; out8[3] = (int64_t)(offs[1] - offs[0]);  // tile instances per view
+    out8[2] = (int64_t)offs[0]; out8[3] = (int64_t)offs[1];              // tile instances per view
     out8[4] = (int64_t)h[2]; out8[5] = (int64_t)h[3];              // sum of n_contrib per view (pairs walked)
     out8[6] = (int64_t)n_active;                                   // (view, Gaussian) pairs with a non-zero blend gradient
-    out8[7] = (int64_t)e->sort_n;                                  // slots sorted (instances + padding)
+    out8[7] = (int64_t)e->bk_total;                                // key slots of the bucket segments (bucket keys + slack)
     return 0;
 }
 
@@ -1314,19 +1265,15 @@ GSEVT_API int gsevt_engine_split_info(GsevtEngine* e, int32_t out6[6], void* str
 
 GSEVT_API int gsevt_engine_set_binning(GsevtEngine* e, int32_t mode) {
     if (!e || mode < 0 || mode > 2) { set_error("set_binning: bad arguments"); return GSEVT_EINVAL; }
-    if (mode == 1 && e->lv[0].gx * e->lv[0].gy > GSEVT_TILEBIN_MAX_BINS) {
-        set_error("set_binning: %d tiles per view exceed the counting kernels' %d bins", e->lv[0].gx * e->lv[0].gy, GSEVT_TILEBIN_MAX_BINS);
-        return GSEVT_EINVAL;
-    }
-    e->bin_mode = mode;
+    e->bin_mode = mode;   // takes effect at the next begin_level / eval / resume (the graph is keyed on the bucket shape)
     return 0;
 }
 
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e) {
-    // preprocess_map, compact_pairs, {tile_count, tile_scan, tile_scatter | emit_tiles, identify_ranges16},
-    // blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, engine_update; plus CUB library kernels: the depth sort
-    // (histogram + exclusive sum + four onesweep passes), the offsets scan, and on the radix path the 16-bit tile sort.
-    return e && e->bin_path == 1 ? 10 : 11;
+    // preprocess_map, bucket_scatter, bucket_sort, blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, engine_update:
+    // all of them this library's own kernels
+    (void)e;
+    return 9;
 }
 
 }  // extern "C"

@@ -104,10 +104,11 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     const float4* __restrict__ rec = a.rec + 2 * (size_t)view * a.view_stride_gauss;
     const int todo = (int)(range.y - range.x);
     const int rounds = (todo + 255) / 256;
-    // engine: this warp's row of the hit-mask table; word (range.x >> 5) + tile_lin + g holds list positions
-    // [32 g, 32 g + 32) of this tile (rows of consecutive tiles cannot overlap: floor(len/32) + 1 >= ceil(len/32))
+    // engine: this warp's row of the hit-mask table; word hit_base[tile] + g holds list positions [32 g, 32 g + 32) of this
+    // tile.  hit_base = (range.x >> 5) + (rank of the tile in memory order), written with the ranges by bucket_sort: rows
+    // of consecutive tiles cannot overlap (floor(len/32) + 1 >= ceil(len/32))
     uint32_t* __restrict__ hitrow =
-        OPERATOR || !a.hitmask ? nullptr : a.hitmask + (size_t)warp * a.hitmask_stride + (range.x >> 5) + (uint32_t)tile_lin;
+        OPERATOR || !a.hitmask ? nullptr : a.hitmask + (size_t)warp * a.hitmask_stride + a.hit_base[tile_lin];
 
     float T = 1.0f;
     uint32_t last_contributor = 0;
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     float* __restrict__ grad_f = reinterpret_cast<float*>(a.grad8 + 2 * (size_t)view * a.view_stride_gauss);
     const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
     const uint32_t* __restrict__ hitrow =
-        OPERATOR ? nullptr : a.hitmask + (size_t)warp * a.hitmask_stride + (range.x >> 5) + (uint32_t)tile_lin;
+        OPERATOR ? nullptr : a.hitmask + (size_t)warp * a.hitmask_stride + a.hit_base[tile_lin];
 
     float T = T_final;
     float accum_rec[C], last_color[C];

@@ -68,8 +68,8 @@ struct SplitComm {
     unsigned long long timeout_ns;
     MailBox* box[GSEVT_SPLIT_MAX];      // box[rank] is local
 };
-// Pairs' tile-rect rows: hist[y] += width of every rect covering tile row y (both views), for strip balancing.
-void launch_row_histogram(int n_pairs, const uint64_t* pairs, uint32_t* hist256, cudaStream_t s);
+// Tile-rect rows: hist[y] += width of every rect covering tile row y (both views), for strip balancing.
+void launch_row_histogram(int n_pairs, const uint32_t* rect_raw, uint32_t* hist256, cudaStream_t s);
 
 // ---- preprocess ------------------------------------------------------------------------------
 struct PreAosArgs {
@@ -103,23 +103,14 @@ struct PreMapArgs {
     const float2* cov3D_b;
     const float* sh_planar;   // [48][P]
     // per pair in index order (padded to preprocess_map_raw_items): tile rect x0 | y0<<8 | x1<<16 | y1<<24, 0 = not visible
-    // (culled, or outside this engine's strip), and the float bits of the view depth
+    // (culled, or outside this engine's strip), and the float bits of the view depth — what the bucket scatter reads
     uint32_t* rect_raw;
     uint32_t* depth_raw;
     uint8_t* clamped;         // [2P]
-    // visible pairs only, compacted in index order per view (compact_pairs_kernel): entries [0, *n_vis)
-    uint32_t* depth_key;      // float bits of the view depth
-    uint64_t* pairs;          // {tile rect} << 32 | pair id (= view * P + Gaussian)
-    uint32_t* cta_count;      // [2][P / 256] visible pairs per projection CTA and view (zero between launches), followed by
-                              // their exclusive prefix [2][P / 256]: preprocess_map_state_bytes(P) in all
-    uint32_t* n_vis;          // out: [0] number of visible pairs, [1] number of visible pairs of view 0
-    int vis_cap;              // slots the depth sort covers: [*n_vis, vis_cap) are filled with sentinels
-    int* overflow;            // set when *n_vis > vis_cap (may be NULL)
     float4* rec;              // [2][2P]
     float4* grad8;            // [2][2P]
 };
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s);
-size_t preprocess_map_state_bytes(int P);
 size_t preprocess_map_raw_items(int P);
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s);
 void launch_pack_map(int P, int M, const float* xyz, const float* scales, const float* rots, const float* opac,
@@ -145,51 +136,35 @@ void launch_sort_pairs(void* temp, size_t temp_bytes, const uint64_t* keys_in, u
 void launch_identify_ranges(const uint64_t* keys, uint2* ranges, int ntiles_total, int n_host, const uint32_t* n_dev,
                             int cap, cudaStream_t s);
 uint32_t higher_msb(uint32_t n);
-// engine: depth sort of the visible (view, Gaussian) pairs; radix fallback of the tile binning (stable 16-bit tile sort)
-size_t sort32_temp_bytes(int n);
-size_t sort16_temp_bytes(int n);
-size_t scan_gather_temp_bytes(int n);
-void launch_sort_pairs32(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out,
-                         const uint64_t* vals_in, uint64_t* vals_out, int n, cudaStream_t s);
-void launch_sort_pairs16(void* temp, size_t temp_bytes, const uint16_t* keys_in, uint16_t* keys_out,
-                         const uint32_t* vals_in, uint32_t* vals_out, int n, int end_bit, cudaStream_t s);
-// offsets = inclusive sum of the tile-rect areas of `pairs` ({rect (high 32) | pair id (low 32)}), in array order;
-// entries at and past *n_live count as empty
-void launch_scan_gather(void* temp, size_t temp_bytes, const uint64_t* pairs, const uint32_t* n_live, uint32_t* offsets, int n,
-                        cudaStream_t s);
-void launch_emit_tiles(int P, int n_pairs, int grid_x, int tiles_per_view, const uint64_t* pairs, const uint32_t* offsets,
-                       uint16_t* keys, uint32_t* values, int cap, int* overflow, const EngineCtl* ctl, cudaStream_t s);
-// ---- tile binning without instance records (tilebin.cu) ----------------------------------------
-struct TileBinArgs {
-    int P, n_pairs, grid_x;
-    int tiles_per_view;         // bins per view: the tiles of this engine's strip of tile rows (the whole grid unless split)
-    int row0, tiles_global;     // first tile row of the strip; tiles per view of the whole grid (ranges are indexed globally)
-    const uint64_t* pairs;      // depth-sorted {rect | pair id}, n_pairs entries (sentinels with rect 0 at the end)
-    const uint32_t* offsets;    // inclusive sum of the rect areas
-    const uint32_t* n_vis;      // [0] visible pairs, [1] those of view 0 (they come first: the sort key carries the view)
-    uint16_t* hist;             // [chunks + 1][tiles_per_view]: a chunk holds instances of ONE view
-    uint32_t* base;             // [chunks + 1][tiles_per_view]
-    uint16_t* inst_tile;        // [cap] bin of every instance, in sequence order (count -> scatter)
-    uint32_t* inst_id;          // [cap] Gaussian index of every instance, in sequence order
-    uint32_t* tile_total;       // [2 * tiles_per_view]
-    uint32_t* ticket;           // one zero-initialised word: CTAs of tile_scan done (the last one computes the ranges and resets it)
-    uint2* ranges;              // [2 * tiles_per_view] out
-    uint32_t* values;           // [cap] out: Gaussian index per slot of the per-tile lists
-    int cap;                    // instance slots available; more live instances -> *overflow = 1, nothing written
+// ---- engine binning (bucketbin.cu) -------------------------------------------------------------------
+#define GSEVT_BK_CURSOR_STRIDE 64        // u32 words between two bucket cursors: 256 B, one L2 atomic unit each
+#define GSEVT_BK_SMEM_MAX_ELEMS 14080    // keys per shared-memory buffer of bucket_sort (2 buffers x 8 B: 220 KB)
+struct BucketArgs {
+    int P;
+    int s;                      // log2 of the bucket edge in tiles: 0 or 1
+    int nbx, nby, by_origin;    // bucket grid of the engine's strip; by_origin = first tile row >> s
+    int nb;                     // buckets per view (nbx * nby); bucket index = view * nb + by * nbx + bx
+    int gx, gy, tiles_global;   // tile grid of the level; ranges / hit_base are indexed view * tiles_global + ty * gx + tx
+    const uint32_t* rect_raw;   // [2P] projection output, index order
+    const uint32_t* depth_raw;  // [2P]
+    uint32_t* cursor;           // [2 nb][GSEVT_BK_CURSOR_STRIDE] keys taken per bucket; zero between iterations
+    const uint32_t* bk_start;   // [2 nb] first key slot of the bucket's segment (multiple of 8)
+    const uint32_t* bk_cap;     // [2 nb] slots of the segment (multiple of 8)
+    uint64_t* keys;             // bucket segments: (depth bits << 32) | Gaussian index
+    uint64_t* keys2;            // second buffer for buckets sorted in global memory
+    uint32_t* vals;             // per-tile lists: tile k of bucket b at (start[b] << 2s) + k * cap[b]
+    uint2* ranges;              // out: (begin, end) into vals per tile
+    uint32_t* hit_base;         // out: first word of the tile's hit-mask rows (blend.cu)
+    int smem_elems;             // keys per shared-memory buffer of this launch (multiple of 8)
     int* overflow;
     const EngineCtl* ctl;
 };
-int tilebin_chunk();
-size_t tilebin_chunks(int cap);   // chunk CTAs (= rows of hist / base) for `cap` instance slots
-int tilebin_configure(int max_tiles_per_view);
-void launch_tile_count(const TileBinArgs& a, cudaStream_t s);
-void launch_tile_scan(const TileBinArgs& a, cudaStream_t s);
-void launch_tile_scatter(const TileBinArgs& a, cudaStream_t s);
-void launch_keys_from_ranges(int nt, const uint2* ranges, uint16_t* keys, cudaStream_t s);
-void launch_identify_ranges16(const uint16_t* keys, uint2* ranges, int ntiles_total, const uint32_t* n_dev, int cap,
-                              cudaStream_t s);
-void launch_rebuild_keys(const uint16_t* tile_keys, const uint32_t* vals, const float4* rec_view, uint32_t tile_base,
-                         uint32_t first, uint32_t count, uint64_t* keys_out, uint32_t* list_out, cudaStream_t s);
+int bucket_sort_configure();
+void launch_bucket_scatter(const BucketArgs& a, bool count_only, cudaStream_t s);
+void launch_bucket_sort(const BucketArgs& a, cudaStream_t s);
+void launch_bucket_counts(int n, const uint32_t* cursor, uint32_t* out, cudaStream_t s);
+void launch_export_lists(int tiles, const uint2* ranges_view, const uint32_t* vals, const float4* rec_view, const uint32_t* packed_start,
+                         uint64_t* keys_out, uint32_t* list_out, cudaStream_t s);
 
 // ---- blending --------------------------------------------------------------------------------
 struct BlendFwdArgs {
@@ -211,6 +186,7 @@ struct BlendFwdArgs {
     int* n_touched;              // operator only, may be NULL
     uint32_t* hitmask;           // engine: [8 warps][hitmask_stride] which list positions each warp blended (may be NULL)
     size_t hitmask_stride;
+    const uint32_t* hit_base;    // engine: first word of each tile's rows in the hit-mask table (written by bucket_sort)
     const EngineCtl* ctl;
 };
 void launch_blend_fwd_rgb(const BlendFwdArgs& a, cudaStream_t s);
@@ -239,6 +215,7 @@ struct BlendBwdArgs {
     // outputs (accumulated with float atomics, must be zero on entry)
     const uint32_t* hitmask;     // engine: written by the forward (required on the engine path)
     size_t hitmask_stride;
+    const uint32_t* hit_base;
     float4* grad8;               // [nviews][2P]: operator {dmx, dmy, dA, dB | dC, dopacity, dcol0, ddepth}
                                  //               engine   {dmx, dmy, dA, dB | dC, dgray, 0, 0}
     float2* gradc;               // operator: [P] {dcol1, dcol2}

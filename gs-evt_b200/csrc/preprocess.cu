@@ -142,7 +142,6 @@ __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a)
     __shared__ ViewParams s_vp[2];
     load_views(s_vp, a.views, 2);
     const int idx = blockIdx.x * 256 + threadIdx.x;
-    const unsigned live_mask = __ballot_sync(0xffffffffu, idx < a.P);   // a prefix of the warp's lanes
     if (idx >= a.P) return;
     const float4 xo = __ldg(a.xyz_opacity + idx);
     float cov[6];
@@ -167,17 +166,8 @@ __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a)
             o[v].rect = (r & 0x00FF00FFu) | (y0 << 8) | (y1 << 24);
         }
     }
-    // visible pairs of this CTA per view, for the compaction pass (one fire-and-forget add per warp and view; the
-    // counters are zero on entry: compact_scan_kernel clears what it reads)
-    {
-        const unsigned b0 = __ballot_sync(live_mask, ok[0]), b1 = __ballot_sync(live_mask, ok[1]);
-        if ((threadIdx.x & 31) == 0) {
-            if (b0) atomicAdd(a.cta_count + blockIdx.x, (uint32_t)__popc(b0));
-            if (b1) atomicAdd(a.cta_count + gridDim.x + blockIdx.x, (uint32_t)__popc(b1));
-        }
-    }
-    // per pair, in index order: the tile rect (0 = not visible here) and the depth bits; compact_pairs_kernel squeezes
-    // the visible ones together for the depth sort
+    // per pair, in index order: the tile rect (0 = not visible here) and the depth bits — the input of the bucket scatter
+    // (bucketbin.cu), which reads them with unit stride and skips the zeros: no compaction pass in between
 #pragma unroll
     for (int v = 0; v < 2; v++) {
         const size_t j = (size_t)v * a.P + idx;
@@ -225,112 +215,6 @@ __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a)
     }
 }
 
-// Compaction of the visible (view, Gaussian) pairs, in index order — two small passes between the projection and the
-// depth sort.  Within a view the compact order is the index order, which is all the stable depth sort needs to reproduce
-// the reference's (depth, index) tie-break; pairs of different views never meet in a tile list.  The depth sort / scan /
-// tile binning then run over the visible pairs instead of all 2P (and, under the screen-tile split, over this rank's
-// strip only).
-//   projection    adds every warp's visible count to its CTA's counter (per view)
-//   compact_scan  one CTA: exclusive prefix over the 2 x (P / 256) counters (view 0 first), clears them, publishes the
-//                 totals (all / view 0) and checks them against the slots the depth sort covers
-//   compact_pairs CTA = the same 256 Gaussians of one view: ballot + 8 warp counts + the CTA's base -> unit-stride
-//                 writes of (key, {rect | id}); a few extra CTAs write the sentinel keys behind the visible pairs
-// No chained scan, no spinning: what was tried before — the scan inside the projection kernel (barriers and look-back
-// cost the heavy kernel 30 us) and a chained-scan pass of its own (25 us, of which the look-back of a resident wave of
-// CTAs was most) — is in the history of this file.
-__global__ void __launch_bounds__(1024) compact_scan_kernel(int nblk, uint32_t* __restrict__ cta_count, uint32_t* __restrict__ cta_base,
-                                                            uint32_t* __restrict__ n_vis, int vis_cap, int* __restrict__ overflow,
-                                                            const EngineCtl* __restrict__ ctl) {
-    if (ctl && ctl->level_done) return;
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = 2 * nblk;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int t0 = 0; t0 < n; t0 += 4096) {
-        const int i = t0 + threadIdx.x * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            v[k] = i + k < n ? cta_count[i + k] : 0u;
-            if (i + k < n) cta_count[i + k] = 0u;
-        }
-        const uint32_t sum = v[0] + v[1] + v[2] + v[3];
-        uint32_t x = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = s_warp[lane];
-            uint32_t xs = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
-                if (lane >= o) xs += y;
-            }
-            s_warp[lane] = xs - w;   // exclusive
-        }
-        __syncthreads();
-        uint32_t run = s_carry + s_warp[warp] + x - sum;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (i + k < n) cta_base[i + k] = run;
-            if (i + k == nblk) n_vis[1] = run;   // everything in front of view 1 = the visible pairs of view 0
-            run += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = run;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const uint32_t total = s_carry;
-        n_vis[0] = total;
-        if (overflow && total > (uint32_t)vis_cap) *overflow = 1;
-    }
-}
-
-constexpr int CP_FILL_CTAS = 16;
-__global__ void __launch_bounds__(256) compact_pairs_kernel(int P, int nblk, const uint32_t* __restrict__ rect_raw,
-                                                            const uint32_t* __restrict__ depth_raw,
-                                                            const uint32_t* __restrict__ cta_base, const uint32_t* __restrict__ n_vis,
-                                                            uint32_t* __restrict__ depth_key, uint64_t* __restrict__ pairs, int vis_cap,
-                                                            const EngineCtl* __restrict__ ctl) {
-    if (ctl && ctl->level_done) return;
-    if ((int)blockIdx.x >= nblk) {
-        // sentinel keys behind the visible pairs (0xFFFFFFFF sorts last; the offsets scan treats entries past *n_vis as
-        // empty, see PairArea in binning.cu): the fixed-size depth sort over vis_cap slots is defined whatever the count
-        if (blockIdx.y) return;
-        for (uint32_t i = n_vis[0] + (blockIdx.x - nblk) * 256u + threadIdx.x; i < (uint32_t)vis_cap; i += CP_FILL_CTAS * 256u)
-            depth_key[i] = 0xFFFFFFFFu;
-        return;
-    }
-    __shared__ uint32_t s_warp[8];
-    const int view = blockIdx.y;
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    const size_t j = (size_t)view * P + idx;
-    const uint32_t rect = idx < P ? __ldg(rect_raw + j) : 0u;
-    const uint32_t key = idx < P ? __ldg(depth_raw + j) : 0u;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned b = __ballot_sync(0xffffffffu, rect != 0u);
-    if (lane == 0) s_warp[warp] = (uint32_t)__popc(b);
-    __syncthreads();
-    if (rect == 0u) return;
-    uint32_t slot = __ldg(cta_base + (size_t)view * nblk + blockIdx.x) + (uint32_t)__popc(b & ((1u << lane) - 1u));
-#pragma unroll
-    for (int w = 0; w < 8; w++) slot += w < warp ? s_warp[w] : 0u;
-    // Sort key: view << 31 | depth bits (depths are positive floats: bit 31 is free).  The depth sort then also separates
-    // the two views — pairs of different views never meet in a tile list, so the order inside every list is unchanged —
-    // and the tile binning works on one view (half the bins) at a time.
-    depth_key[slot] = key | ((uint32_t)view << 31);
-    pairs[slot] = ((uint64_t)rect << 32) | (uint64_t)j;
-}
-
-size_t preprocess_map_state_bytes(int P) { return ((size_t)(P + 255) / 256 * 4 + 16) * sizeof(uint32_t); }   // counts + bases, 2 views
 size_t preprocess_map_raw_items(int P) { return (2 * (size_t)P + 1023) / 1024 * 1024; }
 
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
@@ -349,10 +233,6 @@ void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
             else preprocess_map_kernel<3, 3><<<blocks, 256, 0, s>>>(a);
             break;
     }
-    uint32_t* cta_base = a.cta_count + 2 * (size_t)blocks;
-    compact_scan_kernel<<<1, 1024, 0, s>>>(blocks, a.cta_count, cta_base, a.n_vis, a.vis_cap, a.overflow, a.ctl);
-    compact_pairs_kernel<<<dim3(blocks + CP_FILL_CTAS, 2), 256, 0, s>>>(a.P, blocks, a.rect_raw, a.depth_raw, cta_base, a.n_vis,
-                                                                       a.depth_key, a.pairs, a.vis_cap, a.ctl);
 }
 
 // checkFrustum (rasterizer_impl.cu:54-66)

@@ -239,7 +239,8 @@ class TrackingEngine:
         return dict(visible=v[0:2], instances=v[2:4], pairs_walked=v[4:6], gaussians_with_grad=v[6], sorted_slots=v[7])
 
     def set_binning(self, mode):
-        """0 automatic, 1 tile binning by counting, 2 emit + radix sort (diagnostic: both give identical lists)."""
+        """Bucket shape of the binning from the next begin_level / eval on: 0 automatic, 1 one tile per bucket,
+        2 buckets of 2 x 2 tiles (diagnostic: all give identical lists)."""
         _lib.check(self._lib.gsevt_engine_set_binning(self.handle, int(mode)), "gsevt_engine_set_binning")
 
     @property

@@ -309,19 +309,17 @@ def test_engine_eval_matches_oracle(built, cuda_dev, level, signed):
     Lo, go, aux = orc.tracking_eval(*args)
     assert abs(L - Lo) < 1e-5 * abs(Lo)
     assert H.rel_max(gl, aux["gray"][0]) < TOL_IMG and H.rel_max(gn, aux["gray"][1]) < TOL_IMG
-    # the engine bins with a depth sort + a stable partition by tile (csrc/tilebin.cu); the resulting lists must be the
-    # reference's, bit for bit — and so must those of the radix fallback it uses on grids too large for the counting kernels
-    for view in (0, 1):
-        keys, ids, ranges = eng.binning(view, level)
-        fw = aux["fw"][view]
-        assert np.array_equal(keys, fw["keys"]) and np.array_equal(ids, fw["point_list"]) and np.array_equal(ranges, fw["ranges"])
-    eng.set_binning(2)
-    L2, g2 = eng.eval(level, signed)
-    assert L2 == L
-    for view in (0, 1):
-        keys, ids, ranges = eng.binning(view, level)
-        fw = aux["fw"][view]
-        assert np.array_equal(keys, fw["keys"]) and np.array_equal(ids, fw["point_list"]) and np.array_equal(ranges, fw["ranges"])
+    # the engine bins by scattering the visible pairs into buckets of tiles, sorting every bucket on (depth bits, index) and
+    # filtering it into its tiles (csrc/bucketbin.cu); the resulting lists must be the reference's, bit for bit, whatever
+    # the bucket shape: automatic, one tile per bucket, 2 x 2 tiles per bucket
+    for mode in (0, 1, 2):
+        eng.set_binning(mode)
+        Lm, gm = eng.eval(level, signed)
+        assert Lm == L
+        for view in (0, 1):
+            keys, ids, ranges = eng.binning(view, level)
+            fw = aux["fw"][view]
+            assert np.array_equal(keys, fw["keys"]) and np.array_equal(ids, fw["point_list"]) and np.array_equal(ranges, fw["ranges"]), (mode, view)
     eng.set_binning(0)
     if signed:
         assert H.rel_max(g, go) < TOL_GRAD

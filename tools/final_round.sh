@@ -5,13 +5,13 @@
 set -u
 TAG="${1:-final}"; OUT=gpurun_out; mkdir -p $OUT
 bash tools/gpu_round.sh "$TAG" tests smoke bench ref launches
-REGEX='preprocess_map|compact_scan|compact_pairs|tile_count|tile_scan|tile_scatter|blend_fwd|blend_bwd|geom_compact|geom_bwd|loss_stats|engine_update|Onesweep|Histogram|ExclusiveSum|DeviceScan'
+REGEX='preprocess_map|bucket_scatter|bucket_sort|blend_fwd|blend_bwd|geom_compact|geom_bwd|loss_stats|engine_update'
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"$REGEX" -s "${NCU_SKIP:-100}" -c "${NCU_COUNT:-40}" \
     -o "$OUT/${TAG}_full" -f python bench.py --steps 6 --warmup 3 --no-cpu-baseline > "$OUT/${TAG}_full.log" 2>&1
 tail -2 "$OUT/${TAG}_full.log"
 ncu -i "$OUT/${TAG}_full.ncu-rep" --page raw --csv > "$OUT/${TAG}_full_raw.csv" 2>/dev/null
 ncu -i "$OUT/${TAG}_full.ncu-rep" --page details --csv > "$OUT/${TAG}_full_details.csv" 2>/dev/null
-for k in blend_fwd_kernelILi1ELb0 blend_bwd_kernelILi1ELb0 tile_scatter_kernel tile_count_kernel preprocess_map_kernelILi3 compact_pairs_kernel; do
+for k in blend_fwd_kernelILi1ELb0 blend_bwd_kernelILi1ELb0 bucket_sort_kernel bucket_scatter_kernel preprocess_map_kernelILi3; do
   python tools/ncu_lines.py "$OUT/${TAG}_full.ncu-rep" $k --top 30 > "$OUT/${TAG}_lines_$k.txt" 2>&1
 done
 ls -la $OUT/${TAG}_full*

@@ -33,7 +33,7 @@ fi
 if has full; then
   # kernels of the steady-state iterations only: skip the map packing / probing / warm-up launches
   timeout 1200 ncu --set full --clock-control none --import-source on \
-      -k regex:'preprocess_map|compact_scan|compact_pairs|tile_count|tile_scan|tile_scatter|blend_fwd|blend_bwd|geom_compact|geom_bwd|loss_stats|engine_update|Onesweep|Histogram|ExclusiveSum|DeviceScan' \
+      -k regex:'preprocess_map|bucket_scatter|bucket_sort|blend_fwd|blend_bwd|geom_compact|geom_bwd|loss_stats|engine_update' \
       -s "${NCU_SKIP:-120}" -c "${NCU_COUNT:-40}" -o "$OUT/${TAG}_full" -f \
       python bench.py --steps 6 --warmup 3 --no-cpu-baseline > "$OUT/${TAG}_full.log" 2>&1
   tail -2 "$OUT/${TAG}_full.log"

@@ -2,7 +2,7 @@
 # ncu --set full of the binning / projection kernels of two steady-state iterations; exports CSV pages on the box and drops
 # the report when it is too large to travel back (gpurun_out is limited to 64 MiB).
 TAG="${1:-run}"; OUT=gpurun_out; mkdir -p $OUT
-REGEX="${2:-preprocess_map|compact_scan|compact_pairs|tile_count|tile_scan|tile_scatter|geom_compact}"
+REGEX="${2:-preprocess_map|bucket_scatter|bucket_sort|geom_compact}"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$REGEX" -s "${NCU_SKIP:-40}" -c "${NCU_COUNT:-14}" \
     -o "$OUT/${TAG}_full" -f python bench.py --steps 6 --warmup 3 --no-cpu-baseline > "$OUT/${TAG}_full.log" 2>&1
 tail -2 "$OUT/${TAG}_full.log"

@@ -14,13 +14,10 @@ import csv
 import json
 import os
 
-STAGE_OF = [  # (substring of the kernel name, stage); CUB kernels are attributed by position, see below
-    ("preprocess_map_kernel", "preprocess_map"), ("compact_pairs_kernel", "preprocess_map"), ("compact_scan_kernel", "preprocess_map"),
-    ("tile_count_kernel", "tile_count"), ("tile_scan_kernel", "tile_scan"),
-    ("tile_scatter_kernel", "tile_scatter"),
+STAGE_OF = [  # (substring of the kernel name, stage)
+    ("preprocess_map_kernel", "preprocess_map"), ("bucket_scatter_kernel", "bucket_scatter"), ("bucket_sort_kernel", "bucket_sort"),
     ("blend_fwd_kernel", "blend_fwd_gray"), ("loss_stats_kernel", "loss_stats"), ("blend_bwd_kernel", "blend_bwd_gray"),
     ("geom_compact_kernel", "geom_bwd_pose"), ("geom_bwd_kernel", "geom_bwd_pose"), ("engine_update_kernel", "engine_update"),
-    ("depth_sort_", "depth_sort"), ("tile_sort_", "tile_sort"), ("tile_bin_", "tile_sort"),
 ]
 
 
@@ -48,15 +45,8 @@ def main():
     for row in keep:
         name = row[k]
         stage = next((s for sub, s in STAGE_OF if sub in name), None)
-        if stage is None and "cub::" in name:
-            if "DeviceScan" in name:
-                stage = "scan(cub)"
-            elif "RadixSort" in name:
-                stage = "depth_sort(cub)"
         if stage is None:
             continue
-        if "cub::" not in name:
-            after = stage
         b = float(row[r]) * sr + float(row[w]) * sw
         per[stage][0] += b
         per[stage][1] += float(row[t])
