@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -413,7 +414,8 @@ struct GsevtEngine {
     uint64_t *bk_keys = nullptr, *bk_keys2 = nullptr;
     long long bk_total = 0;              // key slots of the current level (sum of the bucket capacities)
     long long bk_alloc = 0, vals_alloc = 0;   // allocated key slots (each buffer) / list slots
-    int bk_smem_elems = 8;
+    int bk_smem_elems = 8, bk_smem_bins = 2048; size_t bk_smem_bytes = 0;   // shared memory of a sort CTA (bucket_sort_smem)
+    uint32_t* bk_order = nullptr;        // [bk_max_buckets] buckets by decreasing key count: the order the sort CTAs take them
     uint32_t* vals = nullptr;            // per-tile lists: Gaussian index per slot
     uint32_t* hit_base = nullptr;        // [2 tiles]
     uint2* ranges = nullptr;
@@ -529,7 +531,8 @@ static BucketArgs bucket_args(GsevtEngine* e) {
     b.rect_raw = e->rect_raw; b.depth_raw = e->depth_raw;
     b.cursor = e->bk_cursor; b.bk_start = e->bk_start; b.bk_cap = e->bk_cap;
     b.keys = e->bk_keys; b.keys2 = e->bk_keys2; b.vals = e->vals; b.ranges = e->ranges; b.hit_base = e->hit_base;
-    b.smem_elems = e->bk_smem_elems; b.overflow = e->overflow; b.ctl = e->ctl;
+    b.bk_order = e->bk_order; b.smem_elems = e->bk_smem_elems; b.smem_bins = e->bk_smem_bins; b.smem_bytes = e->bk_smem_bytes;
+    b.overflow = e->overflow; b.ctl = e->ctl;
     return b;
 }
 
@@ -700,13 +703,16 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->active_list, p2);
     rc |= dev_alloc(e, &e->active_count, 1);
     e->bk_max_buckets = 2 * L0.gx * L0.gy;
-    rc |= dev_alloc(e, &e->bk_cursor, (size_t)e->bk_max_buckets * GSEVT_BK_CURSOR_STRIDE);
+    rc |= dev_alloc(e, &e->bk_cursor, (size_t)e->bk_max_buckets * GSEVT_BK_SUB * GSEVT_BK_CURSOR_STRIDE);
     rc |= dev_alloc(e, &e->bk_start, (size_t)e->bk_max_buckets);
     rc |= dev_alloc(e, &e->bk_cap, (size_t)e->bk_max_buckets);
-    rc |= dev_alloc(e, &e->bk_counts, (size_t)e->bk_max_buckets);
+    rc |= dev_alloc(e, &e->bk_counts, (size_t)e->bk_max_buckets * GSEVT_BK_SUB);
+    rc |= dev_alloc(e, &e->bk_order, (size_t)e->bk_max_buckets);
     rc |= dev_alloc(e, &e->ranges, (size_t)e->bk_max_buckets);
     rc |= dev_alloc(e, &e->hit_base, (size_t)e->bk_max_buckets);
-    if (bucket_sort_configure()) { set_error("bucket_sort: cannot reserve %d bytes of shared memory", GSEVT_BK_SMEM_MAX_ELEMS * 16); gsevt_engine_destroy(e); return GSEVT_ECUDA; }
+    if (bucket_sort_configure()) { set_error("bucket_sort: cannot reserve %d bytes of shared memory", GSEVT_BK_SMEM_MAX_BYTES); gsevt_engine_destroy(e); return GSEVT_ECUDA; }
+    if (P >= (1 << 28)) { set_error("map too large: the tile filter packs a Gaussian index into 28 bits"); gsevt_engine_destroy(e); return GSEVT_EINVAL; }
+    bucket_sort_smem(8, &e->bk_smem_elems, &e->bk_smem_bins, &e->bk_smem_bytes);
     {
         // first guess of the list memory (grows on demand at begin_level): 16 instances per Gaussian or the caller's hint
         long long keys = cfg->instance_capacity > 0 ? (long long)cfg->instance_capacity * 2 : (long long)P * 4;
@@ -740,7 +746,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     float bg[4] = {cfg->background[0], cfg->background[1], cfg->background[2], 0.f};
     cudaMemcpy(e->bg3, bg, sizeof(bg), cudaMemcpyHostToDevice);
     cudaMemset(e->overflow, 0, 4);
-    cudaMemset(e->bk_cursor, 0, (size_t)e->bk_max_buckets * GSEVT_BK_CURSOR_STRIDE * 4);
+    cudaMemset(e->bk_cursor, 0, (size_t)e->bk_max_buckets * GSEVT_BK_SUB * GSEVT_BK_CURSOR_STRIDE * 4);
     cudaMemset(e->ranges, 0, (size_t)e->bk_max_buckets * sizeof(uint2));
     cudaMemset(e->hit_base, 0, (size_t)e->bk_max_buckets * 4);
     cudaMemset(e->loss_partials, 0, ((size_t)e->loss_nb * 3 + 2) * 8);
@@ -809,21 +815,21 @@ static void set_bucket_grid(GsevtEngine* e, int shift) {
     e->bk_nb = e->bk_nbx * e->bk_nby;
 }
 
-// pose_setup + projection + a count-only run of the bucket scatter at the current state: keys per bucket of the
-// current bucket grid -> counts[2 * bk_nb] (host).  Leaves the cursors at zero.
+// pose_setup + projection + a count-only run of the bucket scatter at the current state: keys per (bucket, sub-segment)
+// of the current bucket grid -> counts[2 * bk_nb * GSEVT_BK_SUB] (host).  Leaves the cursors at zero.
 static int probe_buckets(GsevtEngine* e, cudaStream_t s, std::vector<uint32_t>& counts) {
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // pending iterations first (see gsevt_engine_status)
     SETF(level_done, (int)0);
     launch_pose_setup(e->ctl, e->views, e->bg3, e->cfg.znear, e->cfg.zfar, s);
     launch_preprocess_map(premap_args(e), s);
-    const int nbt = 2 * e->bk_nb;
-    counts.assign((size_t)(nbt > 0 ? nbt : 1), 0u);
-    if (nbt <= 0) return 0;
+    const int nc = 2 * e->bk_nb * GSEVT_BK_SUB;
+    counts.assign((size_t)(nc > 0 ? nc : 1), 0u);
+    if (nc <= 0) return 0;
     launch_bucket_scatter(bucket_args(e), true, s);
-    launch_bucket_counts(nbt, e->bk_cursor, e->bk_counts, s);
-    GSEVT_CUDA_OK(cudaMemsetAsync(e->bk_cursor, 0, (size_t)nbt * GSEVT_BK_CURSOR_STRIDE * 4, s));
+    launch_bucket_counts(nc, e->bk_cursor, e->bk_counts, s);
+    GSEVT_CUDA_OK(cudaMemsetAsync(e->bk_cursor, 0, (size_t)nc * GSEVT_BK_CURSOR_STRIDE * 4, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // counts is pageable host memory: wait first (see gsevt_engine_status)
-    GSEVT_CUDA_OK(cudaMemcpyAsync(counts.data(), e->bk_counts, (size_t)nbt * 4, cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(counts.data(), e->bk_counts, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -883,12 +889,17 @@ static int size_level(GsevtEngine* e, cudaStream_t s, bool rebalance, int slack_
     const int strip_tiles = (e->strip_y1 - e->strip_y0) * L.gx;
     int shift = e->bin_mode == 1 ? 0 : (e->bin_mode == 2 ? 1 : (strip_tiles >= 256 ? 1 : 0));
     uint32_t maxc = 0;
+    std::vector<uint32_t> keys_of;   // keys per bucket (all sub-segments)
     for (;;) {
         set_bucket_grid(e, shift);
         if ((rc = probe_buckets(e, s, counts))) return rc;   // with this engine's strip in force
         maxc = 0;
-        for (int b = 0; b < 2 * e->bk_nb; b++) maxc = counts[b] > maxc ? counts[b] : maxc;
-        if (shift == 1 && e->bin_mode == 0 && maxc + maxc / 8 + 64 > GSEVT_BK_SMEM_MAX_ELEMS) { shift = 0; continue; }
+        keys_of.assign((size_t)(2 * e->bk_nb > 0 ? 2 * e->bk_nb : 1), 0u);
+        for (int b = 0; b < 2 * e->bk_nb; b++) {
+            for (int j = 0; j < GSEVT_BK_SUB; j++) keys_of[b] += counts[(size_t)b * GSEVT_BK_SUB + j];
+            maxc = keys_of[b] > maxc ? keys_of[b] : maxc;
+        }
+        if (shift == 1 && e->bin_mode == 0 && maxc + maxc / 4 + 512 > GSEVT_BK_SMEM_MAX_ELEMS) { shift = 0; continue; }
         break;
     }
     const int nbt = 2 * e->bk_nb;
@@ -896,19 +907,28 @@ static int size_level(GsevtEngine* e, cudaStream_t s, bool rebalance, int slack_
     long long total = 0;
     uint32_t maxcap = 8;
     for (int b = 0; b < nbt; b++) {
-        long long c = (long long)counts[b] + counts[b] / 16 + 64;
-        if (slack_div > 0) c += counts[b] / slack_div;
-        c = (c + 7) / 8 * 8;
+        // every sub-segment gets the largest sub-count of its bucket + slack (the sub-segments fill evenly: they are picked
+        // by the scatter CTA's index)
+        uint32_t mj = 0;
+        for (int j = 0; j < GSEVT_BK_SUB; j++) mj = counts[(size_t)b * GSEVT_BK_SUB + j] > mj ? counts[(size_t)b * GSEVT_BK_SUB + j] : mj;
+        long long c = (long long)mj + mj / 16 + 24;
+        if (slack_div > 0) c += mj / slack_div;
+        c = (c + 7) / 8 * 8 * GSEVT_BK_SUB;
         start[b] = (uint32_t)total; cap[b] = (uint32_t)c;
         total += c;
         if ((uint32_t)c > maxcap) maxcap = (uint32_t)c;
     }
     if ((rc = ensure_capacity(e, total, shift, s))) return rc;
     e->bk_total = total;
-    e->bk_smem_elems = (int)(maxcap < GSEVT_BK_SMEM_MAX_ELEMS ? maxcap : GSEVT_BK_SMEM_MAX_ELEMS);
+    bucket_sort_smem((int)maxcap, &e->bk_smem_elems, &e->bk_smem_bins, &e->bk_smem_bytes);
+    // sort CTAs take the buckets largest first (longest-processing-time order: the tail of the launch is made of small buckets)
+    std::vector<uint32_t> order((size_t)(nbt > 0 ? nbt : 1), 0u);
+    for (int b = 0; b < nbt; b++) order[b] = (uint32_t)b;
+    std::stable_sort(order.begin(), order.begin() + (nbt > 0 ? nbt : 0), [&](uint32_t x, uint32_t y) { return keys_of[x] > keys_of[y]; });
     if (nbt > 0) {
         GSEVT_CUDA_OK(cudaMemcpyAsync(e->bk_start, start.data(), (size_t)nbt * 4, cudaMemcpyHostToDevice, s));
         GSEVT_CUDA_OK(cudaMemcpyAsync(e->bk_cap, cap.data(), (size_t)nbt * 4, cudaMemcpyHostToDevice, s));
+        GSEVT_CUDA_OK(cudaMemcpyAsync(e->bk_order, order.data(), (size_t)nbt * 4, cudaMemcpyHostToDevice, s));
     }
     GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // start / cap are stack-frame vectors
@@ -958,7 +978,7 @@ GSEVT_API int gsevt_engine_iterate(GsevtEngine* e, int32_t n, void* stream) {
     // (buffers that grow destroy the graph: quiesce())
     if (can_graph && (e->graph == nullptr || e->graph_level != e->cur_level || e->graph_stream != s ||
                       e->graph_y0 != e->strip_y0 || e->graph_y1 != e->strip_y1 ||
-                      e->graph_shift != e->bk_shift || e->graph_smem != e->bk_smem_elems)) {
+                      e->graph_shift != e->bk_shift || e->graph_smem != (int)e->bk_smem_bytes)) {
         if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
         cudaGraph_t g = nullptr;
         GSEVT_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
@@ -969,7 +989,7 @@ GSEVT_API int gsevt_engine_iterate(GsevtEngine* e, int32_t n, void* stream) {
         cudaGraphDestroy(g);
         if (err != cudaSuccess) { e->graph = nullptr; set_error("graph instantiate failed: %s", cudaGetErrorString(err)); return GSEVT_ECUDA; }
         e->graph_level = e->cur_level; e->graph_stream = s;
-        e->graph_y0 = e->strip_y0; e->graph_y1 = e->strip_y1; e->graph_shift = e->bk_shift; e->graph_smem = e->bk_smem_elems;
+        e->graph_y0 = e->strip_y0; e->graph_y1 = e->strip_y1; e->graph_shift = e->bk_shift; e->graph_smem = (int)e->bk_smem_bytes;
     }
     for (int i = 0; i < n; i++) {
         if (can_graph) GSEVT_CUDA_OK(cudaGraphLaunch(e->graph, s));

@@ -137,8 +137,10 @@ void launch_identify_ranges(const uint64_t* keys, uint2* ranges, int ntiles_tota
                             int cap, cudaStream_t s);
 uint32_t higher_msb(uint32_t n);
 // ---- engine binning (bucketbin.cu) -------------------------------------------------------------------
-#define GSEVT_BK_CURSOR_STRIDE 64        // u32 words between two bucket cursors: 256 B, one L2 atomic unit each
-#define GSEVT_BK_SMEM_MAX_ELEMS 14080    // keys per shared-memory buffer of bucket_sort (2 buffers x 8 B: 220 KB)
+#define GSEVT_BK_CURSOR_STRIDE 64        // u32 words between two cursors: 256 B, one L2 atomic unit each
+#define GSEVT_BK_SUB 8                   // sub-segments (cursors) per bucket: the L2 serialises atomics on one address
+#define GSEVT_BK_SMEM_MAX_ELEMS 16000    // largest bucket bucket_sort handles in shared memory: 10 B per key + 4 B per bin
+#define GSEVT_BK_SMEM_MAX_BYTES (16000 * 10 + 16384 * 4)
 struct BucketArgs {
     int P;
     int s;                      // log2 of the bucket edge in tiles: 0 or 1
@@ -147,19 +149,22 @@ struct BucketArgs {
     int gx, gy, tiles_global;   // tile grid of the level; ranges / hit_base are indexed view * tiles_global + ty * gx + tx
     const uint32_t* rect_raw;   // [2P] projection output, index order
     const uint32_t* depth_raw;  // [2P]
-    uint32_t* cursor;           // [2 nb][GSEVT_BK_CURSOR_STRIDE] keys taken per bucket; zero between iterations
+    uint32_t* cursor;           // [2 nb][GSEVT_BK_SUB][GSEVT_BK_CURSOR_STRIDE] keys taken per sub-segment; zero between iterations
     const uint32_t* bk_start;   // [2 nb] first key slot of the bucket's segment (multiple of 8)
-    const uint32_t* bk_cap;     // [2 nb] slots of the segment (multiple of 8)
-    uint64_t* keys;             // bucket segments: (depth bits << 32) | Gaussian index
+    const uint32_t* bk_cap;     // [2 nb] slots of the segment: GSEVT_BK_SUB sub-segments of cap / GSEVT_BK_SUB (a multiple of 8) each
+    uint64_t* keys;             // bucket segments: depth bits << 32 | Gaussian index << 4 | cover mask of the bucket's 2 x 2 tiles
     uint64_t* keys2;            // second buffer for buckets sorted in global memory
     uint32_t* vals;             // per-tile lists: tile k of bucket b at (start[b] << 2s) + k * cap[b]
     uint2* ranges;              // out: (begin, end) into vals per tile
     uint32_t* hit_base;         // out: first word of the tile's hit-mask rows (blend.cu)
-    int smem_elems;             // keys per shared-memory buffer of this launch (multiple of 8)
+    const uint32_t* bk_order;   // [2 nb] buckets in the order the sort CTAs take them (largest first), or NULL
+    int smem_elems, smem_bins;  // shared memory of a sort CTA: keys it can hold, depth bins (see bucket_sort_smem)
+    size_t smem_bytes;
     int* overflow;
     const EngineCtl* ctl;
 };
 int bucket_sort_configure();
+void bucket_sort_smem(int max_keys, int* elems, int* bins, size_t* bytes);
 void launch_bucket_scatter(const BucketArgs& a, bool count_only, cudaStream_t s);
 void launch_bucket_sort(const BucketArgs& a, cudaStream_t s);
 void launch_bucket_counts(int n, const uint32_t* cursor, uint32_t* out, cudaStream_t s);
