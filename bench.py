@@ -275,6 +275,24 @@ def run_ours(args):
     default_wl = (args.gaussians, d["W"], d["H"], args.camera, args.seed) == (1_000_000, 640, 480, "robot", 1)
     roof, stage_table = roofline(stages, wl, args.gaussians, d["W"] * d["H"], clocks, default_wl, tiles=((d["W"] + 15) // 16) * ((d["H"] + 15) // 16))
 
+    # ---- parity of the benchmarked path at the benchmarked size (outside every timed region) ------------
+    # the fused engine against the reference-shaped autograd loop through the drop-in operator — the path the parity tests
+    # pin to the live reference build: loss, 12 gradients, gray images, and the per-tile lists / ranges bit for bit
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        from gaussian_splatting.scene.gaussian_model import GaussianModel
+        from gsevt import selfcheck
+        gm = synth.load_map_into(GaussianModel(3, device=dev), raw, device=dev)
+        eng.begin_frame(d["delta_tau"], ef.sign_pyramid, ef.unsign_pyramid)
+        parity = selfcheck.engine_vs_operator(eng, gm, (R0, T0, w0, v0), d["delta_tau"], ef.builder.level_view(ef.sign_pyramid, 0))
+        parity["gates"] = {"loss_rel": 1e-5, "grad_rel_max": 1e-3, "gray_rel_max": 1e-4, "lists_bit_identical": True}
+        parity["ok"] = bool(parity["loss_rel"] < 1e-5 and parity["grad_rel_max"] < 1e-3 and parity.get("gray_rel_max", 0.0) < 1e-4
+                            and parity.get("lists_bit_identical", True))
+        parity["against"] = ("RenderFrame -> torch.norm -> backward through this repo's drop-in diff_gaussian_rasterization "
+                             "(pinned to the live reference build by tests/test_gpu_parity.py), same state, same event frame")
+        del gm
+        assert parity["ok"], f"benchmarked path disagrees with the operator path: {parity}"
+
     out = None
     if rank == 0:
         value = world * args.steps / (ms_max / 1e3)
@@ -299,6 +317,7 @@ def run_ours(args):
                                  "geom_compact, geom_bwd, engine_update) x steps: all this library's own, no library kernels, one CUDA "
                                  "graph launch per iteration",
             "roofline": roof,
+            "parity_check": parity,
             "stages_ms": stage_table,
             "workload_counters": wl,
         }
@@ -516,7 +535,7 @@ def run_reference(args):
 
     warm = max(args.warmup, 3)
     it.new_frame(arrays[0])
-    it.iterate(0, min(warm, args.iters_per_frame), opt_vel=True)
+    it.iterate(0, min(warm, args.iters_per_frame), opt_vel=True, want_grads=False)
     torch.cuda.synchronize()
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     sampler.start()
@@ -531,7 +550,7 @@ def run_reference(args):
         ta = time.perf_counter()
         it.new_frame(arrays[j % len(arrays)])
         tb = time.perf_counter()
-        ls, _ = it.iterate(0, n, opt_vel=True)
+        ls, _ = it.iterate(0, n, opt_vel=True, want_grads=False)   # statement for statement tracker.py:176-222, nothing added
         torch.cuda.synchronize()
         tc = time.perf_counter()
         t_frames += tb - ta
@@ -583,6 +602,7 @@ def main():
     ap.add_argument("--iters-per-frame", type=int, default=50)
     ap.add_argument("--cpu-sample-gaussians", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the engine-vs-operator-path check after the timed region")
     ap.add_argument("--mode", choices=["hypotheses", "tilesplit"], default="hypotheses",
                     help="hypotheses: one independent hypothesis per GPU (weak scaling, the driver's line); "
                          "tilesplit: one hypothesis, screen tiles split over the GPUs (strong scaling, configs[4])")

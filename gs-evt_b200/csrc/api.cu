@@ -1038,11 +1038,14 @@ GSEVT_API int gsevt_engine_losses(GsevtEngine* e, float* out, int32_t capacity, 
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // see gsevt_engine_status
     GSEVT_CUDA_OK(cudaMemcpyAsync(&n, (char*)e->ctl + offsetof(EngineCtl, n_losses), 4, cudaMemcpyDeviceToHost, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));
-    int c = n < capacity ? n : capacity;
-    if (c > GSEVT_MAX_LOSSES) c = GSEVT_MAX_LOSSES;
+    // the device keeps a ring of the last GSEVT_MAX_LOSSES losses: return the most recent min(n, capacity, ring) in order
+    int have = n < GSEVT_MAX_LOSSES ? n : GSEVT_MAX_LOSSES;
+    int c = have < capacity ? have : capacity;
     if (c > 0) {
-        GSEVT_CUDA_OK(cudaMemcpyAsync(out, (char*)e->ctl + offsetof(EngineCtl, losses), (size_t)c * 4, cudaMemcpyDeviceToHost, s));
+        static thread_local float ring[GSEVT_MAX_LOSSES];
+        GSEVT_CUDA_OK(cudaMemcpyAsync(ring, (char*)e->ctl + offsetof(EngineCtl, losses), sizeof(ring), cudaMemcpyDeviceToHost, s));
         GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+        for (int i = 0; i < c; i++) out[i] = ring[(n - c + i) % GSEVT_MAX_LOSSES];
     }
     return c;
 }

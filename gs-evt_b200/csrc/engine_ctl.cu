@@ -185,7 +185,9 @@ __device__ void engine_control(EngineCtl* c, float* losses, const float* s_g, in
         return;
     }
     c->iters_executed += 1;
-    if (c->n_losses < GSEVT_MAX_LOSSES) losses[c->n_losses] = c->last_loss;
+    // the history is a ring of the last GSEVT_MAX_LOSSES losses: the stopping rule only ever looks at the last 11
+    // (tracker.py:65-76), so levels of any length keep honouring it
+    losses[c->n_losses % GSEVT_MAX_LOSSES] = c->last_loss;
     c->n_losses += 1;
 
     // learning rates (tracker.py:161-170,188-202)
@@ -207,9 +209,10 @@ __device__ void engine_control(EngineCtl* c, float* losses, const float* s_g, in
     }
     // check_convergence (tracker.py:65-76): mean |diff| of the last 11 losses, in double
     bool converged = false;
-    if (c->n_losses > 10 && c->n_losses <= GSEVT_MAX_LOSSES) {
+    if (c->n_losses > 10) {
         double acc = 0.0;
-        for (int i = c->n_losses - 10; i < c->n_losses; i++) acc += fabs((double)losses[i] - (double)losses[i - 1]);
+        for (int i = c->n_losses - 10; i < c->n_losses; i++)
+            acc += fabs((double)losses[i % GSEVT_MAX_LOSSES] - (double)losses[(i - 1) % GSEVT_MAX_LOSSES]);
         converged = (acc / 10.0) < (double)c->converged_threshold;
     }
     // update_vwRT / update_pose (camera.py:129-155)

@@ -8,7 +8,8 @@
 //      row pass  s = k0*x[-4]; s = fma(x[i], k[i], s)            (left to right)
 //      col pass  t = k4*x[0];  t = fma(x[+j] + x[-j], k[4+j], t) (j = 1..4)
 //   E3 cv2.normalize(L2) == x * float(1 / sqrt(sum_fp64 x^2))
-//   E4 abs, and nearest-neighbour pyramid frame[::2^l, ::2^l]
+//   E4 abs, and the INTER_NEAREST pyramid (source index floor(dst * src_size / dst_size): frame[::2^l, ::2^l] for
+//      sizes divisible by 2^l)
 // Loss (frame.py:86-92 + tracker.py:93-103): d = gray_next - gray_last, u = d/||d||,
 //   L = ||u - E||  (signed)  or  || |u| - |E| ||  (unsigned).  One pass computes
 //   Sd2 = sum d^2, S2 = sum d*E (or |d||E|), SE2 = sum E^2 in double; then
@@ -25,7 +26,11 @@ __global__ void event_accumulate_kernel(const int16_t* __restrict__ x, const int
                                         int* __restrict__ oob) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int xi = x[i], yi = y[i];
+    // numpy indexing (event.py:118-120: frame[y, x] += ...): a negative index in [-size, -1] counts from the end, anything
+    // else raises IndexError — here: flagged and dropped
+    int xi = x[i], yi = y[i];
+    if (xi < 0) xi += W;
+    if (yi < 0) yi += H;
     if (xi < 0 || xi >= W || yi < 0 || yi >= H) {
         if (oob) *oob = 1;
         return;
@@ -119,15 +124,22 @@ __global__ void event_finish_kernel(const float* __restrict__ in, const double* 
     const float scale = s_scale;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= W * H) return;
-    const int y = i / W, x = i - y * W;
     const float v = __fmul_rn(in[i], scale);
-    size_t off = 0;
-    for (int l = 0; l < levels; l++) {
-        const int Wl = W >> l, Hl = H >> l, st = 1 << l;
-        if ((x & (st - 1)) == 0 && (y & (st - 1)) == 0 && (x >> l) < Wl && (y >> l) < Hl) {
-            const size_t o = off + (size_t)(y >> l) * Wl + (x >> l);
-            sign_out[o] = v;
-            unsign_out[o] = fabsf(v);
+    sign_out[i] = v;
+    unsign_out[i] = fabsf(v);
+    // pyramid levels: cv2.resize(frame, (int(W s), int(H s)), INTER_NEAREST) (tracker.py:87-88) samples source column
+    // min(floor(dx * (1 / (Wl / W))), W - 1) — evaluated in double like OpenCV's resizeNN; this is dx << l whenever the size
+    // is a multiple of 2^l, and drifts from it otherwise (e.g. 346 x 260 at level 2)
+    size_t off = (size_t)W * H;
+    for (int l = 1; l < levels; l++) {
+        const int Wl = W >> l, Hl = H >> l;
+        if (i < Wl * Hl) {
+            const int dy = i / Wl, dx = i - dy * Wl;
+            const double ifx = 1.0 / ((double)Wl / (double)W), ify = 1.0 / ((double)Hl / (double)H);
+            const int sx = min((int)floor((double)dx * ifx), W - 1), sy = min((int)floor((double)dy * ify), H - 1);
+            const float u = __fmul_rn(in[(size_t)sy * W + sx], scale);
+            sign_out[off + i] = u;
+            unsign_out[off + i] = fabsf(u);
         }
         off += (size_t)Wl * Hl;
     }

@@ -31,7 +31,25 @@ class PackedMap:
         dev = xyz.device
         f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
         xyz, scales, rotations, opacities, shs = f(xyz), f(scales), f(rotations), f(opacities), f(shs)
+        # the C ABI takes raw pointers: every shape is checked here.  An isotropic map stores one scale per Gaussian
+        # (PLY with scale_0 only); the reference expands it with get_scaling.repeat(1, 3) in the renderer
+        # (gaussian_renderer/__init__.py:283-286)
+        if xyz.dim() != 2 or xyz.shape[1] != 3:
+            raise ValueError(f"xyz must be (P, 3), got {tuple(xyz.shape)}")
         P = xyz.shape[0]
+        if scales.dim() == 2 and scales.shape == (P, 1):
+            scales = scales.repeat(1, 3).contiguous()
+        if tuple(scales.shape) != (P, 3):
+            raise ValueError(f"scales must be (P, 3) or (P, 1), got {tuple(scales.shape)}")
+        if tuple(rotations.shape) != (P, 4):
+            raise ValueError(f"rotations must be (P, 4), got {tuple(rotations.shape)}")
+        if opacities.numel() != P:
+            raise ValueError(f"opacities must hold P values, got {tuple(opacities.shape)}")
+        opacities = opacities.reshape(P).contiguous()
+        if shs.dim() != 3 or shs.shape[0] != P or shs.shape[2] != 3 or not 1 <= shs.shape[1] <= 16:
+            raise ValueError(f"shs must be (P, M <= 16, 3), got {tuple(shs.shape)}")
+        if (int(sh_degree) + 1) ** 2 > shs.shape[1]:
+            raise ValueError(f"sh_degree {sh_degree} needs {(int(sh_degree) + 1) ** 2} coefficients, shs has {shs.shape[1]}")
         if shs.shape[1] != 16:
             full = torch.zeros((P, 16, 3), dtype=torch.float32, device=dev)
             full[:, :shs.shape[1]] = shs
@@ -80,6 +98,7 @@ class TrackingEngine:
         self.map = packed_map
         self.device = packed_map.device
         self.width, self.height, self.levels = int(width), int(height), int(levels)
+        self.fx, self.fy = float(fx), float(fy)
         cfg = _lib.GsevtEngineConfig()
         cfg.width, cfg.height, cfg.levels = int(width), int(height), int(levels)
         cfg.fx, cfg.fy, cfg.znear, cfg.zfar = float(fx), float(fy), float(znear), float(zfar)

@@ -10,12 +10,20 @@ class Logger:
         self.logger = logging.getLogger(name)
         self.logger.setLevel(level)
         self.logger.propagate = False
-        if not self.logger.handlers:
-            fmt = logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s")
+        fmt = logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s")
+        if not any(type(h) is logging.StreamHandler for h in self.logger.handlers):
             ch = logging.StreamHandler()
             ch.setFormatter(fmt)
             self.logger.addHandler(ch)
-            if log_file:
+        if log_file:
+            # logging.getLogger(name) is a process-wide singleton: a second Logger of the same name with another file
+            # (a second Tracker with its own save_path) must get its own file handler, and the old file is released
+            want = os.path.abspath(log_file)
+            for h in [h for h in self.logger.handlers if isinstance(h, logging.FileHandler)]:
+                if os.path.abspath(h.baseFilename) != want:
+                    self.logger.removeHandler(h)
+                    h.close()
+            if not any(isinstance(h, logging.FileHandler) for h in self.logger.handlers):
                 os.makedirs(os.path.dirname(log_file) or ".", exist_ok=True)
                 fh = logging.FileHandler(log_file)
                 fh.setFormatter(fmt)

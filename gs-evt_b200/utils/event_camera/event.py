@@ -129,7 +129,9 @@ class EventFrame:
     def integrate_events(self, event_array):
         b = _builder(self.img_width, self.img_height, self.intrinsic, self.distortion_factors, self.device)
         _, x, y, p = event_array.columns()
-        if x.size and (x.min() < 0 or y.min() < 0 or x.max() >= self.img_width or y.max() >= self.img_height):
+        # numpy indexing of the reference (frame[y, x] += ..., event.py:118-120): [-size, size) is legal, negative indices
+        # count from the end (the scatter kernel wraps them the same way); anything else is an IndexError
+        if x.size and (x.min() < -self.img_width or y.min() < -self.img_height or x.max() >= self.img_width or y.max() >= self.img_height):
             raise IndexError("event coordinates outside the frame")
         self.sign_pyramid, self.unsign_pyramid = b.build(x, y, p)
         self.builder = b

@@ -63,10 +63,18 @@ class Tracker:
         return bool(np.mean(np.abs(np.diff(losses[-11:]))) < threshold)
 
     def image_pyramid(self, image):
-        """Nearest-neighbour pyramid: cv2.resize(INTER_NEAREST) by 0.5**l == image[..., ::2**l, ::2**l]."""
+        """Nearest-neighbour pyramid: cv2.resize(image, (int(w s), int(h s)), INTER_NEAREST) with s = 0.5**l, i.e.
+        source index min(floor(dst / (dst_size / src_size)), src_size - 1) — image[..., ::2**l, ::2**l] when the size is a
+        multiple of 2**l."""
         _, h, w = image.shape
-        return [image[:, ::2 ** l, ::2 ** l][:, :int(h * 0.5 ** l), :int(w * 0.5 ** l)].contiguous()
-                for l in range(self.pyramid_lvl)]
+        out = []
+        for l in range(self.pyramid_lvl):
+            hl, wl = int(h * 0.5 ** l), int(w * 0.5 ** l)
+            iy = np.minimum(np.floor(np.arange(hl) * (1.0 / (hl / h))).astype(np.int64), h - 1)
+            ix = np.minimum(np.floor(np.arange(wl) * (1.0 / (wl / w))).astype(np.int64), w - 1)
+            iy, ix = torch.from_numpy(iy).to(image.device), torch.from_numpy(ix).to(image.device)
+            out.append(image[:, iy][:, :, ix].contiguous())
+        return out
 
     def tracking_loss(self, delta_Ir, delta_Ie, mask=None, huber=False):
         residual = delta_Ir * mask - delta_Ie if mask is not None else delta_Ir - delta_Ie

@@ -162,9 +162,10 @@ GSEVT_API int64_t gsevt_raster_img_offset(const char* name, int32_t width, int32
  * (the reference raises ValueError), GSEVT_ENOMEM when n > capacity.  Host pointers; no device involved. */
 GSEVT_API int64_t gsevt_parse_int_table(const char* text, size_t len, int64_t* out, size_t capacity, int32_t threads);
 /* E0: counts[y*W+x] += p ? +1 : -1  (integer scatter-add, bit-exact).  x,y int16, p uint8, device
- * pointers; counts int32[H*W] must be zeroed by the caller (or pass zero_first != 0).  Events with
- * coordinates outside the frame are an error in the reference (IndexError); here they set the
- * returned device flag *oob (may be NULL) and are dropped. */
+ * pointers; counts int32[H*W] must be zeroed by the caller (or pass zero_first != 0).  Coordinates follow
+ * numpy's indexing in the reference's loop (frame[y, x] += ..., event.py:118-120): [-size, -1] counts from the
+ * end; anything outside [-size, size) is an IndexError in the reference; here it sets the returned device
+ * flag *oob (may be NULL) and the event is dropped. */
 GSEVT_API int gsevt_event_accumulate(const int16_t* x, const int16_t* y, const uint8_t* p, int32_t n,
                            int32_t width, int32_t height, int32_t* counts, int32_t zero_first,
                            int32_t* oob, void* stream);
@@ -251,7 +252,9 @@ typedef struct GsevtEngineStatus {
 } GsevtEngineStatus;
 /* Copies the status block to the host (synchronises `stream`). */
 GSEVT_API int gsevt_engine_status(GsevtEngine* e, GsevtEngineStatus* out, void* stream);
-/* Per-iteration loss history of the current level (device->host, synchronises). Returns count. */
+/* Per-iteration loss history of the current level (device->host, synchronises): the most recent
+ * min(iterations, capacity, 1024) losses in order (the device keeps a ring of 1024; the stopping rule of
+ * utils/tracker.py:65-76 only needs the last 11).  Returns the count. */
 GSEVT_API int gsevt_engine_losses(GsevtEngine* e, float* out, int32_t capacity, void* stream);
 /* End-of-frame velocity blend (Camera.cal_weighted_velocity, camera.py:157-181) and the constant
  * velocity prediction (Camera.const_vel_model, camera.py:183-201), on the device. */
@@ -280,16 +283,16 @@ GSEVT_API const char* gsevt_engine_stage_name(int32_t i);
 GSEVT_API int gsevt_engine_profile(GsevtEngine* e, int32_t n_iters, float* stage_ms, void* stream);
 /* Data-dependent work of the most recent iteration: out8 = {visible Gaussians view 0, view 1, tile
  * instances view 0, view 1, sum of n_contrib view 0, view 1, (view, Gaussian) pairs with a non-zero blend
- * gradient, slots sorted}.  Synchronises. */
+ * gradient, key slots of the bucket segments (bucket keys + slack)}.  Synchronises. */
 GSEVT_API int gsevt_engine_workload(GsevtEngine* e, int64_t* out8, void* stream);
 /* Number of kernels the engine launches per executed iteration (for bench.py's gpu_launches). */
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e);
-/* Which binning path the engine uses from the next begin_level / eval on: 0 = automatic (tile binning by counting up
- * to 2048 tiles per view and strip, emit + radix sort above), 1 = counting, 2 = radix.  Both produce the reference's
- * per-tile lists (rasterizer_impl.cu:70-138) bit for bit; the knob exists so that tests can compare them.
- * Returns GSEVT_EINVAL when `mode` 1 is asked for a grid the counting kernels cannot hold. */
+/* Bucket shape of the engine's binning from the next begin_level / eval / resume on: 0 = automatic (buckets of 2 x 2
+ * tiles while a bucket sorts in shared memory, one tile per bucket on coarse pyramid levels / very dense maps), 1 = one
+ * tile per bucket, 2 = 2 x 2 tiles per bucket.  All produce the reference's per-tile lists (rasterizer_impl.cu:70-138) bit
+ * for bit; the knob exists so that tests can compare them. */
 GSEVT_API int gsevt_engine_set_binning(GsevtEngine* e, int32_t mode);
-/* After gsevt_engine_poll_done() returned 2: the tile-instance list outgrew the slots sorted per iteration
+/* After gsevt_engine_poll_done() returned 2: a bucket of the binning outgrew its key segment
  * (the pose moved a lot inside one level).  The device voided that iteration (state untouched) and paused the
  * level; this call re-counts at the current pose, grows the buffers and clears the pause.  Synchronises. */
 GSEVT_API int gsevt_engine_resume(GsevtEngine* e, void* stream);

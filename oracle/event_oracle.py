@@ -145,11 +145,16 @@ def event_frame(x, y, p, W, H, K, D):
 
 
 def pyramid(frame, levels=3):
-    """P — cv2.resize(INTER_NEAREST) by 0.5**l == frame[::2**l, ::2**l] (no re-normalisation)."""
+    """P — cv2.resize(frame, (int(W s), int(H s)), INTER_NEAREST), s = 0.5**l (tracker.py:87-88; no re-normalisation).
+    OpenCV's resizeNN samples source index min(floor(dst * (1 / (dst_size / src_size))), src_size - 1) in double: this is
+    frame[::2**l, ::2**l] when the size is a multiple of 2**l and drifts from it otherwise (checked against cv2 itself in
+    tests/test_event_oracle.py on 346 x 260)."""
     f = np.asarray(frame)
     H, W = f.shape[-2:]
     out = []
     for l in range(levels):
-        s = 2 ** l
-        out.append(np.ascontiguousarray(f[..., ::s, ::s][..., :int(H * 0.5 ** l), :int(W * 0.5 ** l)]))
+        Hl, Wl = int(H * 0.5 ** l), int(W * 0.5 ** l)
+        iy = np.minimum(np.floor(np.arange(Hl) * (1.0 / (Hl / H))).astype(np.int64), H - 1)
+        ix = np.minimum(np.floor(np.arange(Wl) * (1.0 / (Wl / W))).astype(np.int64), W - 1)
+        out.append(np.ascontiguousarray(f[..., iy, :][..., ix]))
     return out

@@ -29,8 +29,25 @@ def available():
             and any(f.startswith("_C") and f.endswith(".so") for f in os.listdir(ext)))
 
 
-def activate():
-    """Puts the reference (and the shims for munch/plyfile/natsort/open3d/rosbag) first on sys.path."""
+def _load_by_path(name, path):
+    """Imports the package at `path` under `name` without touching sys.path."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(path, "__init__.py"), submodule_search_locations=[path])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def activate(operator="reference"):
+    """Puts the reference (and the shims for munch/plyfile/natsort/open3d/rosbag) first on sys.path.
+
+    operator="reference": the reference's own extension (oracle/_ref/ext).
+    operator="ours": INTEGRATION.md section 1(b) — the reference's UNMODIFIED Python pipeline with only the rasteriser
+    operator replaced: `diff_gaussian_rasterization` resolves to this repo's drop-in package (and its ctypes binding
+    `gsevt`), loaded by file path because the product's source root must stay off sys.path here (its `utils` package would
+    shadow the reference's namespace package of the same name)."""
+    product = os.path.join(os.path.dirname(HERE), "gs-evt_b200")
     for name in ("utils", "gaussian_splatting", "diff_gaussian_rasterization"):
         m = sys.modules.get(name)
         if m is not None:
@@ -39,18 +56,26 @@ def activate():
                 raise RuntimeError(f"module '{name}' was already imported from the product; run the reference in its own process")
     # The reference's `utils` has no __init__.py (namespace package): any regular `utils` package anywhere
     # on sys.path would shadow it, so the product's source root must not be importable in this process.
-    product = os.path.join(os.path.dirname(HERE), "gs-evt_b200")
     sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != product]
-    for p in (os.path.join(REF, "ext"), os.path.join(REF, "pipeline"), os.path.join(HERE, "shims")):
+    paths = [os.path.join(REF, "pipeline"), os.path.join(HERE, "shims")]
+    if operator == "reference":
+        paths.insert(0, os.path.join(REF, "ext"))
+    for p in paths:
         if p in sys.path:
             sys.path.remove(p)
         sys.path.insert(0, p)
+    if operator == "ours":
+        _load_by_path("gsevt", os.path.join(product, "gsevt"))
+        _load_by_path("diff_gaussian_rasterization", os.path.join(product, "diff_gaussian_rasterization"))
+    elif operator != "reference":
+        raise ValueError(operator)
     import importlib
     for name in ("utils.tracker", "utils.event_camera.event", "gaussian_splatting", "diff_gaussian_rasterization"):
         m = importlib.import_module(name)
         src = os.path.abspath(getattr(m, "__file__", None) or list(m.__path__)[0])
-        if not src.startswith(os.path.abspath(REF)):
-            raise RuntimeError(f"'{name}' resolved to {src}, not to the reference under {REF}")
+        want = os.path.abspath(product if (operator == "ours" and name == "diff_gaussian_rasterization") else REF)
+        if not src.startswith(want):
+            raise RuntimeError(f"'{name}' resolved to {src}, not under {want}")
 
 
 def make_config(d, save_path, map_path="", events_path="", device="cuda"):
@@ -135,10 +160,11 @@ class RefIterations:
         self.unsign_pyr = t.image_pyramid(eFrame.unsign_delta_Ie)
         self.eFrame = eFrame
 
-    def iterate(self, lvl, n, opt_vel=True, k0=0, step=True):
+    def iterate(self, lvl, n, opt_vel=True, k0=0, step=True, want_grads=True):
         """n iterations of tracker.py:176-222 at level `lvl` (fine stage when opt_vel).  k0 = optim_iter -
         start_vel_opt_iter of the first one (drives the LR cross-fade).  Returns per-iteration losses and
-        the gradients [rho, theta, v, w] of each iteration."""
+        the gradients [rho, theta, v, w] of each iteration (want_grads=False: no gradient read-back — the reference's loop has
+        none, so the timed reference arm of bench.py runs without it)."""
         from utils.render_camera.frame import RenderFrame
         torch, vp, cfg, t = self.torch, self.viewpoint, self.config["Optimizer"], self.tracker
         fraction_num = t.max_optim_iter / 2
@@ -168,12 +194,14 @@ class RefIterations:
                 loss = t.tracking_loss(rFrame.sign_delta_Ir, self.sign_pyr[lvl], huber=False)
             loss.backward()
             losses.append(loss.item())
-            z = torch.zeros(3, device="cuda")
-            gg = [vp.cam_trans_delta.grad, vp.cam_rot_delta.grad, vp.cam_v_delta.grad, vp.cam_w_delta.grad]
-            grads.append(torch.cat([z if x is None else x.detach().reshape(-1) for x in gg]).cpu().numpy())
+            if want_grads:
+                z = torch.zeros(3, device="cuda")
+                gg = [vp.cam_trans_delta.grad, vp.cam_rot_delta.grad, vp.cam_v_delta.grad, vp.cam_w_delta.grad]
+                grads.append(torch.cat([z if x is None else x.detach().reshape(-1) for x in gg]).cpu().numpy())
             with torch.no_grad():
                 if step:
                     self.optimizer.step()
+                    t.check_convergence(losses, t.converged_threshold)   # tracker.py:217 (its result is not acted on here)
                     if not opt_vel:
                         vp.update_pose()
                     else:
@@ -246,8 +274,10 @@ def _main():
     ap.add_argument("mode", choices=["iterations", "tracker"])
     ap.add_argument("--inp", required=True)
     ap.add_argument("--out", required=True)
+    ap.add_argument("--operator", choices=["reference", "ours"], default="reference",
+                    help="ours: the reference's Python with this repo's drop-in diff_gaussian_rasterization (INTEGRATION.md 1b)")
     a = ap.parse_args()
-    activate()
+    activate(a.operator)
     z = np.load(a.inp, allow_pickle=True)
     desc = z["desc"].item()
     raw = {k: z[k] for k in ("xyz", "scaling", "rotation", "opacity", "f_dc", "f_rest")}

@@ -119,3 +119,23 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M) or "liboracle" in txt or "oracle/" in txt:
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_reference_install_is_not_tracked():
+    """oracle/_ref holds the unmodified reference (built by oracle/build_ref.sh): it travels to the GPU box with the snapshot
+    but must never enter the history."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, ".git")):
+        pytest.skip("not a git checkout")
+    out = subprocess.run(["git", "ls-files", "oracle/_ref", "baseline/_ref"], cwd=root, capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "", out.stdout
+
+
+def test_logger_follows_the_log_file(tmp_path):
+    """Two Trackers in one process with different save paths: each gets its own tracking_log.log."""
+    from utils.auxiliary import Logger
+    a, b = tmp_path / "a" / "tracking_log.log", tmp_path / "b" / "tracking_log.log"
+    Logger(name="T_gsevt_test", log_file=str(a)).info("first")
+    Logger(name="T_gsevt_test", log_file=str(b)).info("second")
+    assert "first" in a.read_text() and "second" in b.read_text() and "second" not in a.read_text()

@@ -41,6 +41,27 @@ def test_stages_match_opencv_bit_exactly(W, Hh, n, seed):
         assert H.bits_equal(lvl, ref)
 
 
+@pytest.mark.parametrize("W,Hh", [(346, 260), (641, 479), (100, 75), (640, 480)])
+def test_pyramid_is_opencv_nearest_on_sizes_not_divisible_by_four(W, Hh):
+    """cv2.resize(INTER_NEAREST) samples floor(dst * src / dst_size): on 346 x 260 (DAVIS346) level 2 is NOT frame[::4, ::4]."""
+    import cv2
+    rng = np.random.default_rng(W)
+    f = rng.normal(size=(Hh, W)).astype(np.float32)
+    for l, lvl in enumerate(eo.pyramid(f)):
+        ref = cv2.resize(f, (int(W * 0.5 ** l), int(Hh * 0.5 ** l)), interpolation=cv2.INTER_NEAREST)
+        assert lvl.shape == ref.shape and H.bits_equal(lvl, ref), (W, Hh, l)
+    if (W, Hh) == (346, 260):
+        assert not np.array_equal(eo.pyramid(f)[2], f[::4, ::4][:65, :86])   # the case the old restatement got wrong
+
+
+def test_negative_event_coordinates_wrap_like_numpy():
+    """frame[y, x] += polarity with numpy indexing (reference event.py:118-120): -1 is the last row / column."""
+    cnt = eo.accumulate([-1, 3, -96], [-1, -64, 2], [1, 0, 1], 96, 64)
+    assert cnt[63, 95] == 1 and cnt[0, 3] == -1 and cnt[2, 0] == 1 and np.abs(cnt).sum() == 3
+    with pytest.raises(IndexError):
+        eo.accumulate([-97], [0], [1], 96, 64)
+
+
 def test_empty_and_degenerate_frames():
     K = np.array([50.0, 0, 48, 0, 50.0, 32, 0, 0, 1.0]).reshape(3, 3)
     D = np.zeros(5)

@@ -255,6 +255,34 @@ def test_event_frame_bit_exact(built, cuda_dev, n, seed):
         assert H.bits_equal(b.level_view(sign, 0)[0].cpu().numpy(), c), "against OpenCV itself"
 
 
+def test_event_frame_odd_sizes_and_negative_coordinates(built, cuda_dev):
+    """346 x 260 (DAVIS346): the pyramid is OpenCV's nearest mapping floor(dst * src / dst_size), not frame[::4, ::4];
+    negative coordinates wrap like numpy's indexing in the reference's scatter loop (event.py:118-120)."""
+    import cv2
+    from gsevt import synth
+    from gsevt.engine import EventFrameBuilder
+    from oracle import event_oracle as eo
+    W, Hh = 346, 260
+    K = np.array([250.0, 0, 173, 0, 250.0, 130, 0, 0, 1.0]).reshape(3, 3)
+    dist = [-0.05, 0.01, 0.0, 0.0, 0.0]
+    ev = synth.random_events(20000, W, Hh, 0, 50000, seed=5)
+    x, y, p = ev[:, 1].astype(np.int16), ev[:, 2].astype(np.int16), ev[:, 3].astype(np.uint8)
+    x[:500] -= W      # numpy: frame[y, x - W] is frame[y, x]
+    y[200:900] -= Hh
+    b = EventFrameBuilder(W, Hh, K, dist, levels=3, device=cuda_dev)
+    sign, unsign = b.build(x, y, p)
+    assert int(b.oob.item()) == 0
+    assert np.array_equal(b.counts.cpu().numpy(), eo.accumulate(x, y, p, W, Hh)), "E0 with wrapped coordinates"
+    s_ref, _ = eo.event_frame(x, y, p, W, Hh, K, dist)
+    for l in range(3):
+        got = b.level_view(sign, l)[0].cpu().numpy()
+        ref = cv2.resize(s_ref[0], (int(W * 0.5 ** l), int(Hh * 0.5 ** l)), interpolation=cv2.INTER_NEAREST)
+        assert got.shape == ref.shape and H.bits_equal(got, ref), f"level {l} against cv2.resize"
+    # out of numpy's range: flagged and dropped
+    b.build(np.array([-W - 1], np.int16), np.array([0], np.int16), np.array([1], np.uint8))
+    assert int(b.oob.item()) == 1
+
+
 def test_event_frame_python_surface(built, cuda_dev):
     """utils.event_camera.event mirrors the reference API: load_events_from_txt + EventFrame."""
     import tempfile
@@ -386,6 +414,58 @@ def test_engine_optimisation_loop_control(built, cuda_dev):
     assert st.start_vel_opt_iter == 10 and st.optim_iter == 11 and st.iters_executed == 12 and st.opt_vel == 1
 
 
+def test_engine_levels_longer_than_the_loss_ring(built, cuda_dev):
+    """max_optim_iter above 510 makes a level longer than the 1024-entry loss history: the history is a ring,
+    the stopping rule keeps working on its last 11 entries, losses() returns the most recent 1024 in order."""
+    sc = H.small_scene(3000, 160, 120, seed=6)
+    eng, *_ = _engine(sc, cuda_dev, levels=1, max_optim_iter=700, converged_threshold=0.0)
+    st = eng.run_level(0, opt_vel=False, chunk=64)        # never converges: 701 coarse iterations
+    assert st.iters_executed == 701 and st.level_done == 1
+    assert eng.losses().shape[0] == 701
+    st = eng.run_level(0, opt_vel=True, chunk=64)
+    assert st.iters_executed == 701
+    eng2, *_ = _engine(sc, cuda_dev, levels=1, max_optim_iter=1500, converged_threshold=0.0)
+    st = eng2.run_level(0, opt_vel=False, chunk=128)
+    L = eng2.losses()
+    assert st.iters_executed == 1501 and L.shape[0] == 1024 and np.all(np.isfinite(L)) and L[-1] == np.float32(st.last_loss)
+    # a threshold that only trips once the optimisation has settled, far beyond 1024 iterations... or never: either way the
+    # rule must still be evaluated (it used to be switched off for good after 1024 losses)
+    eng3, *_ = _engine(sc, cuda_dev, levels=1, max_optim_iter=3000, converged_threshold=1e9)
+    eng3.begin_level(0, False)
+    eng3.iterate(5)
+    eng3.stream.synchronize()
+    assert eng3.status().iters_executed == 5 and eng3.poll_done() == 0   # fewer than 11 losses: cannot converge yet
+    eng3.iterate(20)
+    eng3.stream.synchronize()
+    assert eng3.status().opt_vel == 1 and eng3.poll_done() == 1
+
+
+def test_packed_map_accepts_isotropic_scales_and_rejects_bad_shapes(built, cuda_dev):
+    """An isotropic map stores one scale per Gaussian; the reference expands it with repeat(1, 3)
+    (gaussian_renderer/__init__.py:283-286).  The engine path must do the same, and must not hand mis-shaped tensors to C."""
+    import torch
+    from gsevt.engine import PackedMap, TrackingEngine
+    sc = H.small_scene(2000, 160, 120, seed=7)
+    A = {k: torch.from_numpy(v).to(cuda_dev) for k, v in sc["act"].items()}
+    iso = A["scales"][:, :1].contiguous()
+    eng0, b, sign, _ = _engine(sc, cuda_dev, levels=1)     # (only for the event frame)
+    engs = []
+    for scales in (iso, iso.repeat(1, 3).contiguous()):
+        pm = PackedMap(A["xyz"], scales, A["rotations"], A["opacities"], A["shs"], 3)
+        eng = TrackingEngine(pm, sc["W"], sc["H"], sc["fx"], sc["fy"], levels=1)
+        eng.set_state(sc["R"], sc["T"], sc["w"], sc["v"])
+        eng.begin_frame(sc["dtau"], sign, None)
+        engs.append(eng.eval(0, True))
+    # identical maps: the loss is bit-identical, the gradients agree to the order-of-accumulation noise of float atomics
+    assert engs[0][0] == engs[1][0] and H.rel_max(engs[0][1], engs[1][1]) < 1e-4
+    with pytest.raises(ValueError):
+        PackedMap(A["xyz"], A["scales"][:, :2].contiguous(), A["rotations"], A["opacities"], A["shs"], 3)
+    with pytest.raises(ValueError):
+        PackedMap(A["xyz"], A["scales"], A["rotations"][:, :3].contiguous(), A["opacities"], A["shs"], 3)
+    with pytest.raises(ValueError):
+        PackedMap(A["xyz"], A["scales"], A["rotations"], A["opacities"][:-1], A["shs"], 3)
+
+
 def test_engine_pauses_and_resumes_when_the_instance_list_outgrows_its_slots(built, cuda_dev):
     """The per-iteration sort runs over a fixed number of slots (CUDA graph).  When the pose moves so far inside
     a level that the live instances no longer fit, the device must void that iteration, pause, and continue after
@@ -510,6 +590,156 @@ def test_engine_iterations_match_reference_pipeline(built, cuda_dev, tmp_path):
         "1 mm / 0.05 deg over the %d iterations the reference reproduces itself" % n_together
     assert dT_or[-1] < max(1e-3, 3 * dT_rr.max()), "final translation vs the reference's own spread"
     assert dR_or[-1] < max(0.05, 3 * dR_rr.max()), "final rotation vs the reference's own spread"
+
+
+def test_reference_pipeline_with_only_the_operator_swapped(built, cuda_dev, tmp_path):
+    """the reference's UNMODIFIED Python (Camera, RenderFrame, render2, Tracker.tracking_loss, autograd,
+    Adam, update_vwRT — oracle/_ref/pipeline) with `diff_gaussian_rasterization` resolving to this repo's drop-in package,
+    next to the same pipeline with the reference's own extension: same losses, same 12 gradients, same optimiser steps."""
+    import subprocess
+    import sys
+    from oracle import ref_runner
+    from gsevt import synth
+    if not ref_runner.available():
+        pytest.skip("oracle/_ref did not travel with this snapshot")
+    sc = H.small_scene(60000, 640, 480, seed=3, ang_scale=20.0)
+    D = synth.DESK
+    ev = synth.random_events(30000, 640, 480, 0, 50000, seed=8)
+    # (fine stage only: with an uninformative random event frame the coarse, unsigned stage is Adam stepping along the sign of
+    # gradient noise, where two runs of the reference itself part ways — profiles/r1_traj_separation_v11.log)
+    plan = [(0, 1, 10)]
+    desc = dict(W=640, H=480, fx=sc["fx"], fy=sc["fy"], cx=320.0, cy=240.0, dist=list(D["dist"]), R=sc["R"].ravel().tolist(),
+                T=sc["T"].tolist(), angular_vel=sc["w"].tolist(), linear_vel=sc["v"].tolist(), lr=dict(D["lr"]), plan=plan, step=True)
+    inp = str(tmp_path / "in.npz")
+    np.savez(inp, desc=np.array(desc, dtype=object), events=ev, **sc["raw"])
+    outs = {}
+    for op in ("reference", "ours"):
+        out = str(tmp_path / f"out_{op}.npz")
+        subprocess.run([sys.executable, os.path.join(H.ROOT, "oracle", "ref_runner.py"), "iterations", "--inp", inp, "--out", out,
+                        "--operator", op], check=True, timeout=900)
+        outs[op] = np.load(out)
+    r, o = outs["reference"], outs["ours"]
+    assert H.bits_equal(r["sign_Ie"], o["sign_Ie"])                       # same host-side event frame (reference code both times)
+    for lvl, opt_vel, n in plan:
+        lr_, lo = r[f"loss_L{lvl}_{opt_vel}"], o[f"loss_L{lvl}_{opt_vel}"]
+        gr, go = r[f"grad_L{lvl}_{opt_vel}"], o[f"grad_L{lvl}_{opt_vel}"]
+        assert lr_.shape == lo.shape == (n,)
+        if (lvl, opt_vel) == plan[0][:2]:
+            # first iteration of the run: identical state -> the operator alone is compared
+            assert abs(lr_[0] - lo[0]) < 1e-5 * abs(lr_[0])
+            assert H.rel_max(go[0], gr[0]) < TOL_GRAD
+        # the following iterations run from each side's own updated state (Adam's first steps are lr * sign(g))
+        assert np.abs(lr_ - lo).max() < 2e-3
+    assert np.abs(r["states"][0] - o["states"][0]).max() < 2e-6            # one optimiser step from identical state
+    assert np.abs(r["T"] - o["T"]).max() < 1e-3                            # 1 mm after 10 steps
+    dR = r["R"].astype(np.float64) @ o["R"].astype(np.float64).T
+    assert np.degrees(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1))) < 0.05
+
+
+# ---- BASELINE.json sizes against the live reference ---------------------------------------------------------
+def _reference_objective(ref, sc, dev, E, signed=True):
+    """The reference's tracking objective with the reference's own extension: two rasterisations (last / next view), gray,
+    normalised difference, norm against E, backward to the 12 pose / velocity gradients [rho, theta, v, w]
+    (frame.py:61-94, tracker.py:93-103, dgr/diff_gaussian_rasterization/__init__.py:163-169).  Returns the loss, the
+    gradients, the gray images and per view (sorted keys, sorted ids, ranges) from the reference's work buffers."""
+    import torch
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    act = sc["act"]
+    P, W, Hh = act["xyz"].shape[0], sc["views"][0]["W"], sc["views"][0]["H"]
+    leaf = {k: t(act[k]) for k in ("xyz", "opacities", "scales", "rotations", "shs")}
+    pose = {k: torch.zeros(3, device=dev, requires_grad=True) for k in ("theta", "rho", "w", "v")}
+    bg = torch.zeros(3, device=dev)
+    grays, bins = [], []
+    for view in sc["views"]:
+        r = ref.GaussianRasterizer(H.settings(ref, view, bg, dev))
+        color, radii, depth, opacity, n_touched = r(means3D=leaf["xyz"], means2D=torch.zeros((P, 3), device=dev), opacities=leaf["opacities"],
+                                                    shs=leaf["shs"], scales=leaf["scales"], rotations=leaf["rotations"],
+                                                    theta=pose["theta"], rho=pose["rho"], w=pose["w"], v=pose["v"])
+        sb = tuple(color.grad_fn.saved_tensors)
+        rg = H.parse_ref_geom(sb[-3].cpu().numpy(), P)
+        N = int(rg["tiles_touched"].astype(np.int64).sum())
+        rb = H.parse_ref_binning(sb[-2].cpu().numpy(), N)
+        ri = H.parse_ref_img(sb[-1].cpu().numpy(), W, Hh)
+        bins.append((rb["point_list_keys"], rb["point_list"], ri["ranges"]))
+        wgt = torch.tensor([0.2989, 0.5870, 0.1140], device=dev).view(3, 1, 1)
+        grays.append((color * wgt).sum(dim=0))
+    d = grays[1] - grays[0]
+    u = d / torch.norm(d, p=2)
+    loss = torch.norm(u - E) if signed else torch.norm(torch.abs(u) - torch.abs(E))
+    loss.backward()
+    g = torch.cat([pose["rho"].grad.view(-1), pose["theta"].grad.view(-1), pose["v"].grad.view(-1), pose["w"].grad.view(-1)]).cpu().numpy()
+    return float(loss), g, [x.detach().cpu().numpy() for x in grays], bins
+
+
+@pytest.mark.parametrize("P,W,Hh", [(1_000_000, 640, 480), (1_000_000, 1280, 720), (300_000, 1280, 720)])
+def test_engine_matches_live_reference_at_baseline_sizes(built, cuda_dev, P, W, Hh):
+    """The BENCHMARKED path (fused engine) at BASELINE.json's sizes against the unmodified reference extension on identical
+    tensors: sorted keys / per-tile lists / tile ranges bit-exact (1200 and 3600 tiles per view: 11- and 12-bit tile keys in
+    the reference's radix sort), gray images 1e-4, loss 1e-5, the 12 gradients 1e-3 — per component, with a floor at 5 % of
+    the largest one, and relative to the largest one."""
+    from gsevt import selfcheck
+    ref = load_reference_extension()
+    if ref is None:
+        pytest.skip("oracle/_ref (the reference build) did not travel with this snapshot")
+    sc = H.small_scene(P, W, Hh, seed=1)
+    eng, b, sign, _ = _engine(sc, cuda_dev)
+    E = b.level_view(sign, 0)
+    L, g = eng.eval(0, True)
+    gl, gn = eng.gray_images(0)
+    Lr, gr, grays, bins = _reference_objective(ref, sc, cuda_dev, E[0])
+    tiles = ((W + 15) // 16) * ((Hh + 15) // 16)
+    for view in (0, 1):
+        keys, ids, ranges = eng.binning(view, 0)
+        rk, rl, rr = bins[view]
+        assert keys.size == rk.size > P and ranges.shape == (tiles, 2)
+        assert np.array_equal(keys, rk), f"sorted keys, view {view}"
+        assert np.array_equal(ids, rl), f"per-tile lists, view {view}"
+        assert np.array_equal(ranges, rr), f"tile ranges, view {view}"
+    assert H.rel_max(gl.cpu().numpy(), grays[0]) < TOL_IMG and H.rel_max(gn.cpu().numpy(), grays[1]) < TOL_IMG
+    assert abs(L - Lr) < 1e-5 * abs(Lr)
+    print("gradients vs reference at %d / %dx%d: rel to max %.2e, per component (floor 5%%) %.2e" % (P, W, Hh, H.rel_max(g, gr), selfcheck.rel_comp(g, gr)))
+    assert H.rel_max(g, gr) < TOL_GRAD and selfcheck.rel_comp(g, gr) < TOL_GRAD
+    # and the other bucket shape gives the same lists (2 x 2 buckets by default at these sizes)
+    eng.set_binning(1)
+    L1, _ = eng.eval(0, True)
+    assert L1 == L and all(np.array_equal(a, c) for a, c in zip(eng.binning(1, 0), bins[1]))
+
+
+def test_operator_matches_live_reference_at_1280x720(built, cuda_dev):
+    """The drop-in operator at 3600 tiles (the reference sorts 44-bit keys there): buffers byte for byte."""
+    ref = load_reference_extension()
+    if ref is None:
+        pytest.skip("oracle/_ref (the reference build) did not travel with this snapshot")
+    P, W, Hh = 300_000, 1280, 720
+    sc = H.small_scene(P, W, Hh, seed=2)
+    dcol = np.random.default_rng(5).normal(size=(3, Hh, W)).astype(np.float32)
+    view = sc["views"][1]
+    a = H.run_operator(_ours(), sc, view, cuda_dev, dcol=dcol, want_map_grads=False)
+    r = H.run_operator(ref, sc, view, cuda_dev, dcol=dcol, want_map_grads=False)
+    rg = H.parse_ref_geom(r["saved"][-3].cpu().numpy(), P)
+    N = int(rg["tiles_touched"].astype(np.int64).sum())
+    rb, ri = H.parse_ref_binning(r["saved"][-2].cpu().numpy(), N), H.parse_ref_img(r["saved"][-1].cpu().numpy(), W, Hh)
+    ob, oi = H.parse_our_binning(built, a["saved"][-2], N), H.parse_our_img(built, a["saved"][-1], W, Hh)
+    assert np.array_equal(a["radii"], r["radii"])
+    assert np.array_equal(ob["point_list_keys"], rb["point_list_keys"]) and np.array_equal(ob["point_list"], rb["point_list"])
+    assert np.array_equal(oi["ranges"], ri["ranges"]) and np.array_equal(oi["n_contrib"], ri["n_contrib"])
+    assert H.rel_max(a["color"], r["color"]) < TOL_IMG and H.rel_max(a["pose"], r["pose"]) < TOL_GRAD
+
+
+def test_bench_parity_check_runs_on_the_engine_path(built, cuda_dev):
+    """gsevt.selfcheck (what bench.py prints as `parity_check`): engine vs the autograd loop through the drop-in operator."""
+    import torch
+    from gsevt import selfcheck, synth
+    from gaussian_splatting.scene.gaussian_model import GaussianModel
+    sc = H.small_scene(100000, 640, 480, seed=3)
+    eng, b, sign, _ = _engine(sc, cuda_dev)
+    gm = synth.load_map_into(GaussianModel(3, device=cuda_dev), sc["raw"], device=cuda_dev)
+    for level, signed in ((0, True), (1, True), (2, False)):
+        r = selfcheck.engine_vs_operator(eng, gm, (sc["R"], sc["T"], sc["w"], sc["v"]), sc["dtau"], b.level_view(sign, level), level, signed)
+        assert r["lists_bit_identical"] and r["instances_compared"] > 100000
+        assert r["loss_rel"] < 1e-5 and r["gray_rel_max"] < TOL_IMG
+        if signed:
+            assert r["grad_rel_max"] < TOL_GRAD and r["grad_rel_comp"] < TOL_GRAD
 
 
 # ---- full-size, size-independent properties (BASELINE.json sizes) ----------------------------------------
