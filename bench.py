@@ -280,17 +280,18 @@ def run_ours(args):
     # pin to the live reference build: loss, 12 gradients, gray images, and the per-tile lists / ranges bit for bit
     parity = None
     if rank == 0 and not args.no_parity_check:
-        from gaussian_splatting.scene.gaussian_model import GaussianModel
         from gsevt import selfcheck
-        gm = synth.load_map_into(GaussianModel(3, device=dev), raw, device=dev)
+        A = {k: torch.from_numpy(v).to(dev) for k, v in act.items()}
         eng.begin_frame(d["delta_tau"], ef.sign_pyramid, ef.unsign_pyramid)
-        parity = selfcheck.engine_vs_operator(eng, gm, (R0, T0, w0, v0), d["delta_tau"], ef.builder.level_view(ef.sign_pyramid, 0))
-        parity["gates"] = {"loss_rel": 1e-5, "grad_rel_max": 1e-3, "gray_rel_max": 1e-4, "lists_bit_identical": True}
-        parity["ok"] = bool(parity["loss_rel"] < 1e-5 and parity["grad_rel_max"] < 1e-3 and parity.get("gray_rel_max", 0.0) < 1e-4
-                            and parity.get("lists_bit_identical", True))
-        parity["against"] = ("RenderFrame -> torch.norm -> backward through this repo's drop-in diff_gaussian_rasterization "
-                             "(pinned to the live reference build by tests/test_gpu_parity.py), same state, same event frame")
-        del gm
+        parity = selfcheck.engine_vs_operator(eng, A, (R0, T0, w0, v0), ef.builder.level_view(ef.sign_pyramid, 0)[0])
+        parity["gates"] = {"loss_rel": 1e-5, "grad_rel_max": 1e-3, "gray_rel_max": 1e-4, "lists_bit_identical": True,
+                           "n_contrib_final_T_bit_identical": True}
+        parity["ok"] = bool(parity["loss_rel"] < 1e-5 and parity["grad_rel_max"] < 1e-3 and parity["gray_rel_max"] < 1e-4
+                            and parity["lists_bit_identical"] and parity["n_contrib_final_T_bit_identical"])
+        parity["against"] = ("two rasterisations + torch loss + backward through this repo's drop-in diff_gaussian_rasterization (pinned to "
+                             "the live reference build by tests/test_gpu_parity.py), same state, same event frame, the camera blocks "
+                             "of the engine's pose kernel")
+        del A
         assert parity["ok"], f"benchmarked path disagrees with the operator path: {parity}"
 
     out = None

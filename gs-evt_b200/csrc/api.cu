@@ -416,6 +416,7 @@ struct GsevtEngine {
     long long bk_alloc = 0, vals_alloc = 0;   // allocated key slots (each buffer) / list slots
     int bk_smem_elems = 8, bk_smem_bins = 2048; size_t bk_smem_bytes = 0;   // shared memory of a sort CTA (bucket_sort_smem)
     uint32_t* bk_order = nullptr;        // [bk_max_buckets] buckets by decreasing key count: the order the sort CTAs take them
+    uint32_t* tile_order = nullptr;      // [bk_max_buckets] tiles of the strip in the same order: what the blend CTAs take
     uint32_t* vals = nullptr;            // per-tile lists: Gaussian index per slot
     uint32_t* hit_base = nullptr;        // [2 tiles]
     uint2* ranges = nullptr;
@@ -565,7 +566,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     f.tile_y0 = e->strip_y0; f.tile_rows = e->strip_y1 - e->strip_y0;
     f.ranges = e->ranges; f.point_list = e->vals; f.rec = e->rec; f.view_stride_gauss = (size_t)P;
     f.views = e->views; f.final_T = e->final_T; f.n_contrib = e->n_contrib; f.out_color = e->gray; f.ctl = e->ctl;
-    f.hitmask = e->hitmask; f.hitmask_stride = e->hitmask_stride; f.hit_base = e->hit_base;
+    f.hitmask = e->hitmask; f.hitmask_stride = e->hitmask_stride; f.hit_base = e->hit_base; f.tile_order = e->tile_order;
     launch_blend_fwd_gray(f, s);
     mark();
     const float* evf = e->ev_sign + L.ev_offset;
@@ -583,7 +584,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     b.tile_y0 = e->strip_y0; b.tile_rows = e->strip_y1 - e->strip_y0;
     b.ranges = e->ranges; b.point_list = e->vals; b.rec = e->rec; b.view_stride_gauss = (size_t)P; b.views = e->views;
     b.final_T = e->final_T; b.n_contrib = e->n_contrib; b.gray = e->gray; b.event_frame = evf; b.ctl = e->ctl;
-    b.grad8 = e->grad8; b.hitmask = e->hitmask; b.hitmask_stride = e->hitmask_stride; b.hit_base = e->hit_base;
+    b.grad8 = e->grad8; b.hitmask = e->hitmask; b.hitmask_stride = e->hitmask_stride; b.hit_base = e->hit_base; b.tile_order = e->tile_order;
     launch_blend_bwd_gray(b, s);
     mark();
     GeomBwdArgs q;
@@ -708,6 +709,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->bk_cap, (size_t)e->bk_max_buckets);
     rc |= dev_alloc(e, &e->bk_counts, (size_t)e->bk_max_buckets * GSEVT_BK_SUB);
     rc |= dev_alloc(e, &e->bk_order, (size_t)e->bk_max_buckets);
+    rc |= dev_alloc(e, &e->tile_order, (size_t)e->bk_max_buckets);
     rc |= dev_alloc(e, &e->ranges, (size_t)e->bk_max_buckets);
     rc |= dev_alloc(e, &e->hit_base, (size_t)e->bk_max_buckets);
     if (bucket_sort_configure()) { set_error("bucket_sort: cannot reserve %d bytes of shared memory", GSEVT_BK_SMEM_MAX_BYTES); gsevt_engine_destroy(e); return GSEVT_ECUDA; }
@@ -930,6 +932,23 @@ static int size_level(GsevtEngine* e, cudaStream_t s, bool rebalance, int slack_
         GSEVT_CUDA_OK(cudaMemcpyAsync(e->bk_cap, cap.data(), (size_t)nbt * 4, cudaMemcpyHostToDevice, s));
         GSEVT_CUDA_OK(cudaMemcpyAsync(e->bk_order, order.data(), (size_t)nbt * 4, cudaMemcpyHostToDevice, s));
     }
+    // the blend CTAs take the strip's tiles in the same order (a tile's list is at most its bucket's keys)
+    std::vector<uint32_t> torder;
+    {
+        const int tiles = L.gx * L.gy, edge = 1 << shift;
+        torder.reserve((size_t)2 * strip_tiles + 1);
+        for (int i = 0; i < nbt; i++) {
+            const int b = (int)order[i], view = b >= e->bk_nb ? 1 : 0, bl = b - view * e->bk_nb;
+            const int by = bl / e->bk_nbx, bx = bl - by * e->bk_nbx;
+            for (int ky = 0; ky < edge; ky++)
+                for (int kx = 0; kx < edge; kx++) {
+                    const int tx = (bx << shift) + kx, ty = ((by + e->bk_by_origin) << shift) + ky;
+                    if (tx < L.gx && ty >= e->strip_y0 && ty < e->strip_y1) torder.push_back((uint32_t)(view * tiles + ty * L.gx + tx));
+                }
+        }
+        if ((int)torder.size() != 2 * strip_tiles) { set_error("internal: tile order covers %zu of %d tiles", torder.size(), 2 * strip_tiles); return GSEVT_ESTATE; }
+        if (!torder.empty()) GSEVT_CUDA_OK(cudaMemcpyAsync(e->tile_order, torder.data(), torder.size() * 4, cudaMemcpyHostToDevice, s));
+    }
     GSEVT_CUDA_OK(cudaMemsetAsync(e->overflow, 0, 4, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // start / cap are stack-frame vectors
     return 0;
@@ -1104,6 +1123,38 @@ GSEVT_API int gsevt_engine_render_delta(GsevtEngine* e, int32_t level, float* de
     if (gray_last) GSEVT_CUDA_OK(cudaMemcpyAsync(gray_last, e->gray, hw * 4, cudaMemcpyDeviceToDevice, s));
     if (gray_next) GSEVT_CUDA_OK(cudaMemcpyAsync(gray_next, e->gray + hw, hw * 4, cudaMemcpyDeviceToDevice, s));
     (void)delta_out;
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_image_state(GsevtEngine* e, int32_t level, float* final_T, uint32_t* n_contrib, void* stream) {
+    // Per-pixel blending state of the most recent evaluation / iteration at `level`, both views: [2][H*W] each.
+    if (!e || level != e->cur_level) { set_error("image_state: run gsevt_engine_eval at this level first"); return GSEVT_ESTATE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const LevelInfo& L = e->lv[level];
+    const size_t hw = (size_t)L.W * L.H;
+    if (final_T) GSEVT_CUDA_OK(cudaMemcpyAsync(final_T, e->final_T, 2 * hw * 4, cudaMemcpyDeviceToDevice, s));
+    if (n_contrib) GSEVT_CUDA_OK(cudaMemcpyAsync(n_contrib, e->n_contrib, 2 * hw * 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+GSEVT_API int gsevt_engine_view_params(GsevtEngine* e, int32_t view, float* out73, void* stream) {
+    // The camera block the kernels of the most recent evaluation / iteration used for `view` (0 last, 1 next), computed on
+    // the device by the pose kernel: viewmatrix[16], projmatrix[16] (column-major), campos[3], tanfovx, tanfovy,
+    // projmatrix_raw[0], [5], [11], vel_transform[16], vel_transform_inv[16], delta_time.  Host output.
+    if (!e || view < 0 || view > 1 || !out73) { set_error("bad arguments"); return GSEVT_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    ViewParams h;
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    GSEVT_CUDA_OK(cudaMemcpyAsync(&h, e->views + view, sizeof(h), cudaMemcpyDeviceToHost, s));
+    GSEVT_CUDA_OK(cudaStreamSynchronize(s));
+    float* o = out73;
+    memcpy(o, h.view, 64); o += 16;
+    memcpy(o, h.proj, 64); o += 16;
+    memcpy(o, h.campos, 12); o += 3;
+    *o++ = h.tanfovx; *o++ = h.tanfovy; *o++ = h.proj_a; *o++ = h.proj_b; *o++ = h.proj_e;
+    memcpy(o, h.vel, 64); o += 16;
+    memcpy(o, h.vel_inv, 64); o += 16;
+    *o++ = h.delta_time;
     return 0;
 }
 

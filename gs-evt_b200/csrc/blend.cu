@@ -87,14 +87,24 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     __shared__ float4 s_rgb[OPERATOR ? 2 : 1][OPERATOR ? 256 : 1];
     __shared__ int s_id[OPERATOR ? 2 : 1][OPERATOR ? 256 : 1];
 
-    const int view = blockIdx.z;
     const int tiles = a.grid_x * a.grid_y;
     const int HW = a.W * a.H;
-    const int tile_y = blockIdx.y + a.tile_y0;
-    const int tile_lin = view * tiles + tile_y * a.grid_x + blockIdx.x;
+    // engine: CTA i takes tile tile_order[i] — the tiles of the largest buckets first, so that the tail of the launch is
+    // made of short lists; operator: the 3-D grid is the tile grid
+    int view, tile_x, tile_y;
+    if (a.tile_order) {
+        const uint32_t t = a.tile_order[blockIdx.x];
+        view = (int)(t / (uint32_t)tiles);
+        const int tt = (int)(t - (uint32_t)view * (uint32_t)tiles);
+        tile_y = tt / a.grid_x;
+        tile_x = tt - tile_y * a.grid_x;
+    } else {
+        view = blockIdx.z; tile_x = blockIdx.x; tile_y = blockIdx.y + a.tile_y0;
+    }
+    const int tile_lin = view * tiles + tile_y * a.grid_x + tile_x;
     const uint2 range = a.ranges[tile_lin];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bx = blockIdx.x * GSEVT_TILE + (warp & 1) * 8, by = tile_y * GSEVT_TILE + (warp >> 1) * 4;
+    const int bx = tile_x * GSEVT_TILE + (warp & 1) * 8, by = tile_y * GSEVT_TILE + (warp >> 1) * 4;
     const int pixx = bx + (lane & 7), pixy = by + (lane >> 3);
     const float cxw = (float)bx + 3.5f, cyw = (float)by + 1.5f;
     const float pxf = (float)pixx, pyf = (float)pixy;
@@ -228,6 +238,7 @@ void launch_blend_fwd_rgb(const BlendFwdArgs& a, cudaStream_t s) {
 void launch_blend_fwd_gray(const BlendFwdArgs& a, cudaStream_t s) {
     dim3 grid(a.grid_x, a.tile_rows, a.nviews);
     if (a.tile_rows <= 0) return;
+    if (a.tile_order) grid = dim3((unsigned)(a.grid_x * a.tile_rows * a.nviews), 1, 1);
     blend_fwd_kernel<1, false><<<grid, 256, 0, s>>>(a);
 }
 
@@ -275,14 +286,24 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     __shared__ uint32_t s_id[2][256];
     __shared__ uint32_t s_max[8];
 
-    const int view = blockIdx.z;
     const int tiles = a.grid_x * a.grid_y;
     const int HW = a.W * a.H;
-    const int tile_y = blockIdx.y + a.tile_y0;
-    const int tile_lin = view * tiles + tile_y * a.grid_x + blockIdx.x;
+    // engine: CTA i takes tile tile_order[i] — the tiles of the largest buckets first, so that the tail of the launch is
+    // made of short lists; operator: the 3-D grid is the tile grid
+    int view, tile_x, tile_y;
+    if (a.tile_order) {
+        const uint32_t t = a.tile_order[blockIdx.x];
+        view = (int)(t / (uint32_t)tiles);
+        const int tt = (int)(t - (uint32_t)view * (uint32_t)tiles);
+        tile_y = tt / a.grid_x;
+        tile_x = tt - tile_y * a.grid_x;
+    } else {
+        view = blockIdx.z; tile_x = blockIdx.x; tile_y = blockIdx.y + a.tile_y0;
+    }
+    const int tile_lin = view * tiles + tile_y * a.grid_x + tile_x;
     const uint2 range = a.ranges[tile_lin];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bx = blockIdx.x * GSEVT_TILE + (warp & 1) * 8, by = tile_y * GSEVT_TILE + (warp >> 1) * 4;
+    const int bx = tile_x * GSEVT_TILE + (warp & 1) * 8, by = tile_y * GSEVT_TILE + (warp >> 1) * 4;
     const int pixx = bx + (lane & 7), pixy = by + (lane >> 3);
     const float cxw = (float)bx + 3.5f, cyw = (float)by + 1.5f;
     const float pxf = (float)pixx, pyf = (float)pixy;
@@ -370,8 +391,18 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
         const float4 r1 = s_r1[buf][j];
         const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
         const float power = eval_power(dx, dy, r0.z, r0.w, r1.x);
-        const float G = expf(power);
-        const float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
+        // Operator: the reference's arithmetic (expf, IEEE reciprocal).  Engine: the backward is gated at 1e-3, not bit for
+        // bit, so exp is ex2.approx (2 instructions instead of 11) and 1 / (1 - alpha) is rcp.approx (instead of 14) — except
+        // within 1e-6 of the alpha >= 1/255 test, which must fall as it did in the forward pass: a pair blended there and
+        // skipped here would leave T off by (1 - alpha) for everything in front of it.
+        float G = OPERATOR ? expf(power) : __expf(power);
+        float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
+        if constexpr (!OPERATOR) {
+            if (fabsf(alpha - kAlphaMin) < 1e-6f) {
+                G = expf(power);
+                alpha = fminf(0.99f, __fmul_rn(r1.y, G));
+            }
+        }
         const bool skip = pos >= last_contributor || power > 0.0f || alpha < kAlphaMin;   // !inside => last_contributor == 0
         if constexpr (OPERATOR) {
             if (__all_sync(0xffffffffu, skip)) return;
@@ -380,7 +411,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
 #pragma unroll
         for (int k = 0; k < KR; k++) v[k] = 0.0f;
         if (!skip) {
-            const float inv = __frcp_rn(1.0f - alpha);
+            const float inv = OPERATOR ? __frcp_rn(1.0f - alpha) : __fdividef(1.0f, 1.0f - alpha);
             T = T * inv;
             const float w = alpha * T;
             float dL_dalpha = 0.0f;
@@ -483,6 +514,7 @@ void launch_blend_bwd_rgb(const BlendBwdArgs& a, cudaStream_t s) {
 void launch_blend_bwd_gray(const BlendBwdArgs& a, cudaStream_t s) {
     dim3 grid(a.grid_x, a.tile_rows, a.nviews);
     if (a.tile_rows <= 0) return;
+    if (a.tile_order) grid = dim3((unsigned)(a.grid_x * a.tile_rows * a.nviews), 1, 1);
     blend_bwd_kernel<1, false><<<grid, 256, 0, s>>>(a);
 }
 

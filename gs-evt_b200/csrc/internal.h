@@ -192,6 +192,7 @@ struct BlendFwdArgs {
     uint32_t* hitmask;           // engine: [8 warps][hitmask_stride] which list positions each warp blended (may be NULL)
     size_t hitmask_stride;
     const uint32_t* hit_base;    // engine: first word of each tile's rows in the hit-mask table (written by bucket_sort)
+    const uint32_t* tile_order;  // engine: tile (view * tiles + ty * grid_x + tx) of CTA i, longest lists first; NULL: 3-D grid
     const EngineCtl* ctl;
 };
 void launch_blend_fwd_rgb(const BlendFwdArgs& a, cudaStream_t s);
@@ -221,6 +222,7 @@ struct BlendBwdArgs {
     const uint32_t* hitmask;     // engine: written by the forward (required on the engine path)
     size_t hitmask_stride;
     const uint32_t* hit_base;
+    const uint32_t* tile_order;
     float4* grad8;               // [nviews][2P]: operator {dmx, dmy, dA, dB | dC, dopacity, dcol0, ddepth}
                                  //               engine   {dmx, dmy, dA, dB | dC, dgray, 0, 0}
     float2* gradc;               // operator: [P] {dcol1, dcol2}

@@ -225,6 +225,26 @@ class TrackingEngine:
         self.stream.synchronize()
         return last, nxt
 
+    def image_state(self, level):
+        """(final_T, n_contrib) of the most recent evaluation at `level`: tensors (2, H, W) — parity tests."""
+        Wl, Hl = int(self.width * 0.5 ** level), int(self.height * 0.5 ** level)
+        T = torch.empty((2, Hl, Wl), dtype=torch.float32, device=self.device)
+        n = torch.empty((2, Hl, Wl), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_image_state(self.handle, int(level), T.data_ptr(), n.data_ptr(), self.stream.cuda_stream),
+                       "gsevt_engine_image_state")
+        self.stream.synchronize()
+        return T, n
+
+    def view_params(self, view):
+        """The camera block the device-side pose algebra produced for `view` (0 last, 1 next) in the most recent evaluation."""
+        o = np.zeros(73, np.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.gsevt_engine_view_params(self.handle, int(view), _fp(o), self.stream.cuda_stream), "gsevt_engine_view_params")
+        return dict(viewmatrix=o[0:16].copy(), projmatrix=o[16:32].copy(), campos=o[32:35].copy(), tanfovx=float(o[35]), tanfovy=float(o[36]),
+                    proj_a=float(o[37]), proj_b=float(o[38]), proj_e=float(o[39]), vel=o[40:56].copy(), vel_inv=o[56:72].copy(),
+                    delta_time=float(o[72]))
+
     def binning(self, view, level):
         """Sorted (keys, Gaussian ids, tile ranges) of `view` from the most recent evaluation, in the reference's
         representation (parity tests)."""

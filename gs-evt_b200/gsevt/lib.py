@@ -101,6 +101,8 @@ PROTOTYPES = {
     "gsevt_engine_weighted_velocity": (C.c_int, [c_void_p, c_float_p, c_float_p, C.c_double, C.c_double, c_void_p]),
     "gsevt_engine_render_delta": (C.c_int, [c_void_p, C.c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gsevt_engine_eval": (C.c_int, [c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p, c_void_p]),
+    "gsevt_engine_image_state": (C.c_int, [c_void_p, C.c_int32, c_void_p, c_void_p, c_void_p]),
+    "gsevt_engine_view_params": (C.c_int, [c_void_p, C.c_int32, C.POINTER(C.c_float), c_void_p]),
     "gsevt_engine_launches_per_iteration": (C.c_int, [c_void_p]),
     "gsevt_engine_set_binning": (C.c_int, [c_void_p, C.c_int32]),
     "gsevt_parse_int_table": (C.c_int64, [c_void_p, C.c_size_t, c_void_p, C.c_size_t, C.c_int32]),

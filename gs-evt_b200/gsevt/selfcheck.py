@@ -50,58 +50,84 @@ def _operator_buffers(lib, saved, P, W, H):
             im[orr:orr + 8 * tiles].view(np.uint32).reshape(tiles, 2).copy())
 
 
-def engine_vs_operator(eng, gaussians, state, delta_tau, event_level0, level=0, signed=True, background=(0.0, 0.0, 0.0), lists=True):
-    """eng: TrackingEngine with begin_frame() done for `event_level0`'s frame; gaussians: GaussianModel holding the same map;
-    state: (R, T, angular_vel, linear_vel) numpy; event_level0: (1, H, W) tensor of pyramid level `level`.
-    Returns a dict of error measures (all relative)."""
-    from gaussian_splatting.utils.graphics_utils import focal2fov
-    from utils.render_camera.camera import Camera
-    from utils.render_camera.frame import RenderFrame
+def view_dict(eng, view, level):
+    """The camera block of `view` as the device-side pose algebra of the engine produced it in the most recent evaluation,
+    in the argument layout of GaussianRasterizationSettings (dgr/diff_gaussian_rasterization/__init__.py:189-207)."""
+    vp = eng.view_params(view)
+    raw = np.zeros(16, np.float32)
+    raw[0], raw[5], raw[11] = vp["proj_a"], vp["proj_b"], vp["proj_e"]      # the three entries the backward reads (backward.cu:550-560)
+    return dict(W=int(eng.width * 0.5 ** level), H=int(eng.height * 0.5 ** level), tanfovx=vp["tanfovx"], tanfovy=vp["tanfovy"],
+                viewmatrix=vp["viewmatrix"], projmatrix=vp["projmatrix"], projmatrix_raw=raw, campos=vp["campos"], vel=vp["vel"],
+                vel_inv=vp["vel_inv"], delta_time=vp["delta_time"])
+
+
+def operator_objective(mod, views, act, E, dev, signed=True, background=(0.0, 0.0, 0.0)):
+    """The tracking objective through a rasteriser module with the reference's operator API (`mod`: this repo's drop-in
+    package, or the reference's own): two rasterisations, gray, normalised difference, norm against E (frame.py:61-94,
+    tracker.py:93-103), backward to the 12 gradients [rho, theta, v, w].  act: activated map tensors on `dev`.
+    Returns loss, gradients, the two gray images and the saved work buffers of each view."""
+    P = act["xyz"].shape[0]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    pose = {k: torch.zeros(3, device=dev, requires_grad=True) for k in ("theta", "rho", "w", "v")}
+    bg = torch.tensor(background, dtype=torch.float32, device=dev)
+    zero3 = torch.zeros(3, device=dev)
+    grays, saved = [], []
+    for v in views:
+        rs = mod.GaussianRasterizationSettings(
+            image_height=v["H"], image_width=v["W"], tanfovx=v["tanfovx"], tanfovy=v["tanfovy"], bg=bg, scale_modifier=1.0,
+            viewmatrix=t(v["viewmatrix"]).view(4, 4), projmatrix=t(v["projmatrix"]).view(4, 4), projmatrix_raw=t(v["projmatrix_raw"]).view(4, 4),
+            sh_degree=3, campos=t(v["campos"]), prefiltered=False, angular_vel=zero3, linear_vel=zero3,
+            vel_transofrm=t(v["vel"]).view(4, 4), vel_transofrm_inv=t(v["vel_inv"]).view(4, 4), delta_time=v["delta_time"], debug=False)
+        color, radii, depth, opacity, n_touched = mod.GaussianRasterizer(rs)(
+            means3D=act["xyz"], means2D=torch.zeros((P, 3), device=dev), opacities=act["opacities"], shs=act["shs"], scales=act["scales"],
+            rotations=act["rotations"], theta=pose["theta"], rho=pose["rho"], w=pose["w"], v=pose["v"])
+        saved.append(tuple(color.grad_fn.saved_tensors))
+        wgt = torch.tensor(GRAY, device=dev).view(3, 1, 1)
+        grays.append((color * wgt).sum(dim=0))
+    d = grays[1] - grays[0]
+    u = d / torch.norm(d, p=2)
+    loss = torch.norm(u - E) if signed else torch.norm(torch.abs(u) - torch.abs(E))
+    loss.backward()
+    g = torch.cat([pose["rho"].grad.view(-1), pose["theta"].grad.view(-1), pose["v"].grad.view(-1), pose["w"].grad.view(-1)]).cpu().numpy()
+    return float(loss.detach()), g, [x.detach() for x in grays], saved
+
+
+def engine_vs_operator(eng, act, state, event_level, level=0, signed=True, lists=True):
+    """eng: TrackingEngine with begin_frame() done for the event frame; act: dict of the ACTIVATED map tensors on the engine's
+    device (xyz, scales, rotations, opacities, shs); state: (R, T, angular_vel, linear_vel) numpy; event_level: (H, W) tensor
+    of pyramid level `level`.  The operator is fed the camera blocks the engine's own pose kernel produced, so the two paths
+    rasterise bit-identical inputs: lists, ranges, n_contrib and final_T must then be bit-identical, images and gradients
+    agree to rounding.  Returns a dict of error measures."""
+    import diff_gaussian_rasterization as ours
     lib = _lib.load()
     dev = eng.device
     R, T, w, v = (np.asarray(x, np.float32) for x in state)
     eng.set_state(R, T, w, v)
     L, g = eng.eval(level, signed)
     gl, gn = eng.gray_images(level)
-    W0, H0 = eng.width, eng.height
-    cam = Camera(torch.from_numpy(R.reshape(3, 3).copy()), torch.from_numpy(T.copy()), torch.from_numpy(w.copy()).to(dev),
-                 torch.from_numpy(v.copy()).to(dev), focal2fov(eng_fx(eng), W0), focal2fov(eng_fy(eng), H0), W0, H0,
-                 delta_tau=delta_tau, device=dev)
-    cam.fx, cam.fy = eng_fx(eng), eng_fy(eng)
-    for p in (cam.cam_rot_delta, cam.cam_trans_delta, cam.cam_w_delta, cam.cam_v_delta):
-        p.requires_grad_(True)
-        p.grad = None
-    bg = torch.tensor(background, dtype=torch.float32, device=dev)
-    rf = RenderFrame(cam, gaussians, None, bg, level)
-    E = event_level0
-    loss = torch.norm(rf.sign_delta_Ir - E) if signed else torch.norm(rf.unsign_delta_Ir - torch.abs(E))
-    saved = [tuple(img.grad_fn.saved_tensors) for img in getattr(rf, "_raw_colors", [])] if lists else []
-    loss.backward()
-    ga = torch.cat([cam.cam_trans_delta.grad, cam.cam_rot_delta.grad, cam.cam_v_delta.grad, cam.cam_w_delta.grad]).detach().cpu().numpy()
-    Lo = float(loss.detach())
+    Tf, nc = eng.image_state(level)
+    views = [view_dict(eng, k, level) for k in (0, 1)]
+    bg = (0.0, 0.0, 0.0)
+    Lo, ga, grays, saved = operator_objective(ours, views, act, event_level, dev, signed, bg)
     out = {"loss_rel": abs(L - Lo) / max(abs(Lo), 1e-30), "grad_rel_max": rel_max(g, ga), "grad_rel_comp": rel_comp(g, ga),
-           "loss": L, "loss_operator_path": Lo}
-    grays = getattr(rf, "_grays", None)
-    if grays is not None:
-        out["gray_rel_max"] = max(rel_max(gl.cpu().numpy(), grays[0].detach().cpu().numpy()),
-                                  rel_max(gn.cpu().numpy(), grays[1].detach().cpu().numpy()))
-    if lists and saved:
-        Wl, Hl = int(W0 * 0.5 ** level), int(H0 * 0.5 ** level)
-        same = True
-        n_inst = 0
+           "loss": L, "loss_operator_path": Lo,
+           "gray_rel_max": max(rel_max(gl.cpu().numpy(), grays[0].cpu().numpy()), rel_max(gn.cpu().numpy(), grays[1].cpu().numpy()))}
+    if lists:
+        Wl, Hl = views[0]["W"], views[0]["H"]
+        same, same_img, n_inst = True, True, 0
         for view in (0, 1):
             keys, ids, ranges = eng.binning(view, level)
             okeys, oids, oranges = _operator_buffers(lib, saved[view], eng.map.P, Wl, Hl)
             same = same and np.array_equal(keys, okeys) and np.array_equal(ids, oids) and np.array_equal(ranges, oranges)
             n_inst += int(keys.size)
+            img = saved[view][-1]
+            im = img.cpu().numpy()
+            base = (-img.data_ptr()) % 256
+            oT = im[base + lib.gsevt_raster_img_offset(b"accum_alpha", Wl, Hl):][:4 * Wl * Hl].view(np.uint32)
+            on = im[base + lib.gsevt_raster_img_offset(b"n_contrib", Wl, Hl):][:4 * Wl * Hl].view(np.uint32)
+            same_img = same_img and np.array_equal(Tf[view].cpu().numpy().view(np.uint32).ravel(), oT) and \
+                np.array_equal(nc[view].cpu().numpy().view(np.uint32).ravel(), on)
         out["lists_bit_identical"] = bool(same)
+        out["n_contrib_final_T_bit_identical"] = bool(same_img)
         out["instances_compared"] = n_inst
     return out
-
-
-def eng_fx(eng):
-    return float(eng.fx)
-
-
-def eng_fy(eng):
-    return float(eng.fy)

@@ -40,9 +40,6 @@ class RenderFrame:
             cams.append(Camera(pose[:3, :3], pose[:3, 3], vp.angular_vel, vp.linear_vel, focal2fov(vp.fx * s, new_w),
                                focal2fov(vp.fy * s, new_h), new_w, new_h, delta_tau=vp.delta_tau, device=vp.device))
         last_pkg, next_pkg = render2(cams[0], vp, cams[1], self.gaussians, self.background)
-        # kept for inspection (gsevt.selfcheck reads the operator's work buffers through them); not part of the reference's API
-        self._raw_colors = (last_pkg["render"], next_pkg["render"])
-        self._grays = (self.get_intensity_frame(last_pkg["render"]), self.get_intensity_frame(next_pkg["render"]))
-        delta = self._grays[1] - self._grays[0]
+        delta = self.get_intensity_frame(next_pkg["render"]) - self.get_intensity_frame(last_pkg["render"])
         normalized = delta / torch.norm(delta, p=2)
         return normalized, torch.abs(normalized)

@@ -265,6 +265,15 @@ GSEVT_API int gsevt_engine_weighted_velocity(GsevtEngine* e, const float* last_R
  * into out[(H>>level)*(W>>level)] (device pointer) and the two grayscale views if non-NULL. */
 GSEVT_API int gsevt_engine_render_delta(GsevtEngine* e, int32_t level, float* delta_out, float* gray_last, float* gray_next,
                               void* stream);
+/* Parity access: per-pixel blending state of the most recent evaluation at `level`, both views — final transmittance
+ * and last-contributor index (the reference's accum_alpha / n_contrib, rasterizer_impl.h:47-58): device pointers,
+ * [2][H*W] each, either may be NULL. */
+GSEVT_API int gsevt_engine_image_state(GsevtEngine* e, int32_t level, float* final_T, uint32_t* n_contrib, void* stream);
+/* Parity access: the camera block the device-side pose algebra produced for `view` (0 = last, 1 = next) in the most
+ * recent evaluation — what render2 / build_rasterizer hand to the rasteriser (gaussian_renderer/__init__.py:318-337):
+ * out73 (host) = viewmatrix[16], projmatrix[16] (column-major), campos[3], tanfovx, tanfovy, projmatrix_raw[0], [5], [11],
+ * vel_transofrm[16], vel_transofrm_inv[16], delta_time.  Synchronises. */
+GSEVT_API int gsevt_engine_view_params(GsevtEngine* e, int32_t view, float* out73, void* stream);
 /* One gradient evaluation without optimiser step (parity tests): loss and the 12 pose gradients. */
 GSEVT_API int gsevt_engine_eval(GsevtEngine* e, int32_t level, int32_t signed_loss, float* loss_out, float* grads_out12,
                       void* stream);

@@ -637,40 +637,6 @@ def test_reference_pipeline_with_only_the_operator_swapped(built, cuda_dev, tmp_
 
 
 # ---- BASELINE.json sizes against the live reference ---------------------------------------------------------
-def _reference_objective(ref, sc, dev, E, signed=True):
-    """The reference's tracking objective with the reference's own extension: two rasterisations (last / next view), gray,
-    normalised difference, norm against E, backward to the 12 pose / velocity gradients [rho, theta, v, w]
-    (frame.py:61-94, tracker.py:93-103, dgr/diff_gaussian_rasterization/__init__.py:163-169).  Returns the loss, the
-    gradients, the gray images and per view (sorted keys, sorted ids, ranges) from the reference's work buffers."""
-    import torch
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
-    act = sc["act"]
-    P, W, Hh = act["xyz"].shape[0], sc["views"][0]["W"], sc["views"][0]["H"]
-    leaf = {k: t(act[k]) for k in ("xyz", "opacities", "scales", "rotations", "shs")}
-    pose = {k: torch.zeros(3, device=dev, requires_grad=True) for k in ("theta", "rho", "w", "v")}
-    bg = torch.zeros(3, device=dev)
-    grays, bins = [], []
-    for view in sc["views"]:
-        r = ref.GaussianRasterizer(H.settings(ref, view, bg, dev))
-        color, radii, depth, opacity, n_touched = r(means3D=leaf["xyz"], means2D=torch.zeros((P, 3), device=dev), opacities=leaf["opacities"],
-                                                    shs=leaf["shs"], scales=leaf["scales"], rotations=leaf["rotations"],
-                                                    theta=pose["theta"], rho=pose["rho"], w=pose["w"], v=pose["v"])
-        sb = tuple(color.grad_fn.saved_tensors)
-        rg = H.parse_ref_geom(sb[-3].cpu().numpy(), P)
-        N = int(rg["tiles_touched"].astype(np.int64).sum())
-        rb = H.parse_ref_binning(sb[-2].cpu().numpy(), N)
-        ri = H.parse_ref_img(sb[-1].cpu().numpy(), W, Hh)
-        bins.append((rb["point_list_keys"], rb["point_list"], ri["ranges"]))
-        wgt = torch.tensor([0.2989, 0.5870, 0.1140], device=dev).view(3, 1, 1)
-        grays.append((color * wgt).sum(dim=0))
-    d = grays[1] - grays[0]
-    u = d / torch.norm(d, p=2)
-    loss = torch.norm(u - E) if signed else torch.norm(torch.abs(u) - torch.abs(E))
-    loss.backward()
-    g = torch.cat([pose["rho"].grad.view(-1), pose["theta"].grad.view(-1), pose["v"].grad.view(-1), pose["w"].grad.view(-1)]).cpu().numpy()
-    return float(loss), g, [x.detach().cpu().numpy() for x in grays], bins
-
-
 @pytest.mark.parametrize("P,W,Hh", [(1_000_000, 640, 480), (1_000_000, 1280, 720), (300_000, 1280, 720)])
 def test_engine_matches_live_reference_at_baseline_sizes(built, cuda_dev, P, W, Hh):
     """The BENCHMARKED path (fused engine) at BASELINE.json's sizes against the unmodified reference extension on identical
@@ -681,20 +647,37 @@ def test_engine_matches_live_reference_at_baseline_sizes(built, cuda_dev, P, W, 
     ref = load_reference_extension()
     if ref is None:
         pytest.skip("oracle/_ref (the reference build) did not travel with this snapshot")
+    import torch
     sc = H.small_scene(P, W, Hh, seed=1)
     eng, b, sign, _ = _engine(sc, cuda_dev)
     E = b.level_view(sign, 0)
     L, g = eng.eval(0, True)
     gl, gn = eng.gray_images(0)
-    Lr, gr, grays, bins = _reference_objective(ref, sc, cuda_dev, E[0])
+    Tf, nc = eng.image_state(0)
+    # the reference rasterises the camera blocks the engine's pose kernel produced (the pose algebra has its own tests:
+    # test_pose_host.py, the first optimiser step in test_engine_iterations_match_reference_pipeline): identical inputs, so
+    # every discrete decision — tile rect, alpha >= 1/255, T < 1e-4 — must fall the same way
+    views = [selfcheck.view_dict(eng, k, 0) for k in (0, 1)]
+    A = {k: torch.from_numpy(v).to(cuda_dev) for k, v in sc["act"].items()}
+    Lr, gr, grays, saved = selfcheck.operator_objective(ref, views, A, E[0], cuda_dev)
     tiles = ((W + 15) // 16) * ((Hh + 15) // 16)
+    bins = []
     for view in (0, 1):
+        sb = saved[view]
+        rg = H.parse_ref_geom(sb[-3].cpu().numpy(), P)
+        N = int(rg["tiles_touched"].astype(np.int64).sum())
+        rb = H.parse_ref_binning(sb[-2].cpu().numpy(), N)
+        ri = H.parse_ref_img(sb[-1].cpu().numpy(), W, Hh)
+        bins.append((rb["point_list_keys"], rb["point_list"], ri["ranges"]))
         keys, ids, ranges = eng.binning(view, 0)
         rk, rl, rr = bins[view]
         assert keys.size == rk.size > P and ranges.shape == (tiles, 2)
         assert np.array_equal(keys, rk), f"sorted keys, view {view}"
         assert np.array_equal(ids, rl), f"per-tile lists, view {view}"
         assert np.array_equal(ranges, rr), f"tile ranges, view {view}"
+        assert np.array_equal(nc[view].cpu().numpy().view(np.uint32), ri["n_contrib"]), f"n_contrib, view {view}"
+        assert H.bits_equal(Tf[view].cpu().numpy(), ri["accum_alpha"]), f"final_T, view {view}"
+    grays = [x.cpu().numpy() for x in grays]
     assert H.rel_max(gl.cpu().numpy(), grays[0]) < TOL_IMG and H.rel_max(gn.cpu().numpy(), grays[1]) < TOL_IMG
     assert abs(L - Lr) < 1e-5 * abs(Lr)
     print("gradients vs reference at %d / %dx%d: rel to max %.2e, per component (floor 5%%) %.2e" % (P, W, Hh, H.rel_max(g, gr), selfcheck.rel_comp(g, gr)))
@@ -729,14 +712,13 @@ def test_operator_matches_live_reference_at_1280x720(built, cuda_dev):
 def test_bench_parity_check_runs_on_the_engine_path(built, cuda_dev):
     """gsevt.selfcheck (what bench.py prints as `parity_check`): engine vs the autograd loop through the drop-in operator."""
     import torch
-    from gsevt import selfcheck, synth
-    from gaussian_splatting.scene.gaussian_model import GaussianModel
+    from gsevt import selfcheck
     sc = H.small_scene(100000, 640, 480, seed=3)
     eng, b, sign, _ = _engine(sc, cuda_dev)
-    gm = synth.load_map_into(GaussianModel(3, device=cuda_dev), sc["raw"], device=cuda_dev)
+    A = {k: torch.from_numpy(v).to(cuda_dev) for k, v in sc["act"].items()}
     for level, signed in ((0, True), (1, True), (2, False)):
-        r = selfcheck.engine_vs_operator(eng, gm, (sc["R"], sc["T"], sc["w"], sc["v"]), sc["dtau"], b.level_view(sign, level), level, signed)
-        assert r["lists_bit_identical"] and r["instances_compared"] > 100000
+        r = selfcheck.engine_vs_operator(eng, A, (sc["R"], sc["T"], sc["w"], sc["v"]), b.level_view(sign, level)[0], level, signed)
+        assert r["lists_bit_identical"] and r["n_contrib_final_T_bit_identical"] and r["instances_compared"] > 100000
         assert r["loss_rel"] < 1e-5 and r["gray_rel_max"] < TOL_IMG
         if signed:
             assert r["grad_rel_max"] < TOL_GRAD and r["grad_rel_comp"] < TOL_GRAD
