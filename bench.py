@@ -324,6 +324,27 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, d, act, R0, T0, w0, v0, ef)
+    # ---- sub-objects, after every timed region of the headline: configs[3] as written, and (N > 1) configs[4] -------------
+    if not args.no_extras:
+        import argparse as _ap
+        extras = {}
+        try:
+            extras["search"] = hypothesis_search(torch, dist, world, rank, dev, pm, d, ef, args.hypotheses, 4)
+        except Exception as ex:   # the headline line must survive a failing extra
+            extras["search"] = {"error": f"{type(ex).__name__}: {ex}"}
+        eng.close()
+        pm.close()
+        del eng, pm
+        torch.cuda.empty_cache()
+        if world > 1:
+            ts_args = _ap.Namespace(**vars(args))
+            ts_args.gaussians, ts_args.width, ts_args.height, ts_args.steps, ts_args.warmup = 5_000_000, 1280, 720, 100, 5
+            try:
+                extras["tilesplit"] = tilesplit_line(torch, dist, world, rank, local, ts_args)
+            except Exception as ex:
+                extras["tilesplit"] = {"error": f"{type(ex).__name__}: {ex}"}
+        if rank == 0:
+            out.update(extras)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -332,19 +353,149 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: multi-hypothesis initial-pose search, every hypothesis to convergence
+# --------------------------------------------------------------------------------------------------
+def hypothesis_search(torch, dist, world, rank, dev, pm, d, ef, n_hyp, concurrent, assignment="dynamic", chunk=8):
+    """`n_hyp` perturbed pose/velocity seeds (5 cm / 1 deg / +-20 %, gsevt.hypotheses.perturb) tracked against ONE event
+    frame, each through the three pyramid levels with the reference's stopping rule (utils/tracker.py:116-240, threshold
+    1e-4, 200-iteration caps).  Ranks draw hypothesis ids from a shared ticket counter (no up-front partition: iteration
+    counts differ by hypothesis), `concurrent` hypotheses run at a time per GPU on their own streams, and ONE all-reduce at
+    the end gathers the result table.  Device-timed: CUDA events on the default stream, which waits for every engine
+    stream; barrier + synchronize on both sides, max over ranks."""
+    from gsevt import hypotheses as hyp
+    from gsevt.engine import TrackingEngine
+    engines = [TrackingEngine(pm, d["W"], d["H"], d["fx"], d["fy"], levels=3, lr_rot=d["lr"]["cam_rot_delta"],
+                              lr_trans=d["lr"]["cam_trans_delta"], lr_w=d["lr"]["cam_w_delta"], lr_v=d["lr"]["cam_v_delta"],
+                              converged_threshold=1e-4, max_optim_iter=200) for _ in range(concurrent)]
+    state = (d["R"], d["T"], d["angular_vel"], d["linear_vel"])
+
+    def one_search(n, first_id):
+        tickets = hyp.Tickets(dist)
+        static = iter(hyp.assign(n, world)[rank])
+
+        def nxt():
+            h = tickets.next() if assignment == "dynamic" else next(static, n)
+            return None if h >= n else (h, hyp.perturb(*state, first_id + h))
+
+        cur = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier_sync(dist, torch)
+        e0.record(cur)
+        for eng in engines:
+            eng.stream.wait_stream(cur)
+        rows = hyp.track_concurrently(engines, nxt, d["delta_tau"], ef.sign_pyramid, ef.unsign_pyramid, levels=3, chunk=chunk)
+        for eng in engines:
+            cur.wait_stream(eng.stream)
+        e1.record(cur)
+        torch.cuda.synchronize()
+        busy_ms = e0.elapsed_time(e1)        # this rank's own span
+        barrier_sync(dist, torch)
+        ms = max_over_ranks(dist, torch, busy_ms)
+        table = hyp.gather_results(rows, n, dist, dev)
+        return table, ms, busy_ms, len(rows)
+
+    one_search(min(n_hyp, 2 * world * concurrent), 1000)          # warm-up: graphs instantiated, buffers grown
+    table, ms, busy_ms, mine = one_search(n_hyp, 0)
+    per_rank = [None] * world
+    if dist is not None:
+        dist.all_gather_object(per_rank, dict(rank=rank, hypotheses=mine, busy_ms=round(busy_ms, 2)))
+    else:
+        per_rank = [dict(rank=0, hypotheses=mine, busy_ms=round(busy_ms, 2))]
+    for eng in engines:
+        eng.close()
+    h, loss, row = hyp.best(table)
+    iters = table[:, 2]
+    truth_T = np.asarray(d["T"], np.float64)
+    return {"workload": f"configs[3]: {n_hyp} perturbed seeds x one {d['W']}x{d['H']} event frame to convergence (3 pyramid levels, "
+                        f"threshold 1e-4, caps 200), {len(table)} results gathered",
+            "hypotheses": int(n_hyp), "n_gpus": world, "concurrent_per_gpu": concurrent, "assignment": assignment,
+            "seconds": round(ms / 1e3, 4), "hypotheses_per_s": round(n_hyp / (ms / 1e3), 3),
+            "iterations_total": int(iters.sum()), "iterations_per_s": round(float(iters.sum()) / (ms / 1e3), 1),
+            "iterations_per_hypothesis": {"min": int(iters.min()), "median": float(np.median(iters)), "max": int(iters.max())},
+            "best": {"hypothesis": h, "loss": round(loss, 6), "trans_error_m": round(float(np.linalg.norm(row[12:15] - truth_T)), 5)},
+            "start_trans_error_m_median": round(float(np.median([np.linalg.norm(hyp.perturb(*state, k)[1] - truth_T) for k in range(n_hyp)])), 5),
+            "final_trans_error_m_median": round(float(np.median(np.linalg.norm(table[:, 12:15] - truth_T, axis=1))), 5),
+            "per_rank": per_rank, "timing": "CUDA events on the default stream joined with every engine stream; max over ranks"}
+
+
+def run_search(args):
+    """`--mode search`: configs[3] on its own (hypotheses/s); the default mode carries the same object under "search"."""
+    sys.path.insert(0, PKG)
+    import torch
+    dist, world, rank, local = dist_setup(args)
+    from gsevt import lib
+    from gsevt.engine import PackedMap, TrackingEngine
+    from utils.event_camera.event import EventArray, EventFrame
+    lib.require_device()
+    dev = torch.device("cuda", local)
+    d, raw, synth = scene_description(args)
+    act = synth.activate(raw)
+    A = {k: torch.from_numpy(v).to(dev) for k, v in act.items()}
+    pm = PackedMap(A["xyz"], A["scales"], A["rotations"], A["opacities"], A["shs"], 3)
+    del A
+    K = np.array([d["fx"], 0, d["cx"], 0, d["fy"], d["cy"], 0, 0, 1.0]).reshape(3, 3)
+    ef = ground_truth_event_frame(torch, dev, pm, d, K, synth, args.events)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    res = {}
+    for c in args.concurrent:
+        res[f"concurrent_{c}"] = hypothesis_search(torch, dist, world, rank, dev, pm, d, ef, args.hypotheses, c, args.assignment)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        best = max(res.values(), key=lambda r: r["hypotheses_per_s"])
+        out = {"metric": "hypotheses/s (64 perturbed seeds, one event frame each to convergence)", "value": best["hypotheses_per_s"],
+               "unit": "hypotheses/s", "n_gpus": world, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": {"workload": best["workload"], "gaussians": args.gaussians, "width": d["W"], "height": d["H"],
+                                               "parallelism": f"hypotheses over {world} GPUs, ticket counter, no data-path collective"},
+               "clocks": clocks, "runs": res}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def ground_truth_event_frame(torch, dev, pm, d, K, synth, n_events, seed=1000):
+    """Event frame sampled from the intensity change rendered at the TRUE pose / velocity."""
+    from gsevt.engine import TrackingEngine
+    from utils.event_camera.event import EventArray, EventFrame
+    eng = TrackingEngine(pm, d["W"], d["H"], d["fx"], d["fy"], levels=1)
+    dummy = EventFrame(d["W"], d["H"], K, d["dist"], 9, EventArray(*np.zeros((4, 1), np.int64)), device=dev)
+    eng.set_state(np.asarray(d["R"], np.float32).reshape(3, 3), np.asarray(d["T"], np.float32),
+                  np.asarray(d["angular_vel"], np.float32), np.asarray(d["linear_vel"], np.float32))
+    eng.begin_frame(d["delta_tau"], dummy.sign_pyramid, dummy.unsign_pyramid)
+    eng.eval(0, True)
+    g_last, g_next = eng.gray_images(0)
+    tab = synth.sample_events((g_next - g_last).cpu().numpy(), n_events, 0, 50000, K, d["dist"], seed=seed)
+    eng.close()
+    return EventFrame(d["W"], d["H"], K, d["dist"], 9, EventArray(tab[:, 0], tab[:, 1], tab[:, 2], tab[:, 3]), device=dev)
+
+
+# --------------------------------------------------------------------------------------------------
 # this repo, screen-tile split: ONE hypothesis over all ranks (BASELINE configs[4]; strong scaling)
 # --------------------------------------------------------------------------------------------------
 def run_tilesplit(args):
     """`--mode tilesplit`: the tile rows of one hypothesis are split over the N ranks; the loss sums and the 12-float
-    gradient are exchanged inside the kernels over NVLink peer memory (gsevt/tilesplit.py).  Not the driver's default
-    line (that is the hypothesis-parallel weak-scaling mode): run explicitly, e.g.
+    gradient are exchanged inside the kernels over NVLink peer memory (gsevt/tilesplit.py).  The driver's default line
+    (hypothesis-parallel weak scaling) carries the same measurement as its "tilesplit" sub-object when N > 1; run it on its
+    own with e.g.
       torchrun --nproc-per-node 8 bench.py --gpus 8 --mode tilesplit --gaussians 5000000 --width 1280 --height 720"""
     sys.path.insert(0, PKG)
     import torch
     dist, world, rank, local = dist_setup(args)
+    out = tilesplit_line(torch, dist, world, rank, local, args)
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def tilesplit_line(torch, dist, world, rank, local, args):
+    """One hypothesis, tile rows split over `world` ranks (BASELINE.json configs[4] when called with 5 M / 1280x720).
+    Every rank returns; rank 0 gets the JSON object, the others None."""
     from gsevt import lib, tilesplit
     from gsevt.engine import PackedMap, TrackingEngine
-    from utils.event_camera.event import EventArray, EventFrame
     lib.require_device()
     dev = torch.device("cuda", local)
     d, raw, synth = scene_description(args)
@@ -356,21 +507,19 @@ def run_tilesplit(args):
                          lr_trans=d["lr"]["cam_trans_delta"], lr_w=d["lr"]["cam_w_delta"], lr_v=d["lr"]["cam_v_delta"],
                          converged_threshold=0.0, max_optim_iter=1 << 20)
     K = np.array([d["fx"], 0, d["cx"], 0, d["fy"], d["cy"], 0, 0, 1.0]).reshape(3, 3)
-    Rt = np.asarray(d["R"], np.float32).reshape(3, 3)
-    Tt = np.asarray(d["T"], np.float32)
-    wt, vt = np.asarray(d["angular_vel"], np.float32), np.asarray(d["linear_vel"], np.float32)
     # events from the ground-truth intensity change, rendered unsplit on every rank (identical everywhere)
-    dummy = EventFrame(d["W"], d["H"], K, d["dist"], 9, EventArray(*np.zeros((4, 1), np.int64)), device=dev)
-    eng.set_state(Rt, Tt, wt, vt)
-    eng.begin_frame(d["delta_tau"], dummy.sign_pyramid, dummy.unsign_pyramid)
-    eng.eval(0, True)
-    g_last, g_next = eng.gray_images(0)
-    tab = synth.sample_events((g_next - g_last).cpu().numpy(), args.events, 0, 50000, K, d["dist"], seed=1000)
-    ef = EventFrame(d["W"], d["H"], K, d["dist"], 9, EventArray(tab[:, 0], tab[:, 1], tab[:, 2], tab[:, 3]), device=dev)
+    ef = ground_truth_event_frame(torch, dev, pm, d, K, synth, args.events)
     R0, T0, w0, v0 = perturbed_state(d, 0)          # the same hypothesis on every rank
+    # the unsplit answer at the start state, on every rank, before the group exists
+    eng.set_state(R0, T0, w0, v0)
+    eng.begin_frame(d["delta_tau"], ef.sign_pyramid, ef.unsign_pyramid)
+    loss_u, grad_u = eng.eval(0, True)
     grp = tilesplit.TileSplitGroup(eng, rank, world, timeout_s=30.0) if world > 1 else None
     eng.set_state(R0, T0, w0, v0)
     eng.begin_frame(d["delta_tau"], ef.sign_pyramid, ef.unsign_pyramid)
+    loss_s, grad_s = eng.eval(0, True)               # collective: every rank scores its strip, sums exchanged in-kernel
+    gmax = float(np.abs(grad_u).max())
+    vs_unsplit = {"loss_rel": abs(loss_s - loss_u) / max(abs(loss_u), 1e-30), "grad_rel_max": float(np.abs(grad_s - grad_u).max() / max(gmax, 1e-30))}
     eng.begin_level(0, True)
     eng.iterate(max(args.warmup, 3))
     eng.stream.synchronize()
@@ -390,17 +539,21 @@ def run_tilesplit(args):
     info = eng.split_info()
     assert info["comm_error"] == 0
     clocks = sampler.stop() if rank == 0 else None
+    state_bytes = b"".join(np.ascontiguousarray(x, np.float32).tobytes() for x in eng.get_state())
     stages = eng.profile(10)                          # collective: every rank replays 10 un-graphed iterations
     wl = eng.workload()
     rows = [None] * world
     mine = dict(rank=rank, rows=info["rows"], instances=sum(wl["instances"]), pairs_walked=sum(wl["pairs_walked"]),
-                stages_ms={k: round(v, 4) for k, v in stages.items()}, loss=float(st.last_loss))
+                stages_ms={k: round(v, 4) for k, v in stages.items()}, loss=float(st.last_loss), state=state_bytes.hex())
     if dist is not None:
         dist.all_gather_object(rows, mine)
     else:
         rows = [mine]
+    out = None
     if rank == 0:
-        assert all(r["loss"] == rows[0]["loss"] for r in rows), "ranks diverged"
+        identical = all(r["loss"] == rows[0]["loss"] and r["state"] == rows[0]["state"] for r in rows)
+        for r in rows:
+            del r["state"]
         out = {"metric": "pose-track iters/sec (fwd+bwd), one hypothesis, screen-tile split", "value": round(args.steps / (ms_max / 1e3), 2),
                "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": round(ms_max / args.steps, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -409,15 +562,17 @@ def run_tilesplit(args):
                                       f"over {world} GPUs", "gaussians": args.gaussians, "width": d["W"], "height": d["H"],
                           "parallelism": f"tilesplit{world}: in-kernel exchange of 3 loss sums + 12 gradient sums over NVLink peer memory",
                           "l2": "map alone exceeds the 126 MB L2"},
-               "clocks": clocks, "gpu_launches": eng.launches_per_iteration * args.steps, "ranks": rows}
-        print(json.dumps(out))
+               "clocks": clocks, "gpu_launches": eng.launches_per_iteration * args.steps,
+               "ranks_bit_identical": bool(identical),
+               "ranks_bit_identical_what": f"loss and the 18 floats of pose + velocity after {max(args.warmup, 3) + args.steps} optimiser steps, byte compare over all ranks",
+               "vs_unsplit": {k: float(f"{v:.3e}") for k, v in vs_unsplit.items()}, "ranks": rows}
+        assert identical, "ranks diverged"
     if grp is not None:
         dist.barrier()
         grp.close()
     eng.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    pm.close()
+    return out
 
 
 def load_traffic():
@@ -604,7 +759,12 @@ def main():
     ap.add_argument("--cpu-sample-gaussians", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the engine-vs-operator-path check after the timed region")
-    ap.add_argument("--mode", choices=["hypotheses", "tilesplit"], default="hypotheses",
+    ap.add_argument("--hypotheses", type=int, default=64, help="seeds of the configs[3] search")
+    ap.add_argument("--concurrent", type=lambda t: [int(x) for x in t.split(",")], default=[1, 4],
+                    help="--mode search: hypotheses in flight per GPU (comma list = one run each)")
+    ap.add_argument("--assignment", choices=["dynamic", "static"], default="dynamic")
+    ap.add_argument("--no-extras", action="store_true", help="default mode: skip the configs[3] search / configs[4] tile-split sub-objects")
+    ap.add_argument("--mode", choices=["hypotheses", "tilesplit", "search"], default="hypotheses",
                     help="hypotheses: one independent hypothesis per GPU (weak scaling, the driver's line); "
                          "tilesplit: one hypothesis, screen tiles split over the GPUs (strong scaling, configs[4])")
     args = ap.parse_args()
@@ -616,6 +776,8 @@ def main():
         run_reference(args)
     elif args.mode == "tilesplit":
         run_tilesplit(args)
+    elif args.mode == "search":
+        run_search(args)
     else:
         run_ours(args)
 

@@ -421,6 +421,8 @@ struct GsevtEngine {
     uint32_t* hit_base = nullptr;        // [2 tiles]
     uint2* ranges = nullptr;
     uint32_t* hitmask = nullptr; size_t hitmask_stride = 0;   // forward -> backward: what each warp blended
+    int blend_bulk = 0;                  // GSEVT_BLEND_BULK=1: id lists staged with cp.async.bulk + mbarrier (blend.cu); measured 1.3 %
+                                         // slower per iteration than per-thread loads on the B200 (profiles/README.md), hence off
     float* gray = nullptr; float* final_T = nullptr; uint32_t* n_contrib = nullptr;
     double* loss_partials = nullptr;
     float* geom_partials = nullptr;
@@ -567,6 +569,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     f.ranges = e->ranges; f.point_list = e->vals; f.rec = e->rec; f.view_stride_gauss = (size_t)P;
     f.views = e->views; f.final_T = e->final_T; f.n_contrib = e->n_contrib; f.out_color = e->gray; f.ctl = e->ctl;
     f.hitmask = e->hitmask; f.hitmask_stride = e->hitmask_stride; f.hit_base = e->hit_base; f.tile_order = e->tile_order;
+    f.bulk_ids = e->blend_bulk;
     launch_blend_fwd_gray(f, s);
     mark();
     const float* evf = e->ev_sign + L.ev_offset;
@@ -585,6 +588,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     b.ranges = e->ranges; b.point_list = e->vals; b.rec = e->rec; b.view_stride_gauss = (size_t)P; b.views = e->views;
     b.final_T = e->final_T; b.n_contrib = e->n_contrib; b.gray = e->gray; b.event_frame = evf; b.ctl = e->ctl;
     b.grad8 = e->grad8; b.hitmask = e->hitmask; b.hitmask_stride = e->hitmask_stride; b.hit_base = e->hit_base; b.tile_order = e->tile_order;
+    b.bulk_ids = e->blend_bulk;
     launch_blend_bwd_gray(b, s);
     mark();
     GeomBwdArgs q;
@@ -668,6 +672,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     }
     GsevtEngine* e = new GsevtEngine();
     e->map = map; e->cfg = *cfg; e->nlevels = cfg->levels;
+    if (const char* v = getenv("GSEVT_BLEND_BULK")) e->blend_bulk = atoi(v) != 0;
     size_t ev_off = 0;
     for (int l = 0; l < cfg->levels; l++) {
         LevelInfo& L = e->lv[l];

@@ -66,6 +66,80 @@ __device__ __forceinline__ bool ellipse_hits_block(float x, float y, float A, fl
     return qmin <= tau;
 }
 
+// ---- bulk-async staging of a tile's id list (engine) -------------------------------------------------
+// A tile's list is one contiguous run of 32-bit Gaussian indices (bucketbin.cu lays every run out on a 32-byte boundary),
+// so a batch of 256 positions is ONE 1-D bulk copy (cp.async.bulk, the TMA unit's non-tensor mode): a single thread arms
+// an mbarrier with the byte count and issues the copy, the TMA unit writes the ids into a ring of shared-memory slots and
+// completes the barrier's transaction count.  The ids of batch i + 1 are in shared memory long before the CTA stages the
+// batch, so the record gather that follows starts from a shared-memory read instead of a dependent global load, and no
+// thread spends registers or issue slots on the list itself.  (The 32-byte records stay a gather: they are indexed by
+// Gaussian, not by list position — sorted record copies would cost 2 x 32 B x 6.4 M instances of extra HBM traffic per
+// iteration, see DESIGN.md "TMA".)
+constexpr int kIdSlots = 4;          // ring depth: batches i + 1 .. i + 2 in flight while batch i is blended
+constexpr int kIdAhead = 2;          // prefetch distance in batches
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals));
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Ring of id batches.  Batch i lives in slot i % kIdSlots and completes phase (i / kIdSlots) & 1 of the slot's barrier.
+// Only thread 0 touches the barriers: it arms, issues and waits; the CTA barrier that every staging round ends with
+// anyway then publishes the ids to the other 255 threads (thread 0 observed the completed phase before it arrived at
+// that barrier, and bar.sync is cumulative), so the consumers pay nothing — the first version, in which every thread
+// polled the mbarrier, cost each staging round a 90-cycle try_wait per warp and was 2.4 % slower than plain loads.
+struct IdRing {
+    uint32_t (*ids)[256];
+    uint64_t* bar;
+    const uint32_t* list;   // first id of the tile's run (32-byte aligned)
+    int issued, waited;     // batches issued / waited for so far (meaningful on thread 0)
+    __device__ __forceinline__ void init(uint32_t (*ids_)[256], uint64_t* bar_, const uint32_t* list_) {
+        ids = ids_; bar = bar_; list = list_; issued = 0; waited = 0;
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < kIdSlots; k++) mbar_init(bar + k, 1);
+            mbar_init_fence();
+        }
+    }
+    // thread 0: positions [first, first + count) of the list -> slot of batch `issued` (count > 0; first is a multiple of 8)
+    __device__ __forceinline__ void issue(int first, int count) {
+        const uint32_t bytes = (uint32_t)((count + 3) & ~3) * 4u;   // whole 16-byte units: a run's slack covers the overshoot
+        uint64_t* b = bar + (issued & (kIdSlots - 1));
+        mbar_expect_tx(b, bytes);
+        bulk_copy_g2s(ids[issued & (kIdSlots - 1)], list + first, bytes, b);
+        issued++;
+    }
+    // thread 0: waits for the next batch in order
+    __device__ __forceinline__ void wait_next() {
+        const int i = waited++;
+        mbar_wait(bar + (i & (kIdSlots - 1)), (uint32_t)(i / kIdSlots) & 1u);
+    }
+    __device__ __forceinline__ const uint32_t* slot(int batch) const { return ids[batch & (kIdSlots - 1)]; }
+    // thread 0: a CTA must not exit with copies into its shared memory still in flight
+    __device__ __forceinline__ void drain() {
+        while (waited < issued) wait_next();
+    }
+};
+
 // alpha and its ingredients in the reference's rounding order (forward.cu:342-353).
 __device__ __forceinline__ float eval_power(float dx, float dy, float A, float B, float C) {
     const float q = __fmaf_rn(dx, __fmul_rn(dx, A), __fmul_rn(dy, __fmul_rn(dy, C)));
@@ -77,9 +151,12 @@ __device__ __forceinline__ float eval_power(float dx, float dy, float A, float B
 // ------------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------------
-template <int C, bool OPERATOR>
+template <int C, bool OPERATOR, bool BULK = false>
 __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
+    static_assert(!(OPERATOR && BULK), "the operator's packed lists are not aligned for bulk copies");
     if (a.ctl && a.ctl->level_done) return;
+    __shared__ __align__(16) uint32_t s_ids[BULK ? kIdSlots : 1][256];
+    __shared__ __align__(8) uint64_t s_bar[BULK ? kIdSlots : 1];
     __shared__ float4 s_r0[2][256];
     __shared__ float4 s_r1[2][256];
     __shared__ float4 s_cull[2][256];   // {x, y, half extent x, half extent y} of the alpha >= 1/255 ellipse's box
@@ -127,11 +204,26 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     for (int ch = 0; ch < C; ch++) acc[ch] = 0.0f;
     float D = 0.0f;
 
+    IdRing ring;
+    auto issue_ids = [&](int i) {   // thread 0
+        if (i < rounds) ring.issue(i * 256, min(256, todo - i * 256));
+    };
+    if constexpr (BULK) {
+        if (rounds > 0) {
+            ring.init(s_ids, s_bar, a.point_list + range.x);
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int i = 0; i <= kIdAhead; i++) issue_ids(i);
+                ring.wait_next();                    // batch 0
+            }
+            __syncthreads();                         // barriers initialised, batch 0 visible to everyone
+        }
+    }
     // double-buffered staging: ONE block barrier per round (it also counts the finished pixels)
     auto stage = [&](int i, int buf) {
         const int prog = i * 256 + threadIdx.x;
         if (prog < todo) {
-            const uint32_t id = __ldg(a.point_list + range.x + prog);
+            const uint32_t id = BULK ? ring.slot(i)[threadIdx.x] : __ldg(a.point_list + range.x + prog);
             const float4 r0 = __ldg(rec + 2 * (size_t)id);
             const float4 r1 = __ldg(rec + 2 * (size_t)id + 1);
             s_r0[buf][threadIdx.x] = r0;
@@ -150,8 +242,14 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     if (rounds > 0) stage(0, 0);
     for (int i = 0; i < rounds; i++) {
         const int buf = i & 1;
+        if constexpr (BULK) {
+            if (threadIdx.x == 0 && i + 1 < rounds) ring.wait_next();   // batch i + 1, issued two rounds ago; published by the barrier below
+        }
         if (__syncthreads_count(done) == 256) break;
         if (i + 1 < rounds) stage(i + 1, buf ^ 1);
+        if constexpr (BULK) {
+            if (threadIdx.x == 0) issue_ids(i + 1 + kIdAhead);   // its slot held batch i - 1, last read before the barrier above
+        }
         const int base = i * 256;
         const int cnt = min(256, todo - base);
         for (int j0 = 0; j0 < cnt; j0 += 32) {
@@ -213,6 +311,9 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
         }
     }
 
+    if constexpr (BULK) {
+        if (rounds > 0 && threadIdx.x == 0) ring.drain();
+    }
     if (inside) {
         const size_t pix = (size_t)pixy * a.W + pixx;
         a.final_T[(size_t)view * HW + pix] = T;
@@ -239,7 +340,8 @@ void launch_blend_fwd_gray(const BlendFwdArgs& a, cudaStream_t s) {
     dim3 grid(a.grid_x, a.tile_rows, a.nviews);
     if (a.tile_rows <= 0) return;
     if (a.tile_order) grid = dim3((unsigned)(a.grid_x * a.tile_rows * a.nviews), 1, 1);
-    blend_fwd_kernel<1, false><<<grid, 256, 0, s>>>(a);
+    if (a.bulk_ids) blend_fwd_kernel<1, false, true><<<grid, 256, 0, s>>>(a);
+    else blend_fwd_kernel<1, false><<<grid, 256, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -275,10 +377,13 @@ __device__ __forceinline__ float warp_reduce_scatter(float (&v)[N], int lane) {
     return r;
 }
 
-template <int C, bool OPERATOR>
+template <int C, bool OPERATOR, bool BULK = false>
 __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
+    static_assert(!(OPERATOR && BULK), "the operator's packed lists are not aligned for bulk copies");
     if (a.ctl && a.ctl->level_done) return;
     constexpr int K = BwdCfg<OPERATOR>::K, KR = BwdCfg<OPERATOR>::KR;
+    __shared__ __align__(16) uint32_t s_ids[BULK ? kIdSlots : 1][256];
+    __shared__ __align__(8) uint64_t s_bar[BULK ? kIdSlots : 1];
     __shared__ float4 s_r0[2][256];
     __shared__ float4 s_r1[2][256];
     __shared__ float4 s_cull[OPERATOR ? 2 : 1][OPERATOR ? 256 : 1];
@@ -368,10 +473,27 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     // batch b holds positions [top - 256 b - 255, top - 256 b]; staged entry t <-> position hi - t.
     const int top = (int)((max_lc - 1) | 255u);
     const int len = (int)(range.y - range.x);
+    const int nbatches = (top + 1) / 256;
+    IdRing ring;
+    auto issue_ids = [&](int b) {   // thread 0; batch b = positions [lo, lo + 256) ∩ [0, len), lo = top - 256 b - 255 < max_lc <= len
+        if (b < nbatches) {
+            const int lo = top - b * 256 - 255;
+            ring.issue(lo, min(256, len - lo));
+        }
+    };
+    if constexpr (BULK) {
+        ring.init(s_ids, s_bar, a.point_list + range.x);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int b = 0; b <= kIdAhead; b++) issue_ids(b);
+            ring.wait_next();                        // batch 0
+        }
+        __syncthreads();
+    }
     auto stage = [&](int b, int buf) {
         const int pos = top - b * 256 - (int)threadIdx.x;
         if (pos < len) {   // pos >= 0 always: top - 256 b - 255 >= 0 for b < nbatches
-            const uint32_t id = __ldg(a.point_list + range.x + (uint32_t)pos);
+            const uint32_t id = BULK ? ring.slot(b)[255 - (int)threadIdx.x] : __ldg(a.point_list + range.x + (uint32_t)pos);
             const float4 r0 = __ldg(rec + 2 * (size_t)id);
             const float4 r1 = __ldg(rec + 2 * (size_t)id + 1);
             s_r0[buf][threadIdx.x] = r0;
@@ -463,12 +585,17 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
         }
     };
 
-    const int nbatches = (top + 1) / 256;
     stage(0, 0);
     for (int b = 0; b < nbatches; b++) {
         const int buf = b & 1;
+        if constexpr (BULK) {
+            if (threadIdx.x == 0 && b + 1 < nbatches) ring.wait_next();   // ids of batch b + 1; published by the barrier below
+        }
         __syncthreads();                                   // batch b staged; everyone is done with buffer buf^1
         if (b + 1 < nbatches) stage(b + 1, buf ^ 1);
+        if constexpr (BULK) {
+            if (threadIdx.x == 0) issue_ids(b + 1 + kIdAhead);   // its slot held batch b - 1, last read before the barrier above
+        }
         const int hi = top - b * 256;                      // list position of staged entry 0
         if ((uint32_t)(hi - 255) >= wmax) continue;        // nothing of this batch can touch this warp's pixels
         if constexpr (OPERATOR) {
@@ -515,7 +642,8 @@ void launch_blend_bwd_gray(const BlendBwdArgs& a, cudaStream_t s) {
     dim3 grid(a.grid_x, a.tile_rows, a.nviews);
     if (a.tile_rows <= 0) return;
     if (a.tile_order) grid = dim3((unsigned)(a.grid_x * a.tile_rows * a.nviews), 1, 1);
-    blend_bwd_kernel<1, false><<<grid, 256, 0, s>>>(a);
+    if (a.bulk_ids) blend_bwd_kernel<1, false, true><<<grid, 256, 0, s>>>(a);
+    else blend_bwd_kernel<1, false><<<grid, 256, 0, s>>>(a);
 }
 
 }  // namespace gsevt

@@ -193,6 +193,7 @@ struct BlendFwdArgs {
     size_t hitmask_stride;
     const uint32_t* hit_base;    // engine: first word of each tile's rows in the hit-mask table (written by bucket_sort)
     const uint32_t* tile_order;  // engine: tile (view * tiles + ty * grid_x + tx) of CTA i, longest lists first; NULL: 3-D grid
+    int bulk_ids;                // engine: stage the id lists with cp.async.bulk + mbarrier (lists must start on 16-byte boundaries)
     const EngineCtl* ctl;
 };
 void launch_blend_fwd_rgb(const BlendFwdArgs& a, cudaStream_t s);
@@ -223,6 +224,7 @@ struct BlendBwdArgs {
     size_t hitmask_stride;
     const uint32_t* hit_base;
     const uint32_t* tile_order;
+    int bulk_ids;
     float4* grad8;               // [nviews][2P]: operator {dmx, dmy, dA, dB | dC, dopacity, dcol0, ddepth}
                                  //               engine   {dmx, dmy, dA, dB | dC, dgray, 0, 0}
     float2* gradc;               // operator: [P] {dcol1, dcol2}

@@ -2,18 +2,48 @@
 
 The reference has no multi-GPU path; what shards naturally on this problem is the
 set of independent pose / velocity hypotheses: each is its own TrackingEngine against a read-only map,
-so hypothesis h runs on rank h mod world with NO data-path collective.  The only exchange is the final
-gather of (hypothesis id, loss, state) — 20 floats per hypothesis — to pick the winner, done with
-torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+with NO data-path collective.  Two things are shared between the ranks, both outside the optimisation:
+  * a ticket counter (`Tickets`): hypotheses run to convergence and their iteration counts differ by a factor
+    of several (60 .. 400 per pyramid level), so ranks DRAW the next hypothesis id from an atomic counter
+    served by the process group's key-value store instead of owning h mod world up front (SURVEY.md §8e);
+  * the final gather of (hypothesis id, loss, iterations, state) — 21 doubles per hypothesis — to pick the
+    winner, one all-reduce with torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+On one GPU several hypotheses run CONCURRENTLY (`track_concurrently`): one TrackingEngine per hypothesis, each
+on its own CUDA stream with its own CUDA graph, so that the kernels of one hypothesis fill the SMs the tail of
+another leaves idle; the host only polls the engines' mapped done-flags.
 """
+import itertools
 import math
 
 import numpy as np
 
 
 def assign(n_hypotheses, world):
-    """Hypothesis ids per rank: h -> rank h mod world."""
+    """Static assignment: hypothesis ids per rank, h -> rank h mod world."""
     return [list(range(r, n_hypotheses, world)) for r in range(world)]
+
+
+_search_calls = itertools.count()
+
+
+class Tickets:
+    """Atomic ticket counter over all ranks: next() -> 0, 1, 2, ... each value handed out exactly once.
+    With a process group it is `store.add(key, 1)` on the group's store (served by rank 0's TCPStore daemon, a
+    host-side round trip of tens of microseconds per hypothesis, nothing on the GPU data path); without one it
+    is a local counter.  Every rank must construct its Tickets in the same order (the key is numbered)."""
+
+    def __init__(self, dist=None, store=None):
+        self._key = f"gsevt/hypothesis_ticket/{next(_search_calls)}"
+        self._local = itertools.count()
+        self._store = store
+        if store is None and dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+            from torch.distributed import distributed_c10d as c10d
+            self._store = c10d._get_default_store()
+
+    def next(self):
+        if self._store is None:
+            return next(self._local)
+        return int(self._store.add(self._key, 1)) - 1
 
 
 def perturb(R, T, angular_vel, linear_vel, h, sigma_t=0.05, sigma_deg=1.0, vel_frac=0.2, seed=7):
@@ -64,14 +94,93 @@ def best(table):
     return h, float(losses[h]), table[h]
 
 
-def search(make_engine, state, n_hypotheses, run_one, dist=None, device="cpu"):
+def search(make_engine, state, n_hypotheses, run_one, dist=None, device="cpu", assignment="dynamic", tickets=None):
     """Runs this rank's share of the hypotheses and gathers the table on every rank.
-    make_engine() -> engine;  run_one(engine, (R, T, w, v)) -> (loss, iterations, R, T, w, v)."""
+    make_engine() -> engine;  run_one(engine, (R, T, w, v)) -> (loss, iterations, R, T, w, v).
+    assignment "dynamic": ids drawn from the shared ticket counter; "static": h mod world."""
     rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     eng = make_engine()
     rows = []
-    for h in assign(n_hypotheses, world)[rank]:
+    if assignment == "static":
+        ids = iter(assign(n_hypotheses, world)[rank])
+    else:
+        t = tickets if tickets is not None else Tickets(dist)
+        ids = iter(t.next, None)
+    for h in ids:
+        if h >= n_hypotheses:
+            break
         loss, iters, R, T, w, v = run_one(eng, perturb(*state, h))
         rows.append(pack_result(h, loss, iters, R, T, w, v))
     return gather_results(rows, n_hypotheses, dist, device)
+
+
+def track_concurrently(engines, next_hypothesis, delta_tau, sign_pyramid, unsign_pyramid, levels, chunk=8, make_event=None):
+    """Optimises hypotheses to convergence on the engines of ONE GPU, len(engines) at a time.
+
+    engines           TrackingEngine objects over the same PackedMap, each with its own stream;
+    next_hypothesis   () -> (h, (R, T, w, v)) or None when there is nothing left to draw;
+    levels            pyramid levels, run coarse -> fine with the tracker's rule (utils/tracker.py:116-240: the
+                      coarsest level optimises the pose only, the others pose + velocity);
+    make_event        engine -> object with .query() that becomes true when the work queued so far on the engine's
+                      stream has finished (default: a torch.cuda.Event recorded on engine.stream).
+    Returns the result rows (pack_result) of every hypothesis this call ran.
+
+    An engine is never synchronised while another one could be fed: each gets `chunk` graph launches, the host then
+    watches the chunk's event and the engine's done-flag (a mapped host word the device writes) and either queues the
+    next chunk, moves the hypothesis to the next level, or draws the next hypothesis for the engine."""
+    if make_event is None:
+        import torch
+
+        def make_event(eng):
+            ev = torch.cuda.Event()
+            ev.record(eng.stream)
+            return ev
+
+    rows, slots = [], [None] * len(engines)
+
+    def feed(i):
+        slots[i]["event"] = None
+        engines[i].iterate(chunk)
+        slots[i]["event"] = make_event(engines[i])
+
+    def start(i):
+        nxt = next_hypothesis()
+        if nxt is None:
+            slots[i] = None
+            return
+        h, st = nxt
+        eng = engines[i]
+        eng.set_state(*st)
+        eng.begin_frame(delta_tau, sign_pyramid, unsign_pyramid)
+        slots[i] = dict(h=h, level=levels - 1, iters=0, event=None)
+        eng.begin_level(levels - 1, opt_vel=False)
+        feed(i)
+
+    for i in range(len(engines)):
+        start(i)
+    while any(s is not None for s in slots):
+        for i, s in enumerate(slots):
+            if s is None or not s["event"].query():
+                continue
+            eng = engines[i]
+            flag = eng.poll_done()
+            if flag == 0:
+                feed(i)
+            elif flag == 2:
+                eng.resume()
+                feed(i)
+            elif flag == 3:
+                raise RuntimeError("tile-split exchange timed out inside a hypothesis search")
+            else:
+                st = eng.status()
+                s["iters"] += int(st.optim_iter)
+                if s["level"] > 0:
+                    s["level"] -= 1
+                    eng.begin_level(s["level"], opt_vel=True)
+                    feed(i)
+                else:
+                    R, T, w, v = eng.get_state()
+                    rows.append(pack_result(s["h"], float(st.last_loss), s["iters"], R, T, w, v))
+                    start(i)
+    return rows

@@ -28,9 +28,16 @@ ROBOT = dict(DESK,
 
 
 def synth_map(P, seed=0, W=DESK["W"], H=DESK["H"], fx=DESK["fx"], fy=DESK["fy"], R=DESK["R"], T=DESK["T"],
-              sh_degree=3):
+              sh_degree=3, structure=0, structure_scale=0.25, fine_opacity_shift=0.0, structure_depth=(3.0, 6.0)):
     """Raw (pre-activation) 3DGS parameters, float32, as a dict:
-    xyz (P,3), f_dc (P,1,3), f_rest (P,15,3), opacity (P,1) logits, scaling (P,3) log-scales, rotation (P,4)."""
+    xyz (P,3), f_dc (P,1,3), f_rest (P,15,3), opacity (P,1) logits, scaling (P,3) log-scales, rotation (P,4).
+
+    structure > 0: a TRACKABLE scene (DESIGN.md "Sequences").  `structure` of the P Gaussians become large, nearly opaque,
+    strongly coloured, view-independent splats (extent `structure_scale` metres at 3..6 m: tens of pixels, well above the
+    9x9 blur of the event frame) spread over 1.6x the initial frustum, and the remaining fine splats get their opacity
+    logits shifted by `fine_opacity_shift` (negative: a faint texture on top of the structure instead of a noise wall)."""
+    if structure > 0:
+        return _structured_map(P, seed, W, H, fx, fy, R, T, sh_degree, int(structure), float(structure_scale), float(fine_opacity_shift), structure_depth)
     rng = np.random.default_rng(seed)
     R0 = np.asarray(R, np.float64).reshape(3, 3)
     T0 = np.asarray(T, np.float64).reshape(3)
@@ -53,6 +60,32 @@ def synth_map(P, seed=0, W=DESK["W"], H=DESK["H"], fx=DESK["fx"], fy=DESK["fy"],
         f_dc=rng.normal(0.0, 1.0, (P, 1, 3)).astype(np.float32),
         f_rest=rng.normal(0.0, 0.1, (P, ncoef - 1, 3)).astype(np.float32),
     )
+
+
+def _structured_map(P, seed, W, H, fx, fy, R, T, sh_degree, n_big, big_scale, fine_shift, depth=(3.0, 6.0)):
+    base = synth_map(P, seed=seed, W=W, H=H, fx=fx, fy=fy, R=R, T=T, sh_degree=sh_degree)
+    rng = np.random.default_rng(seed + 7919)
+    n_big = min(n_big, P)
+    R0 = np.asarray(R, np.float64).reshape(3, 3)
+    T0 = np.asarray(T, np.float64).reshape(3)
+    tanx, tany = W / (2 * fx), H / (2 * fy)
+    sel = rng.choice(P, n_big, replace=False)          # spread over the index range like any other Gaussian
+    z = rng.uniform(depth[0], depth[1], n_big)
+    pc = np.stack([z * tanx * rng.uniform(-1.6, 1.6, n_big), z * tany * rng.uniform(-1.6, 1.6, n_big), z], axis=1)
+    base["opacity"] = (base["opacity"] + np.float32(fine_shift)).astype(np.float32)
+    # nothing within a metre of the camera plane: a splat that crosses the renderer's 0.2 m near cut covers a third of the
+    # image and pops in or out from one iteration to the next (a step in the loss no optimiser can follow)
+    cam = base["xyz"].astype(np.float64) @ R0.T + T0
+    near = (cam[:, 2] > -1.0) & (cam[:, 2] < 1.0)
+    cam[near, 2] -= 2.0
+    base["xyz"] = ((cam - T0) @ R0).astype(np.float32)
+    base["xyz"][sel] = ((pc - T0) @ R0).astype(np.float32)
+    # extent proportional to the depth: every structure splat covers about the same number of pixels
+    base["scaling"][sel] = (np.log(big_scale * z / 4.5)[:, None] + rng.normal(0.0, 0.25, (n_big, 1)) + rng.normal(0.0, 0.1, (n_big, 3))).astype(np.float32)
+    base["opacity"][sel] = rng.normal(2.5, 0.5, (n_big, 1)).astype(np.float32)
+    base["f_dc"][sel] = rng.normal(0.0, 1.6, (n_big, 1, 3)).astype(np.float32)
+    base["f_rest"][sel] = 0.0
+    return base
 
 
 def activate(m):
@@ -117,22 +150,45 @@ def se3_exp(xi):
 
 
 def ground_truth_trajectory(n_frames, dtau=0.05, R=DESK["R"], T=DESK["T"], lin=DESK["linear_vel"], ang=DESK["angular_vel"],
-                            modulation=0.1, period=2.0):
-    """Poses (world->camera 4x4) at frame mid-times and the velocities there: constant yaml velocity with
-    +-10 % sinusoidal modulation.  Frame j spans [j*dtau, (j+1)*dtau]."""
+                            modulation=0.1, period=2.0, mode="drift", orbit_period=12.0):
+    """Poses (world->camera 4x4) at frame mid-times and the velocities there.  Frame j spans [j*dtau, (j+1)*dtau].
+    mode "drift": constant yaml velocity with +-10 % sinusoidal modulation (the camera leaves a frustum-sized synthetic map
+    after a few hundred frames).  mode "orbit": the same speeds, but the body-frame velocity vectors turn at constant
+    magnitude with period `orbit_period` seconds about the axis they make with the optical axis — the camera runs a closed
+    loop of radius |v| * period / 2 pi (0.28 m at the desk yaml's 0.145 m/s) and never stands still, so a sequence of any
+    length stays inside the map."""
     pose = np.eye(4)
     pose[:3, :3], pose[:3, 3] = np.asarray(R, np.float64).reshape(3, 3), np.asarray(T, np.float64)
     lin, ang = np.asarray(lin, np.float64), np.asarray(ang, np.float64)
+
+    def basis(v):
+        n = np.linalg.norm(v)
+        e1 = v / n if n > 0 else np.array([1.0, 0, 0])
+        k = np.cross(e1, np.array([0.0, 0.0, 1.0]))
+        if np.linalg.norm(k) < 1e-6:
+            k = np.cross(e1, np.array([0.0, 1.0, 0.0]))
+        k /= np.linalg.norm(k)
+        return n, e1, np.cross(k, e1)
+
+    nl, l1, l2 = basis(lin)
+    na, a1, a2 = basis(ang)
+
+    def vel(t):
+        if mode == "orbit":
+            c, s_ = math.cos(2 * math.pi * t / orbit_period), math.sin(2 * math.pi * t / orbit_period)
+            return nl * (c * l1 + s_ * l2), na * (c * a1 + s_ * a2)
+        f = 1.0 + modulation * math.sin(2 * math.pi * t / period)
+        return lin * f, ang * f
+
     out, sub = [], 10
     t = 0.0
     for j in range(n_frames):
         for k in range(sub):
+            v, w = vel(t)
             if k == sub // 2:
-                f = 1.0 + modulation * math.sin(2 * math.pi * t / period)
-                out.append((pose.copy(), lin * f, ang * f, t))
-            f = 1.0 + modulation * math.sin(2 * math.pi * t / period)
+                out.append((pose.copy(), v, w, t))
             h = dtau / sub
-            pose = se3_exp(np.concatenate([lin * f * h, ang * f * h])) @ pose
+            pose = se3_exp(np.concatenate([v * h, w * h])) @ pose
             t += h
     return out
 
@@ -168,6 +224,46 @@ def sample_events(delta_I, n_events, t_start_us, t_end_us, K, D, seed):
     return np.stack([ts, x, y, pol], axis=1)
 
 
+def threshold_events(delta_I, n_events, t_start_us, t_end_us, K, D, seed):
+    """Events the way a sensor with a contrast threshold C fires them: a pixel emits floor(|delta_I| / C + u) events of the
+    sign of delta_I (u ~ U[0,1): the charge left over from before the frame), with C chosen by bisection so that the frame
+    holds n_events — the reference cuts the stream into packets of a fixed COUNT (event.py:69-90), so a frame must hold
+    exactly that many; the last few are added / dropped at the pixels nearest to their next threshold crossing.  Same
+    output format as sample_events: int64 (n, 4) ts x y p, forward-distorted to sensor pixels."""
+    rng = np.random.default_rng(seed)
+    H, W = delta_I.shape
+    a = np.abs(delta_I).astype(np.float64).ravel()
+    if a.sum() <= 0:
+        return sample_events(delta_I, n_events, t_start_us, t_end_us, K, D, seed)
+    u = rng.uniform(0.0, 1.0, a.size)
+    lo, hi = 0.0, a.max() * 4.0 + 1e-30               # counts(C) is decreasing in C
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if np.floor(a / mid + u).sum() > n_events:
+            lo = mid
+        else:
+            hi = mid
+    x = a / hi + u
+    cnt = np.floor(x).astype(np.int64)
+    short = int(n_events - cnt.sum())                 # >= 0 by construction of hi
+    if short > 0:
+        frac = x - cnt
+        cnt[np.argsort(-frac, kind="stable")[:short]] += 1
+    elif short < 0:
+        frac = np.where(cnt > 0, x - cnt, 2.0)
+        cnt[np.argsort(frac, kind="stable")[:-short]] -= 1
+    idx = np.repeat(np.arange(a.size), cnt)
+    idx = idx[rng.permutation(idx.size)]
+    v, uu = np.divmod(idx, W)
+    pol = (delta_I.ravel()[idx] > 0).astype(np.int64)
+    ud, vd = distort_points(uu.astype(np.float64), v.astype(np.float64), np.asarray(K, np.float64).reshape(3, 3), D)
+    xs = np.clip(np.rint(ud), 0, W - 1).astype(np.int64)
+    ys = np.clip(np.rint(vd), 0, H - 1).astype(np.int64)
+    ts = np.sort(rng.integers(int(t_start_us), int(t_end_us) + 1, idx.size))
+    ts[0], ts[-1] = int(t_start_us), int(t_end_us)
+    return np.stack([ts, xs, ys, pol], axis=1)
+
+
 def random_events(n_events, W, H, t_start_us, t_end_us, seed):
     rng = np.random.default_rng(seed)
     ts = np.sort(rng.integers(int(t_start_us), int(t_end_us) + 1, n_events))
@@ -177,7 +273,11 @@ def random_events(n_events, W, H, t_start_us, t_end_us, seed):
 
 def write_events_txt(path, ev):
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    np.savetxt(path, ev, fmt="%d", delimiter=" ")
+    try:   # same bytes as np.savetxt(fmt="%d"), twice as fast on tens of millions of rows
+        import pandas as pd
+        pd.DataFrame(np.asarray(ev, np.int64)).to_csv(path, sep=" ", header=False, index=False)
+    except ImportError:
+        np.savetxt(path, ev, fmt="%d", delimiter=" ")
 
 
 def make_config(map_path, events_path, save_path, W=DESK["W"], H=DESK["H"], device="cuda", centered=True, **over):

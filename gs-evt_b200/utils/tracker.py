@@ -53,6 +53,7 @@ class Tracker:
         self.chunk = int(extra.get("iterations_per_poll", 8))
         self.iter_counts = []       # per frame: [(level, coarse_iters, fine_iters, seconds)]
         self.trajectory = []        # per frame: (timestamp, T(3), quat xyzw)
+        self.velocities = []        # per frame: (angular_vel(3), linear_vel(3)) after the frame's optimisation (engine path)
         os.makedirs(self.save_path, exist_ok=True)
         self.log = Logger(name="TrackingLogger", log_file=f"{self.save_path}/tracking_log.log", level=logging.INFO)
 
@@ -146,6 +147,7 @@ class Tracker:
                 eng.weighted_velocity(R0, T0, (delta_tau + last_delta_tau) / 2, 0.5)
             last_delta_tau = delta_tau
             Rm, T, w, v = eng.get_state()
+            self.velocities.append((np.array(w, np.float64), np.array(v, np.float64)))
             dev = vp.device
             vp.update_RT(torch.from_numpy(Rm.copy()).to(dev), torch.from_numpy(T.copy()).to(dev))
             vp.angular_vel, vp.linear_vel = torch.from_numpy(w.copy()).to(dev), torch.from_numpy(v.copy()).to(dev)

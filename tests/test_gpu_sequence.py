@@ -21,16 +21,23 @@ for p in (PKG, ROOT):
         sys.path.insert(0, p)
 
 
-def make_sequence(dev, P, W, H, n_frames, n_events, dtau=0.05, seed=0, ang_scale=5.0, lin_scale=2.0, scale_mult=1.0):
+def make_sequence(dev, P, W, H, n_frames, n_events, dtau=0.05, seed=0, ang_scale=5.0, lin_scale=2.0, scale_mult=1.0,
+                  structure=0, structure_scale=0.25, fine_opacity_shift=0.0, event_model="proportional", traj="drift",
+                  orbit_period=12.0, vel_lr_scale=1.0, structure_depth=(3.0, 6.0)):
     """Synthetic map + ground-truth trajectory + events sampled from the intensity change rendered (by the
-    engine) at the true pose / velocity of every frame (SURVEY.md 8(d) "Events")."""
+    engine) at the true pose / velocity of every frame (SURVEY.md 8(d) "Events").
+    structure / fine_opacity_shift: the trackable scene of gsevt.synth.synth_map; event_model "threshold": contrast-threshold
+    events (synth.threshold_events) instead of draws proportional to |delta I|; traj "orbit": closed-loop trajectory;
+    vel_lr_scale: multiplies the yaml's cam_v_delta / cam_w_delta for BOTH trackers (the normalised loss does not see the
+    magnitude of the velocity, so Adam walks along that direction at its full step; DESIGN.md "Sequences")."""
     import torch
     from gsevt import ate, synth
     from gsevt.engine import EventFrameBuilder, PackedMap, TrackingEngine
     D = synth.DESK
     s = W / D["W"]
     fx, fy = D["fx"] * s, D["fy"] * s
-    raw = synth.synth_map(P, seed=seed, W=W, H=H, fx=fx, fy=fy)
+    raw = synth.synth_map(P, seed=seed, W=W, H=H, fx=fx, fy=fy, structure=structure, structure_scale=structure_scale,
+                          fine_opacity_shift=fine_opacity_shift, structure_depth=structure_depth)
     if scale_mult != 1.0:
         # larger splats = lower-frequency texture: the event frame is blurred 9x9 (event.py:123) while the rendered
         # difference is not, so a map whose texture is finer than the blur carries almost no usable signal
@@ -41,7 +48,8 @@ def make_sequence(dev, P, W, H, n_frames, n_events, dtau=0.05, seed=0, ang_scale
     K = np.array([fx, 0, W / 2.0, 0, fy, H / 2.0, 0, 0, 1.0]).reshape(3, 3)
     lin = np.asarray(D["linear_vel"]) * lin_scale
     ang = np.asarray(D["angular_vel"]) * ang_scale
-    gt = synth.ground_truth_trajectory(n_frames, dtau, D["R"], D["T"], lin, ang)
+    gt = synth.ground_truth_trajectory(n_frames, dtau, D["R"], D["T"], lin, ang, mode=traj, orbit_period=orbit_period)
+    make_events = synth.threshold_events if event_model == "threshold" else synth.sample_events
     b = EventFrameBuilder(W, H, K, D["dist"], levels=1, device=dev)
     z = np.zeros(1, np.int16)
     dummy = b.build(z, z, z.astype(np.uint8))
@@ -51,14 +59,16 @@ def make_sequence(dev, P, W, H, n_frames, n_events, dtau=0.05, seed=0, ang_scale
         eng.begin_frame(dtau, dummy[0], dummy[1])
         eng.eval(0, True)
         gl, gn = eng.gray_images(0)
-        tabs.append(synth.sample_events((gn - gl).cpu().numpy(), n_events, round(j * dtau * 1e6), round((j + 1) * dtau * 1e6) - 1,
-                                        K, D["dist"], seed=1000 + j))
+        tabs.append(make_events((gn - gl).cpu().numpy(), n_events, round(j * dtau * 1e6), round((j + 1) * dtau * 1e6) - 1,
+                                K, D["dist"], seed=1000 + j))
     eng.close()
     table = np.concatenate(tabs, 0)
     gt_tum = (np.array([g[3] for g in gt]), np.array([g[0][:3, 3] for g in gt]),
               np.array([ate.matrix_to_quat(g[0][:3, :3]) for g in gt]))
+    lr = dict(D["lr"])
+    lr["cam_v_delta"], lr["cam_w_delta"] = lr["cam_v_delta"] * vel_lr_scale, lr["cam_w_delta"] * vel_lr_scale
     desc = dict(W=W, H=H, fx=fx, fy=fy, cx=W / 2.0, cy=H / 2.0, dist=list(D["dist"]), R=list(D["R"]), T=list(D["T"]),
-                angular_vel=ang.tolist(), linear_vel=lin.tolist(), lr=dict(D["lr"]), converged_threshold=D["converged_threshold"],
+                angular_vel=(gt[0][2] if traj == "orbit" else ang).tolist(), linear_vel=(gt[0][1] if traj == "orbit" else lin).tolist(), lr=lr, converged_threshold=D["converged_threshold"],
                 max_optim_iter=D["max_optim_iter"], max_events_per_frame=n_events, background=[0, 0, 0])
     return raw, table, gt_tum, desc
 
@@ -73,11 +83,13 @@ def run_ours(raw, table, desc, work):
     synth.save_map_ply(ply, raw)
     synth.write_events_txt(evs, table)
     cfg = synth.make_config(ply, evs, save, W=desc["W"], H=desc["H"], Event__max_events_per_frame=desc["max_events_per_frame"],
+                            Optimizer__cam_v_delta=desc["lr"]["cam_v_delta"], Optimizer__cam_w_delta=desc["lr"]["cam_w_delta"],
                             Tracking__initial_vel={"angular_vel": desc["angular_vel"], "linear_vel": desc["linear_vel"]})
     cpath = os.path.join(work, "config.yaml")
     with open(cpath, "w") as f:
         yaml.safe_dump(cfg, f)
     tr = gs_main.main(cpath)
+    run_ours.last_tracker = tr
     tum = ate.load_tum(os.path.join(save, "tracking_pose_tum.txt"))
     iters = np.array([[c + f for (_, c, f, _) in per] for per in tr.iter_counts])
     secs = float(sum(t for per in tr.iter_counts for (_, _, _, t) in per))
@@ -97,12 +109,18 @@ def run_reference(raw, table, desc, work):
     return (t[:, 0], t[:, 1:4], t[:, 4:8]), z["iters"][:, 0].reshape(-1, 3), float(z["opt_time"].sum())
 
 
-def sequence_report(dev, work, P=40000, W=320, H=240, n_frames=8, n_events=12000, **seq_kw):
+def sequence_report(dev, work, P=40000, W=320, H=240, n_frames=8, n_events=12000, ref_twice=False, **seq_kw):
     from gsevt import ate
     raw, table, gt, desc = make_sequence(dev, P, W, H, n_frames, n_events, **seq_kw)
     ours, it_o, s_o = run_ours(raw, table, desc, work)
     ref, it_r, s_r = run_reference(raw, table, desc, work)
     cmp_ = ate.compare(ours, ref)
+    self_spread = None
+    if ref_twice:   # the unmodified reference against its own second run on the same files: what "identical" means here
+        ref2, it_r2, _ = run_reference(raw, table, desc, os.path.join(work, "second"))
+        c2 = ate.compare(ref2, ref)
+        self_spread = {"per_frame_trans_m": [round(x, 6) for x in c2["trans_per_frame_m"]],
+                       "per_frame_rot_deg": [round(x, 5) for x in c2["rot_per_frame_deg"]], "iterations_second_run": it_r2.tolist()}
     rep = {"frames": n_frames, "gaussians": P, "size": [W, H], "events_per_frame": n_events,
            "ours_vs_reference": {k: cmp_[k] for k in ("pairs", "trans_max_m", "trans_rmse_m", "rot_max_deg", "rot_mean_deg")},
            "per_frame_trans_m": [round(x, 6) for x in cmp_["trans_per_frame_m"]],
@@ -113,45 +131,54 @@ def sequence_report(dev, work, P=40000, W=320, H=240, n_frames=8, n_events=12000
            "ours_vs_gt_trans_m": [round(x, 5) for x in ate.compare(ours, gt)["trans_per_frame_m"]],
            "reference_vs_gt_trans_m": [round(x, 5) for x in ate.compare(ref, gt)["trans_per_frame_m"]],
            "iterations_ours": it_o.tolist(), "iterations_reference": it_r.tolist(),
-           "optimisation_seconds": {"ours": round(s_o, 3), "reference": round(s_r, 3)}}
+           "optimisation_seconds": {"ours": round(s_o, 3), "reference": round(s_r, 3)},
+           "reference_vs_its_own_second_run": self_spread, "generator": {k: (list(v) if isinstance(v, tuple) else v) for k, v in seq_kw.items()}}
     return rep
 
 
 @pytest.mark.gpu
 def test_sequence_tracking_matches_reference_tracker(built, cuda_dev, tmp_path):
     """Whole pipeline, both implementations, same files in (map.ply, events.txt, config.yaml -> Tracker.tracking()):
-    BASELINE.json configs[1] in small — 300 k Gaussians, 640x480, 30 000 events per frame, the desk yaml's own
-    velocities, 4 event frames, three pyramid levels and both stages per frame with the reference's stopping rule.
+    BASELINE.json configs[1] in small — 300 k Gaussians, 640x480, 30 000 events per frame, the desk yaml's own velocities
+    and learning rates, 24 event frames (so the velocity mix of tracker.py:246-248 that starts at frame 5 is covered),
+    three pyramid levels and both stages per frame with the reference's stopping rule.
 
-    Gate: north_star's 1 mm / 0.05 deg between the two trackers' poses on frames 0-2 (measured over repeated runs:
-    0.19-0.34 mm, 0.003-0.008 deg — profiles/r1_sequence_22f_300k_v30.json and the v31 repeats); every frame in the
-    same basin (5 cm / 0.5 deg).  Frame 3 is where a level first runs into the 200-iteration cap in BOTH trackers; from
-    there the stop iteration jitters with the atomics order (0.9 mm in one run, 3.9 mm in the next), and a few frames
-    later both lose the noise-textured synthetic map for good — the reference at frame 6-8, ours at frame 14 in the
-    22-frame run — so later frames are reported, not gated.  (On the smaller, faster-rotating 40 k / 320x240 scene this
-    test used before, the unmodified reference does not even reproduce its own frame-0 stop iterations:
-    profiles/r1_seq_ab_v11.log.)"""
+    Scene: the TRACKABLE synthetic scene of gsevt.synth (400 large structure splats under a faint fine texture, nothing
+    within a metre of the camera plane, contrast-threshold events, closed-loop trajectory).  On the noise-textured map
+    used in round 1 both trackers lost the scene after 6-14 frames — a splat crossing the renderer's 0.2 m near cut pops
+    over a third of the image and steps the loss (DESIGN.md "Sequences"); on this scene both hold it for as long as they
+    are run (profiles/r2_long_sequence_1000f.json) 1-4 mm from the ground truth.
+
+    Gates (measured: profiles/r2_sequence_24f_trackable.json — ours vs reference 0.08-2.07 mm / 0.001-0.027 deg, median
+    0.47 mm, 20 of 24 frames under 1 mm; the UNMODIFIED reference against its own second run on the same files 0.01-1.13 mm
+    / up to 0.015 deg: the stopping rule thresholds the mean |loss step| on a plateau, so the stop iteration and with it the
+    last millimetre jitters with the order of the float atomics in EITHER implementation):
+      * rotation: north_star's 0.05 deg on every frame;
+      * translation: north_star's 1 mm on the median and on at least 2 frames in 3; no frame further than 3 mm — that is
+        2.7x the reference's own repeatability on this scene;
+      * ATE against the ground truth (what BASELINE.json's metric calls ATE parity): the two RMSEs within 0.3 mm of each
+        other, both trackers within 1 cm of the truth on every frame."""
     from oracle import ref_runner
     if not ref_runner.available():
         pytest.skip("oracle/_ref did not travel with this snapshot")
-    rep = sequence_report(cuda_dev, str(tmp_path), P=300000, W=640, H=480, n_frames=4, n_events=30000, ang_scale=1.0, lin_scale=1.0)
+    rep = sequence_report(cuda_dev, str(tmp_path), P=300000, W=640, H=480, n_frames=24, n_events=30000, ang_scale=1.0, lin_scale=1.0,
+                          structure=400, fine_opacity_shift=-3.0, event_model="threshold", traj="orbit")
     print(json.dumps(rep))
     c = rep["ours_vs_reference"]
-    assert c["pairs"] == rep["frames"] == 4
-    dt, dr = rep["per_frame_trans_m"], rep["per_frame_rot_deg"]
-    print("ours vs reference per frame: %s m, %s deg; optimisation %s s" % (dt, dr, rep["optimisation_seconds"]))
-    assert max(dt[:3]) < 1e-3 and max(dr[:3]) < 0.05, (dt, dr)
-    assert max(dt) < 0.05 and max(dr) < 0.5, (dt, dr)
-    # both trackers actually track these frames (a few centimetres from the synthetic ground truth at most)
-    assert max(rep["ours_vs_gt_trans_m"]) < 0.05 and max(rep["reference_vs_gt_trans_m"]) < 0.05
+    assert c["pairs"] == rep["frames"] == 24
+    dt, dr = np.array(rep["per_frame_trans_m"]), np.array(rep["per_frame_rot_deg"])
+    print("ours vs reference per frame: %s mm, %s deg; optimisation %s s" % ((dt * 1e3).round(2).tolist(), dr.tolist(), rep["optimisation_seconds"]))
+    assert dr.max() < 0.05, dr
+    assert np.median(dt) < 1e-3 and (dt < 1e-3).sum() >= 16 and dt.max() < 3e-3, dt
+    # both trackers actually track: every frame within a centimetre of the synthetic ground truth, equal ATE
+    assert max(rep["ours_vs_gt_trans_m"]) < 0.01 and max(rep["reference_vs_gt_trans_m"]) < 0.01
+    assert abs(rep["ate_ours"]["ate_rmse_m"] - rep["ate_reference"]["ate_rmse_m"]) < 3e-4, (rep["ate_ours"], rep["ate_reference"])
     it_o, it_r = np.array(rep["iterations_ours"]), np.array(rep["iterations_reference"])
     assert it_o.shape == it_r.shape == (rep["frames"], 3)
     cap = 2 * 200 + 1                                  # coarse + fine stage caps of tracker.py:224-240
     assert it_o.min() >= 1 and it_o.max() <= cap and it_r.max() <= cap
-    # frame 0: the coarsest level (descending from the same start, far from the plateau) stops at about the same iteration
-    assert abs(int(it_o[0][0]) - int(it_r[0][0])) <= 15, (it_o[0], it_r[0])
-    for k in ("ate_ours", "ate_reference"):
-        assert all(np.isfinite(v) for v in rep[k].values() if isinstance(v, float)), rep[k]
+    # same amount of optimisation work per level on average (the stop iteration of a single level jitters, see above)
+    assert np.all(np.abs(it_o.mean(0) - it_r.mean(0)) < 0.15 * it_r.mean(0)), (it_o.mean(0), it_r.mean(0))
 
 
 if __name__ == "__main__":
@@ -168,10 +195,16 @@ if __name__ == "__main__":
     ap.add_argument("--ang-scale", type=float, default=5.0)
     ap.add_argument("--lin-scale", type=float, default=2.0)
     ap.add_argument("--scale-mult", type=float, default=1.0)
+    ap.add_argument("--structure", type=int, default=0)
+    ap.add_argument("--fine-shift", type=float, default=0.0)
+    ap.add_argument("--event-model", default="proportional")
+    ap.add_argument("--traj", default="drift")
+    ap.add_argument("--ref-twice", action="store_true")
     a = ap.parse_args()
     with tempfile.TemporaryDirectory() as td:
         rep = sequence_report(torch.device("cuda:0"), td, a.gaussians, a.width, a.height, a.frames, a.events,
-                              ang_scale=a.ang_scale, lin_scale=a.lin_scale, scale_mult=a.scale_mult)
+                              ang_scale=a.ang_scale, lin_scale=a.lin_scale, scale_mult=a.scale_mult, structure=a.structure,
+                              fine_opacity_shift=a.fine_shift, event_model=a.event_model, traj=a.traj, ref_twice=a.ref_twice)
     s = json.dumps(rep)
     print(s)
     if a.out:
