@@ -378,6 +378,7 @@ struct GsevtMap {
     float2* cov_b = nullptr;
     float* sh_planar = nullptr;
     float* sh_aos = nullptr;
+    float* smax2 = nullptr;     // [P] largest eigenvalue of the 3-D covariance
     size_t bytes = 0;
 };
 
@@ -520,7 +521,9 @@ static PreMapArgs premap_args(GsevtEngine* e) {
     const GsevtMap* m = e->map;
     PreMapArgs pa;
     pa.P = m->P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
-    pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar;
+    pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar; pa.smax2 = m->smax2;
+    pa.split_pretest = (e->split_n > 1 || getenv("GSEVT_STRIP_PRETEST")) && m->smax2 &&
+                       (e->strip_y0 > 0 || e->strip_y1 < e->lv[e->cur_level].gy) ? 1 : 0;
     pa.rect_raw = e->rect_raw; pa.depth_raw = e->depth_raw; pa.clamped = e->clamped;
     pa.rec = e->rec; pa.grad8 = e->grad8;
     return pa;
@@ -646,21 +649,21 @@ GSEVT_API int gsevt_map_create(int32_t P, int32_t sh_degree, const float* xyz, c
     const size_t p = (size_t)P;
     if (cudaMalloc(&m->xyz_opacity, p * 16) != cudaSuccess || cudaMalloc(&m->cov_a, p * 16) != cudaSuccess ||
         cudaMalloc(&m->cov_b, p * 8) != cudaSuccess || cudaMalloc(&m->sh_planar, p * 48 * 4) != cudaSuccess ||
-        cudaMalloc(&m->sh_aos, p * 48 * 4) != cudaSuccess) {
+        cudaMalloc(&m->sh_aos, p * 48 * 4) != cudaSuccess || cudaMalloc(&m->smax2, p * 4) != cudaSuccess) {
         set_error("gsevt_map_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         gsevt_map_destroy(m);
         return GSEVT_ECUDA;
     }
-    m->bytes = p * (16 + 16 + 8 + 192 + 192);
+    m->bytes = p * (16 + 16 + 8 + 192 + 192 + 4);
     launch_pack_map(P, 16, xyz, scales, rotations, opacities, shs, scale_modifier, m->xyz_opacity, m->cov_a, m->cov_b,
-                    m->sh_planar, m->sh_aos, (cudaStream_t)stream);
+                    m->sh_planar, m->sh_aos, m->smax2, (cudaStream_t)stream);
     GSEVT_CUDA_OK(cudaPeekAtLastError());
     *out = m;
     return 0;
 }
 GSEVT_API void gsevt_map_destroy(GsevtMap* m) {
     if (!m) return;
-    cudaFree(m->xyz_opacity); cudaFree(m->cov_a); cudaFree(m->cov_b); cudaFree(m->sh_planar); cudaFree(m->sh_aos);
+    cudaFree(m->xyz_opacity); cudaFree(m->cov_a); cudaFree(m->cov_b); cudaFree(m->sh_planar); cudaFree(m->sh_aos); cudaFree(m->smax2);
     delete m;
 }
 GSEVT_API int32_t gsevt_map_size(const GsevtMap* m) { return m ? m->P : 0; }

@@ -31,27 +31,11 @@
 // gsevt_engine_binning() re-bases them to the reference's packed representation for the parity tests.
 #include "internal.h"
 #include "sortcore.cuh"
+#include "bucket_scatter.cuh"
 
 namespace gsevt {
 
 using namespace sortcore;
-
-namespace {
-
-// Which of a bucket's 2 x 2 tiles a rect covers, for the bucket at offset (dx, dy) inside the rect's bucket range:
-// ax = 2 * bx0 - x0 (0 or -1), wx = x1 - x0 (tiles), same in y.  bit ky * 2 + kx (== sortcore::cover_mask4).
-__device__ __forceinline__ uint32_t cover_bits(int a0, uint32_t w, uint32_t d) {
-    const uint32_t t = (uint32_t)(a0 + 2 * (int)d);
-    return (t < w ? 1u : 0u) | (t + 1u < w ? 2u : 0u);
-}
-template <int S>
-__device__ __forceinline__ uint32_t key_low(uint32_t id, int ax, uint32_t wx, int ay, uint32_t wy, uint32_t dx, uint32_t dy) {
-    if constexpr (S == 0) return id << 4;
-    const uint32_t cx = cover_bits(ax, wx, dx), cy = cover_bits(ay, wy, dy);
-    return (id << 4) | ((cy & 1u) ? cx : 0u) | ((cy & 2u) ? cx << 2 : 0u);
-}
-
-}  // namespace
 
 template <bool COUNT_ONLY, int S>
 __global__ void __launch_bounds__(256) bucket_scatter_kernel(BucketArgs a) {
@@ -63,69 +47,13 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(BucketArgs a) {
     const uint32_t view = j >= (uint32_t)a.P ? 1u : 0u;
     const uint32_t id = j - view * (uint32_t)a.P;
     const uint32_t sub = blockIdx.x & (GSEVT_BK_SUB - 1);          // this CTA's sub-segment of every bucket
-    const int x0 = (int)(rect & 255u), y0 = (int)(rect >> 8 & 255u), x1 = (int)(rect >> 16 & 255u), y1 = (int)(rect >> 24);
-    const int bx0 = x0 >> S, by0 = y0 >> S;                         // rect == 0: w = h = 0 below
-    const uint32_t w = rect ? (uint32_t)(((x1 - 1) >> S) + 1 - bx0) : 0u, h = rect ? (uint32_t)(((y1 - 1) >> S) + 1 - by0) : 0u;
-    const uint32_t cnt = w * h;
-    const int ax = 2 * bx0 - x0, ay = 2 * by0 - y0;
-    const uint32_t wx = (uint32_t)(x1 - x0), wy = (uint32_t)(y1 - y0);
-    // cursor of (bucket, sub) = cur0 + bucket offset * stride; bucket of the rect's first bucket:
-    const uint32_t b00 = view * (uint32_t)a.nb + (uint32_t)(by0 - a.by_origin) * (uint32_t)a.nbx + (uint32_t)bx0;
-    uint32_t* const cur0 = a.cursor + (size_t)sub * GSEVT_BK_CURSOR_STRIDE;
-    constexpr uint32_t CSTEP = GSEVT_BK_SUB * GSEVT_BK_CURSOR_STRIDE;
-    constexpr uint32_t SMALL = 4;
-    if (cnt && cnt <= SMALL) {
-        // the common case (a rect of 2 x 2 tiles meets 1..4 buckets): all atomics and segment look-ups in flight before
-        // the first store
-        uint32_t slot[SMALL], seg0[SMALL], segc[SMALL], lowk[SMALL];
-#pragma unroll
-        for (uint32_t t = 0; t < SMALL; t++) {
-            if (t > 0 && !__any_sync(__activemask(), cnt > t)) break;
-            const uint32_t dy = t == 0 ? 0u : (t >= w ? 1u : 0u) + (t >= 2u * w ? 1u : 0u) + (t >= 3u * w ? 1u : 0u);
-            const uint32_t dx = t - dy * w;
-            const uint32_t bb = b00 + dy * (uint32_t)a.nbx + dx;
-            if (t < cnt) {
-                slot[t] = atomicAdd(cur0 + (size_t)bb * CSTEP, 1u);
-                if constexpr (!COUNT_ONLY) {
-                    seg0[t] = __ldg(a.bk_start + bb);
-                    segc[t] = __ldg(a.bk_cap + bb);
-                    lowk[t] = key_low<S>(id, ax, wx, ay, wy, dx, dy);
-                }
-            }
-        }
-        if constexpr (!COUNT_ONLY) {
-#pragma unroll
-            for (uint32_t t = 0; t < SMALL; t++) {
-                if (t < cnt) {
-                    const uint32_t subcap = segc[t] / GSEVT_BK_SUB;
-                    if (slot[t] < subcap) a.keys[seg0[t] + sub * subcap + slot[t]] = ((uint64_t)depth << 32) | lowk[t];
-                    else *a.overflow = 1;
-                }
-            }
-        }
-    }
-    // large rects: the whole warp walks one pair's buckets, 32 per step, so that no lane loops over a screen-filling
-    // Gaussian alone
-    unsigned bigs = __ballot_sync(0xffffffffu, cnt > SMALL);
-    const uint32_t lane = threadIdx.x & 31u;
-    while (bigs) {
-        const int src = __ffs(bigs) - 1;
-        bigs &= bigs - 1;
-        const uint32_t b_cnt = __shfl_sync(0xffffffffu, cnt, src), b_w = __shfl_sync(0xffffffffu, w, src);
-        const uint32_t b_b00 = __shfl_sync(0xffffffffu, b00, src), b_wx = __shfl_sync(0xffffffffu, wx, src), b_wy = __shfl_sync(0xffffffffu, wy, src);
-        const int b_ax = __shfl_sync(0xffffffffu, ax, src), b_ay = __shfl_sync(0xffffffffu, ay, src);
-        const uint32_t b_depth = __shfl_sync(0xffffffffu, depth, src), b_id = __shfl_sync(0xffffffffu, id, src);
-        for (uint32_t t = lane; t < b_cnt; t += 32u) {
-            const uint32_t dy = t / b_w, dx = t - dy * b_w;
-            const uint32_t bb = b_b00 + dy * (uint32_t)a.nbx + dx;
-            const uint32_t slot = atomicAdd(cur0 + (size_t)bb * CSTEP, 1u);
-            if constexpr (!COUNT_ONLY) {
-                const uint32_t subcap = __ldg(a.bk_cap + bb) / GSEVT_BK_SUB;
-                if (slot < subcap) a.keys[__ldg(a.bk_start + bb) + sub * subcap + slot] = ((uint64_t)b_depth << 32) | key_low<S>(b_id, b_ax, b_wx, b_ay, b_wy, dx, dy);
-                else *a.overflow = 1;
-            }
-        }
-    }
+    uint32_t* const cur0 = a.cursor + (size_t)sub * GSEVT_BK_CURSOR_STRIDE;   // cursor of (bucket, sub) = cur0 + bucket * CSTEP
+    bscatter::Pair p;
+    bscatter::prepare<S>(a, view, rect, p);
+    // the common case (a rect of 2 x 2 tiles meets 1..4 buckets): all atomics in flight before the first store
+    bscatter::issue_small(a, cur0, p);
+    if constexpr (!COUNT_ONLY) bscatter::finish_small<S>(a, sub, p, depth, id);
+    bscatter::big_rects<COUNT_ONLY, S>(a, cur0, sub, p, depth, id);
 }
 
 // ---- per-bucket sort + tile lists -------------------------------------------------------------------

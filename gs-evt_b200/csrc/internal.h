@@ -102,6 +102,8 @@ struct PreMapArgs {
     const float4* cov3D_a;
     const float2* cov3D_b;
     const float* sh_planar;   // [48][P]
+    const float* smax2;       // [P] largest eigenvalue of the 3-D covariance (strip pre-test of the screen-tile split)
+    int split_pretest;        // run the strip pre-test (the engine's strip is a proper part of the tile grid; needs ctl + smax2)
     // per pair in index order (padded to preprocess_map_raw_items): tile rect x0 | y0<<8 | x1<<16 | y1<<24, 0 = not visible
     // (culled, or outside this engine's strip), and the float bits of the view depth — what the bucket scatter reads
     uint32_t* rect_raw;
@@ -115,7 +117,7 @@ size_t preprocess_map_raw_items(int P);
 void launch_mark_visible(int P, const float* means, const float* view, uint8_t* present, cudaStream_t s);
 void launch_pack_map(int P, int M, const float* xyz, const float* scales, const float* rots, const float* opac,
                      const float* shs, float mod, float4* xyz_opacity, float4* cov_a, float2* cov_b, float* sh_planar,
-                     float* sh_aos, cudaStream_t s);
+                     float* sh_aos, float* smax2, cudaStream_t s);
 // Fills a ViewParams from the operator's device-side matrices.
 void launch_build_view_params(ViewParams* out, const float* view, const float* proj, const float* proj_raw,
                               const float* campos, const float* vel, const float* vel_inv, const float* bg,

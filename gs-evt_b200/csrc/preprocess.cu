@@ -8,6 +8,7 @@
 // HBM-bound: grid = ceil(P/256) x 256 threads, all per-Gaussian loads coalesced (AoS inputs are
 // staged through shared memory in 16-byte vectors; planar SH is read as 48 coalesced lines per warp).
 #include <cstdlib>
+#include <cstring>
 #include "internal.h"
 
 namespace gsevt {
@@ -136,6 +137,38 @@ void launch_preprocess_aos(const PreAosArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Engine path: packed map, two views per thread.
 // ------------------------------------------------------------------------------------------------
+// Screen-tile split: can this Gaussian's tile rect reach tile rows [sy0, sy1) in this view?  A CONSERVATIVE test on 20
+// bytes (position + the largest eigenvalue of the 3-D covariance, precomputed when the map is packed) and ~40
+// instructions, run before the 24 bytes of covariance are even loaded: the rows a rect touches are
+// [trunc((my - r) / 16), trunc((my + r + 15) / 16)) with r = ceil(3 sqrt(lambda_max(cov2D))), and
+// lambda_max(J W S W^T J^T + 0.3 I) <= lambda_max(J J^T) lambda_max(S) + 0.3 for the rotation W, so
+// r <= 3 sqrt(lambda_max(J J^T) smax2 + 0.3) + 1 with the Jacobian of ewa_forward (same clamp of x/z, y/z to 1.3 tan).
+// The pixel row comes from the view-space point directly (the reference goes through the projection matrix: the two
+// agree to ~1e-3 px) — a pixel of slack and 0.1 % on the eigenvalue cover the rounding.  "false" therefore implies the
+// exact path would have produced an empty strip rect; on a rank of an 8-way split 80-90 % of the map takes this exit and
+// the replicated part of the projection shrinks from two EWA projections per Gaussian to this test.
+__device__ __forceinline__ bool strip_may_touch(const ViewParams& vp, float px, float py, float pz, float smax2, float row0_px,
+                                                float row1_px) {
+    const float tz = affine3r(vp.view[2], vp.view[6], vp.view[10], vp.view[14], px, py, pz);   // same value as the exact path
+    if (!(tz > 0.2f)) return false;
+    const float tx = vp.view[0] * px + vp.view[4] * py + vp.view[8] * pz + vp.view[12];
+    const float ty = vp.view[1] * px + vp.view[5] * py + vp.view[9] * pz + vp.view[13];
+    const float iz = 1.0f / tz;
+    const float limx = 1.3f * vp.tanfovx, limy = 1.3f * vp.tanfovy;
+    const float cx = fminf(fmaxf(tx * iz, -limx), limx), cy = fminf(fmaxf(ty * iz, -limy), limy);
+    const float j00 = vp.focal_x * iz, j11 = vp.focal_y * iz, j02 = -cx * j00, j12 = -cy * j11;
+    const float ja = j00 * j00 + j02 * j02, jc = j11 * j11 + j12 * j12, jb = j02 * j12;
+    const float mid = 0.5f * (ja + jc), dif = 0.5f * (ja - jc);
+    const float lamJ = mid + sqrtf(dif * dif + jb * jb);
+    const float r = 3.0f * sqrtf(lamJ * smax2 * 1.001f + 0.3f) + 2.0f;
+    const float my = (ty * iz / vp.tanfovy + 1.0f) * (0.5f * (float)vp.H) - 0.5f;
+    return !(my + r + 15.0f < row0_px) && !(my - r >= row1_px);
+}
+
+// (Measured and dropped, round 2: running the bucket scatter of bucketbin.cu INSIDE this kernel — cursor atomics issued as
+// soon as the two rects are known, SH evaluation while they are in flight, keys written at the end.  126 registers, and
+// the stage took 0.149 ms against 0.081 + 0.055 ms for the two kernels: the atomics' latency was already hidden by the
+// scatter kernel's own occupancy, and the heavy kernel lost more to its third live context than the launch saved.)
 template <int D, int MINB>
 __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a) {
     if (a.ctl && a.ctl->level_done) return;
@@ -144,6 +177,17 @@ __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a)
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= a.P) return;
     const float4 xo = __ldg(a.xyz_opacity + idx);
+    if (a.split_pretest) {
+        // screen-tile split: most of the map cannot reach this engine's strip — decide that on 20 bytes
+        const float smax2 = __ldg(a.smax2 + idx);
+        const float row0 = (float)(a.ctl->strip_y0 * GSEVT_TILE), row1 = (float)(a.ctl->strip_y1 * GSEVT_TILE);
+        if (!strip_may_touch(s_vp[0], xo.x, xo.y, xo.z, smax2, row0, row1) &&
+            !strip_may_touch(s_vp[1], xo.x, xo.y, xo.z, smax2, row0, row1)) {
+            a.rect_raw[idx] = 0u;
+            a.rect_raw[(size_t)a.P + idx] = 0u;
+            return;
+        }
+    }
     float cov[6];
     {
         const float4 c0 = __ldg(a.cov3D_a + idx);
@@ -255,11 +299,16 @@ __global__ void pack_map_kernel(int P, int M, const float* __restrict__ xyz, con
                                 const float* __restrict__ rots, const float* __restrict__ opac,
                                 const float* __restrict__ shs, float mod, float4* __restrict__ xyz_opacity,
                                 float4* __restrict__ cov_a, float2* __restrict__ cov_b, float* __restrict__ sh_planar,
-                                float* __restrict__ sh_aos) {
+                                float* __restrict__ sh_aos, float* __restrict__ smax2) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const size_t i = idx;
     xyz_opacity[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], opac[i]);
+    {
+        // largest eigenvalue of R S^2 R^T = (largest scale x modifier)^2, rounded up: the strip pre-test's radius bound
+        const float sm = fmaxf(fmaxf(fabsf(scales[3 * i]), fabsf(scales[3 * i + 1])), fabsf(scales[3 * i + 2])) * fabsf(mod);
+        smax2[i] = sm * sm * 1.0001f;
+    }
     float cov[6];
     cov3d_from_scale_rot(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2], mod, rots[4 * i], rots[4 * i + 1],
                          rots[4 * i + 2], rots[4 * i + 3], cov);
@@ -275,10 +324,10 @@ __global__ void pack_map_kernel(int P, int M, const float* __restrict__ xyz, con
 
 void launch_pack_map(int P, int M, const float* xyz, const float* scales, const float* rots, const float* opac,
                      const float* shs, float mod, float4* xyz_opacity, float4* cov_a, float2* cov_b, float* sh_planar,
-                     float* sh_aos, cudaStream_t s) {
+                     float* sh_aos, float* smax2, cudaStream_t s) {
     if (P <= 0) return;
     pack_map_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, M, xyz, scales, rots, opac, shs, mod, xyz_opacity, cov_a, cov_b,
-                                                   sh_planar, sh_aos);
+                                                   sh_planar, sh_aos, smax2);
 }
 
 }  // namespace gsevt
