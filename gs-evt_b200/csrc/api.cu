@@ -406,6 +406,8 @@ struct GsevtEngine {
     uint8_t* clamped = nullptr;
     uint32_t* active_list = nullptr;   // [2P] compacted pairs with a gradient
     uint32_t* active_count = nullptr;
+    uint32_t* vis_list = nullptr;        // screen-tile split: visible pairs of the iteration (split projection kernel -> scatter)
+    uint32_t* vis_count = nullptr;
     // binning (bucketbin.cu): bucket grid of the current level / strip, per-bucket segment table, key segments, tile lists
     int bin_mode = 0;                    // gsevt_engine_set_binning: 0 automatic, 1 buckets of one tile, 2 buckets of 2 x 2 tiles
     int bk_shift = 0, bk_nbx = 0, bk_nby = 0, bk_by_origin = 0, bk_nb = 0;
@@ -517,13 +519,19 @@ static void projection_colmajor(double znear, double zfar, double fovX, double f
         for (int r = 0; r < 4; r++) out[4 * c + r] = P[r][c];
 }
 
+// Screen-tile split with a strip that is a proper part of the tile grid: the projection runs the strip pre-test + survivor
+// queue kernel and hands the scatter a list of visible pairs (preprocess.cu, bucketbin.cu).
+static bool split_kernels(const GsevtEngine* e) {
+    return e->split_n > 1 && e->vis_list && e->map->smax2 && (e->strip_y0 > 0 || e->strip_y1 < e->lv[e->cur_level].gy);
+}
+
 static PreMapArgs premap_args(GsevtEngine* e) {
     const GsevtMap* m = e->map;
     PreMapArgs pa;
     pa.P = m->P; pa.D = m->D; pa.views = e->views; pa.ctl = e->ctl;
-    pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar; pa.smax2 = m->smax2;
-    pa.split_pretest = (e->split_n > 1 || getenv("GSEVT_STRIP_PRETEST")) && m->smax2 &&
-                       (e->strip_y0 > 0 || e->strip_y1 < e->lv[e->cur_level].gy) ? 1 : 0;
+    pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar; pa.sh_aos = m->sh_aos; pa.smax2 = m->smax2;
+    pa.split_pretest = split_kernels(e) ? 1 : 0;
+    pa.vis_list = e->vis_list; pa.vis_count = e->vis_count;
     pa.rect_raw = e->rect_raw; pa.depth_raw = e->depth_raw; pa.clamped = e->clamped;
     pa.rec = e->rec; pa.grad8 = e->grad8;
     return pa;
@@ -539,6 +547,8 @@ static BucketArgs bucket_args(GsevtEngine* e) {
     b.keys = e->bk_keys; b.keys2 = e->bk_keys2; b.vals = e->vals; b.ranges = e->ranges; b.hit_base = e->hit_base;
     b.bk_order = e->bk_order; b.smem_elems = e->bk_smem_elems; b.smem_bins = e->bk_smem_bins; b.smem_bytes = e->bk_smem_bytes;
     b.overflow = e->overflow; b.ctl = e->ctl;
+    b.sparse = split_kernels(e) ? 1 : 0;
+    b.vis_list = e->vis_list; b.vis_count = b.sparse ? e->vis_count : nullptr;
     return b;
 }
 
@@ -834,9 +844,14 @@ static int probe_buckets(GsevtEngine* e, cudaStream_t s, std::vector<uint32_t>& 
     launch_preprocess_map(premap_args(e), s);
     const int nc = 2 * e->bk_nb * GSEVT_BK_SUB;
     counts.assign((size_t)(nc > 0 ? nc : 1), 0u);
-    if (nc <= 0) return 0;
+    if (nc <= 0) {
+        if (e->vis_count) GSEVT_CUDA_OK(cudaMemsetAsync(e->vis_count, 0, 4, s));
+        return 0;
+    }
     launch_bucket_scatter(bucket_args(e), true, s);
     launch_bucket_counts(nc, e->bk_cursor, e->bk_counts, s);
+    // (split mode) the probe's projection listed its visible pairs, and no bucket_sort follows to consume the list
+    if (e->vis_count) GSEVT_CUDA_OK(cudaMemsetAsync(e->vis_count, 0, 4, s));
     GSEVT_CUDA_OK(cudaMemsetAsync(e->bk_cursor, 0, (size_t)nc * GSEVT_BK_CURSOR_STRIDE * 4, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // counts is pageable host memory: wait first (see gsevt_engine_status)
     GSEVT_CUDA_OK(cudaMemcpyAsync(counts.data(), e->bk_counts, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
@@ -1321,6 +1336,11 @@ GSEVT_API int gsevt_engine_split_attach(GsevtEngine* e, int32_t rank, int32_t n,
         h.box[r] = (MailBox*)boxes[r];
     }
     if (!e->comm) { int rc = dev_alloc(e, &e->comm, 1); if (rc) return rc; }
+    if (!e->vis_list) {
+        int rc = dev_alloc(e, &e->vis_list, 2 * (size_t)e->map->P) | dev_alloc(e, &e->vis_count, 1);
+        if (rc) return rc;
+        GSEVT_CUDA_OK(cudaMemset(e->vis_count, 0, 4));
+    }
     GSEVT_CUDA_OK(cudaMemcpy(e->comm, &h, sizeof(h), cudaMemcpyHostToDevice));
     // a fresh group starts at sequence 0 with clean slots (every rank attaches before any rank iterates:
     // the caller puts a barrier between attach and the first collective call)

@@ -80,14 +80,17 @@ __device__ __forceinline__ void finish_small(const BucketArgs& a, uint32_t sub, 
 }
 
 // large rects: the whole warp walks one pair's buckets, 32 per step, so that no lane loops over a screen-filling
-// Gaussian alone.  Every lane of the warp must call this (lanes without a large rect pass cnt <= SMALL).
+// Gaussian alone.  Every lane of the warp must call this (lanes without a large rect pass cnt <= SMALL).  `sub` is the
+// OWNER's sub-segment (it may differ from lane to lane when the pairs come from a list).
 template <bool COUNT_ONLY, int S>
-__device__ __forceinline__ void big_rects(const BucketArgs& a, uint32_t* cur0, uint32_t sub, const Pair& p, uint32_t depth, uint32_t id) {
+__device__ __forceinline__ void big_rects(const BucketArgs& a, uint32_t sub_mine, const Pair& p, uint32_t depth, uint32_t id) {
     unsigned bigs = __ballot_sync(0xffffffffu, p.cnt > SMALL);
     const uint32_t lane = threadIdx.x & 31u;
     while (bigs) {
         const int src = __ffs(bigs) - 1;
         bigs &= bigs - 1;
+        const uint32_t sub = __shfl_sync(0xffffffffu, sub_mine, src);
+        uint32_t* const cur0 = a.cursor + (size_t)sub * GSEVT_BK_CURSOR_STRIDE;
         const uint32_t b_cnt = __shfl_sync(0xffffffffu, p.cnt, src), b_w = __shfl_sync(0xffffffffu, p.w, src);
         const uint32_t b_b00 = __shfl_sync(0xffffffffu, p.b00, src), b_wx = __shfl_sync(0xffffffffu, p.wx, src), b_wy = __shfl_sync(0xffffffffu, p.wy, src);
         const int b_ax = __shfl_sync(0xffffffffu, p.ax, src), b_ay = __shfl_sync(0xffffffffu, p.ay, src);

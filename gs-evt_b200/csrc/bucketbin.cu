@@ -53,7 +53,32 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(BucketArgs a) {
     // the common case (a rect of 2 x 2 tiles meets 1..4 buckets): all atomics in flight before the first store
     bscatter::issue_small(a, cur0, p);
     if constexpr (!COUNT_ONLY) bscatter::finish_small<S>(a, sub, p, depth, id);
-    bscatter::big_rects<COUNT_ONLY, S>(a, cur0, sub, p, depth, id);
+    bscatter::big_rects<COUNT_ONLY, S>(a, sub, p, depth, id);
+}
+
+// Screen-tile split: 80-90 % of a rank's pairs are empty, so the scatter walks the list of visible pairs the split
+// projection kernel wrote (preprocess.cu) instead of the dense rect array.  Grid-stride over the device-side count.
+template <int S>
+__global__ void __launch_bounds__(256) bucket_scatter_list_kernel(BucketArgs a) {
+    if (a.ctl && a.ctl->level_done) return;
+    const uint32_t n = *a.vis_count;
+    for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {   // uniform per CTA: whole warps stay for big_rects
+        const uint32_t t = base + threadIdx.x;
+        const uint32_t j = t < n ? __ldg(a.vis_list + t) : 0u;
+        // the sub-segment the dense kernel would have used for this pair (its CTA index there): the segments were sized
+        // from a dense count-only run, so every (bucket, sub-segment) receives exactly the pairs it was sized for
+        const uint32_t sub = (j >> 8) & (GSEVT_BK_SUB - 1);
+        uint32_t* const cur0 = a.cursor + (size_t)sub * GSEVT_BK_CURSOR_STRIDE;
+        const uint32_t rect = t < n ? __ldg(a.rect_raw + j) : 0u;
+        const uint32_t depth = t < n ? __ldg(a.depth_raw + j) : 0u;
+        const uint32_t view = j >= (uint32_t)a.P ? 1u : 0u;
+        const uint32_t id = j - view * (uint32_t)a.P;
+        bscatter::Pair p;
+        bscatter::prepare<S>(a, view, rect, p);
+        bscatter::issue_small(a, cur0, p);
+        bscatter::finish_small<S>(a, sub, p, depth, id);
+        bscatter::big_rects<false, S>(a, sub, p, depth, id);
+    }
 }
 
 // ---- per-bucket sort + tile lists -------------------------------------------------------------------
@@ -122,6 +147,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) bucket_sort_kernel(BucketArgs
     __shared__ uint32_t s_red[2][NW];
     __shared__ uint32_t s_wc[NW][NT];
     __shared__ uint32_t s_tot[NT];
+    if (a.vis_count && blockIdx.x == 0 && threadIdx.x == 0) *a.vis_count = 0u;   // consumed by this iteration's scatter
     const uint32_t b = a.bk_order ? a.bk_order[blockIdx.x] : blockIdx.x;   // largest buckets first
     const uint32_t start = a.bk_start[b], cap = a.bk_cap[b], subcap = cap / R;
     if (threadIdx.x < R) {
@@ -357,6 +383,10 @@ void launch_bucket_scatter(const BucketArgs& a, bool count_only, cudaStream_t s)
     if (count_only) {
         if (a.s == 0) bucket_scatter_kernel<true, 0><<<blocks, 256, 0, s>>>(a);
         else bucket_scatter_kernel<true, 1><<<blocks, 256, 0, s>>>(a);
+    } else if (a.sparse) {
+        const unsigned lb = blocks < 148u * 8u ? blocks : 148u * 8u;   // 8 CTAs per SM, grid-stride over the visible pairs
+        if (a.s == 0) bucket_scatter_list_kernel<0><<<lb, 256, 0, s>>>(a);
+        else bucket_scatter_list_kernel<1><<<lb, 256, 0, s>>>(a);
     } else {
         if (a.s == 0) bucket_scatter_kernel<false, 0><<<blocks, 256, 0, s>>>(a);
         else bucket_scatter_kernel<false, 1><<<blocks, 256, 0, s>>>(a);

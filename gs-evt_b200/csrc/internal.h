@@ -102,7 +102,10 @@ struct PreMapArgs {
     const float4* cov3D_a;
     const float2* cov3D_b;
     const float* sh_planar;   // [48][P]
+    const float* sh_aos;      // [P][48] (split kernel: scattered survivors)
     const float* smax2;       // [P] largest eigenvalue of the 3-D covariance (strip pre-test of the screen-tile split)
+    uint32_t* vis_list;       // split kernel: the visible pairs (view * P + Gaussian), unordered, [2P]
+    uint32_t* vis_count;      // split kernel: their number (zero on entry; bucket_sort clears it for the next iteration)
     int split_pretest;        // run the strip pre-test (the engine's strip is a proper part of the tile grid; needs ctl + smax2)
     // per pair in index order (padded to preprocess_map_raw_items): tile rect x0 | y0<<8 | x1<<16 | y1<<24, 0 = not visible
     // (culled, or outside this engine's strip), and the float bits of the view depth — what the bucket scatter reads
@@ -162,6 +165,9 @@ struct BucketArgs {
     const uint32_t* bk_order;   // [2 nb] buckets in the order the sort CTAs take them (largest first), or NULL
     int smem_elems, smem_bins;  // shared memory of a sort CTA: keys it can hold, depth bins (see bucket_sort_smem)
     size_t smem_bytes;
+    int sparse;                 // screen-tile split: the scatter walks vis_list (written by the split projection kernel)
+    const uint32_t* vis_list;   // [vis_count] visible pairs, unordered
+    uint32_t* vis_count;
     int* overflow;
     const EngineCtl* ctl;
 };

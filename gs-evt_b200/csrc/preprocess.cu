@@ -169,25 +169,12 @@ __device__ __forceinline__ bool strip_may_touch(const ViewParams& vp, float px, 
 // soon as the two rects are known, SH evaluation while they are in flight, keys written at the end.  126 registers, and
 // the stage took 0.149 ms against 0.081 + 0.055 ms for the two kernels: the atomics' latency was already hidden by the
 // scatter kernel's own occupancy, and the heavy kernel lost more to its third live context than the launch saved.)
-template <int D, int MINB>
-__global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a) {
-    if (a.ctl && a.ctl->level_done) return;
-    __shared__ ViewParams s_vp[2];
-    load_views(s_vp, a.views, 2);
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= a.P) return;
-    const float4 xo = __ldg(a.xyz_opacity + idx);
-    if (a.split_pretest) {
-        // screen-tile split: most of the map cannot reach this engine's strip — decide that on 20 bytes
-        const float smax2 = __ldg(a.smax2 + idx);
-        const float row0 = (float)(a.ctl->strip_y0 * GSEVT_TILE), row1 = (float)(a.ctl->strip_y1 * GSEVT_TILE);
-        if (!strip_may_touch(s_vp[0], xo.x, xo.y, xo.z, smax2, row0, row1) &&
-            !strip_may_touch(s_vp[1], xo.x, xo.y, xo.z, smax2, row0, row1)) {
-            a.rect_raw[idx] = 0u;
-            a.rect_raw[(size_t)a.P + idx] = 0u;
-            return;
-        }
-    }
+//
+// One Gaussian, both views: everything from the covariance load to the records.  AOS selects where the SH coefficients
+// come from: the planar copy (dense kernel: 48 coalesced lines per warp) or the per-Gaussian copy (split kernel, whose
+// survivors are scattered over the map: 192 contiguous bytes per lane instead of 48 lone sectors).
+template <int D, bool AOS>
+__device__ __forceinline__ uint32_t project_store(const PreMapArgs& a, const ViewParams* s_vp, int idx, const float4 xo) {
     float cov[6];
     {
         const float4 c0 = __ldg(a.cov3D_a + idx);
@@ -218,15 +205,27 @@ __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a)
         a.rect_raw[j] = ok[v] ? o[v].rect : 0u;
         a.depth_raw[j] = __float_as_uint(o[v].depth);
     }
-    if (!ok[0] && !ok[1]) return;
-    // SH -> RGB for both views from ONE pass over the planar coefficients (coalesced 128-byte lines).  The degree
-    // is a template parameter so that all (D+1)^2 * 3 loads are issued back to back, unconditionally.
-    const float* sh = a.sh_planar + idx;
+    if (!ok[0] && !ok[1]) return 0u;
+    // SH -> RGB for both views from ONE pass over the coefficients.  The degree is a template parameter so that all
+    // (D+1)^2 * 3 loads are issued back to back, unconditionally.
     const size_t P = (size_t)a.P;
     constexpr int NB = (D + 1) * (D + 1);
     float coef[NB * 3];
+    if constexpr (AOS) {
+        const float4* sh4 = reinterpret_cast<const float4*>(a.sh_aos + (size_t)idx * 48);
 #pragma unroll
-    for (int k = 0; k < NB * 3; k++) coef[k] = __ldg(sh + (size_t)k * P);
+        for (int q = 0; q < (NB * 3 + 3) / 4; q++) {
+            const float4 c = __ldg(sh4 + q);
+            coef[4 * q] = c.x;
+            if (4 * q + 1 < NB * 3) coef[4 * q + 1] = c.y;
+            if (4 * q + 2 < NB * 3) coef[4 * q + 2] = c.z;
+            if (4 * q + 3 < NB * 3) coef[4 * q + 3] = c.w;
+        }
+    } else {
+        const float* sh = a.sh_planar + idx;
+#pragma unroll
+        for (int k = 0; k < NB * 3; k++) coef[k] = __ldg(sh + (size_t)k * P);
+    }
     float basis[2][16];
 #pragma unroll
     for (int v = 0; v < 2; v++)
@@ -257,12 +256,115 @@ __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a)
         a.rec[2 * j + 1] = make_float4(o[v].C, xo.w, gray, o[v].depth);
         // (the blend-backward accumulators grad8 are all-zero here: geom_bwd clears what it consumes)
     }
+    return (ok[0] ? 1u : 0u) | (ok[1] ? 2u : 0u);
+}
+
+template <int D, int MINB>
+__global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a) {
+    if (a.ctl && a.ctl->level_done) return;
+    __shared__ ViewParams s_vp[2];
+    load_views(s_vp, a.views, 2);
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= a.P) return;
+    project_store<D, false>(a, s_vp, idx, __ldg(a.xyz_opacity + idx));
+}
+
+// Screen-tile split: the strip pre-test only pays when whole WARPS skip the projection, and in a map without spatial order
+// every warp holds a few Gaussians of every strip.  So a CTA first runs the pre-test over SPLIT_CHUNKS x 256 consecutive
+// Gaussians (20 bytes and ~40 instructions each, the failures' rect words zeroed on the spot) and queues the survivors in
+// shared memory; then it projects the queue 256 at a time with full warps.  On a rank of an 8-way split ~14 % of the
+// map survives: the replicated part of the iteration falls from two EWA projections per Gaussian to the pre-test.
+constexpr int SPLIT_CHUNKS = 16;
+
+template <int D>
+__global__ void __launch_bounds__(256, 2) preprocess_map_split_kernel(PreMapArgs a, int chunks) {
+    if (a.ctl->level_done) return;
+    __shared__ ViewParams s_vp[2];
+    __shared__ int s_queue[SPLIT_CHUNKS * 256];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    load_views(s_vp, a.views, 2);
+    __syncthreads();
+    const float row0 = (float)(a.ctl->strip_y0 * GSEVT_TILE), row1 = (float)(a.ctl->strip_y1 * GSEVT_TILE);
+    const int base = blockIdx.x * (chunks * 256) + threadIdx.x;
+    const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+#pragma unroll 4
+    for (int c = 0; c < chunks; c++) {
+        const int idx = base + c * 256;
+        bool pass = false;
+        if (idx < a.P) {
+            const float4 xo = __ldg(a.xyz_opacity + idx);
+            const float smax2 = __ldg(a.smax2 + idx);
+            pass = strip_may_touch(s_vp[0], xo.x, xo.y, xo.z, smax2, row0, row1) ||
+                   strip_may_touch(s_vp[1], xo.x, xo.y, xo.z, smax2, row0, row1);
+            if (!pass) {
+                a.rect_raw[idx] = 0u;
+                a.rect_raw[(size_t)a.P + idx] = 0u;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (bal) {
+            int pos = 0;
+            if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_n, __popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (pass) s_queue[pos + __popc(bal & lt)] = idx;
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    // project the queue with full warps; the visible (view, Gaussian) pairs of every round go to the global list the
+    // bucket scatter walks in split mode (one reservation per round; the list is unordered, like the scatter itself)
+    __shared__ uint32_t s_wn[8];
+    __shared__ uint32_t s_base;
+    for (int t0 = 0; t0 < n; t0 += 256) {
+        const int t = t0 + (int)threadIdx.x;
+        uint32_t vis = 0;
+        int idx = 0;
+        if (t < n) {
+            idx = s_queue[t];
+            vis = project_store<D, true>(a, s_vp, idx, __ldg(a.xyz_opacity + idx));
+        }
+        const uint32_t mine = (vis & 1u) + (vis >> 1);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= (unsigned)o) incl += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_wn[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const uint32_t c = s_wn[w]; s_wn[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(a.vis_count, tot) : 0u;
+        }
+        __syncthreads();
+        uint32_t pos = s_base + s_wn[threadIdx.x >> 5] + incl - mine;
+        if (vis & 1u) a.vis_list[pos++] = (uint32_t)idx;
+        if (vis & 2u) a.vis_list[pos] = (uint32_t)a.P + (uint32_t)idx;
+        __syncthreads();   // s_wn / s_base are rewritten by the next round
+    }
 }
 
 size_t preprocess_map_raw_items(int P) { return (2 * (size_t)P + 1023) / 1024 * 1024; }
 
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
+    if (a.split_pretest) {
+        // chunks of 256 Gaussians per CTA: as many as the queue holds on large maps (survivors fill whole warps), fewer on
+        // small ones so that the grid still covers the 148 SMs a few times
+        int chunks = a.P / (256 * 148 * 4);
+        chunks = chunks < 2 ? 2 : (chunks > SPLIT_CHUNKS ? SPLIT_CHUNKS : chunks);
+        const int blocks = (a.P + chunks * 256 - 1) / (chunks * 256);
+        switch (a.D) {
+            case 0: preprocess_map_split_kernel<0><<<blocks, 256, 0, s>>>(a, chunks); break;
+            case 1: preprocess_map_split_kernel<1><<<blocks, 256, 0, s>>>(a, chunks); break;
+            case 2: preprocess_map_split_kernel<2><<<blocks, 256, 0, s>>>(a, chunks); break;
+            default: preprocess_map_split_kernel<3><<<blocks, 256, 0, s>>>(a, chunks); break;
+        }
+        return;
+    }
     const int blocks = (a.P + 255) / 256;
     // SH degree 3 needs 105 registers without spills (2 CTAs per SM) or 80 with 56 B of spills (3 CTAs per SM): the
     // former measured 2.3 us faster (0.0985 vs 0.1008 ms for the stage, A/B/A/B on one box); GSEVT_PRE_MINB=3 selects the
