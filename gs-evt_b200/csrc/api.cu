@@ -407,7 +407,8 @@ struct GsevtEngine {
     uint32_t* active_list = nullptr;   // [2P] compacted pairs with a gradient
     uint32_t* active_count = nullptr;
     uint32_t* vis_list = nullptr;        // screen-tile split: visible pairs of the iteration (split projection kernel -> scatter)
-    uint32_t* vis_count = nullptr;
+    uint32_t* vis_count = nullptr;       // vis_count[0] = visible pairs, vis_count[1] = survivors of the strip pre-test
+    uint32_t* surv_list = nullptr;
     // binning (bucketbin.cu): bucket grid of the current level / strip, per-bucket segment table, key segments, tile lists
     int bin_mode = 0;                    // gsevt_engine_set_binning: 0 automatic, 1 buckets of one tile, 2 buckets of 2 x 2 tiles
     int bk_shift = 0, bk_nbx = 0, bk_nby = 0, bk_by_origin = 0, bk_nb = 0;
@@ -532,6 +533,7 @@ static PreMapArgs premap_args(GsevtEngine* e) {
     pa.xyz_opacity = m->xyz_opacity; pa.cov3D_a = m->cov_a; pa.cov3D_b = m->cov_b; pa.sh_planar = m->sh_planar; pa.sh_aos = m->sh_aos; pa.smax2 = m->smax2;
     pa.split_pretest = split_kernels(e) ? 1 : 0;
     pa.vis_list = e->vis_list; pa.vis_count = e->vis_count;
+    pa.surv_list = e->surv_list; pa.surv_count = e->vis_count ? e->vis_count + 1 : nullptr;
     pa.rect_raw = e->rect_raw; pa.depth_raw = e->depth_raw; pa.clamped = e->clamped;
     pa.rec = e->rec; pa.grad8 = e->grad8;
     return pa;
@@ -549,6 +551,7 @@ static BucketArgs bucket_args(GsevtEngine* e) {
     b.overflow = e->overflow; b.ctl = e->ctl;
     b.sparse = split_kernels(e) ? 1 : 0;
     b.vis_list = e->vis_list; b.vis_count = b.sparse ? e->vis_count : nullptr;
+    b.surv_count = b.sparse ? e->vis_count + 1 : nullptr;
     return b;
 }
 
@@ -845,13 +848,13 @@ static int probe_buckets(GsevtEngine* e, cudaStream_t s, std::vector<uint32_t>& 
     const int nc = 2 * e->bk_nb * GSEVT_BK_SUB;
     counts.assign((size_t)(nc > 0 ? nc : 1), 0u);
     if (nc <= 0) {
-        if (e->vis_count) GSEVT_CUDA_OK(cudaMemsetAsync(e->vis_count, 0, 4, s));
+        if (e->vis_count) GSEVT_CUDA_OK(cudaMemsetAsync(e->vis_count, 0, 8, s));
         return 0;
     }
     launch_bucket_scatter(bucket_args(e), true, s);
     launch_bucket_counts(nc, e->bk_cursor, e->bk_counts, s);
     // (split mode) the probe's projection listed its visible pairs, and no bucket_sort follows to consume the list
-    if (e->vis_count) GSEVT_CUDA_OK(cudaMemsetAsync(e->vis_count, 0, 4, s));
+    if (e->vis_count) GSEVT_CUDA_OK(cudaMemsetAsync(e->vis_count, 0, 8, s));
     GSEVT_CUDA_OK(cudaMemsetAsync(e->bk_cursor, 0, (size_t)nc * GSEVT_BK_CURSOR_STRIDE * 4, s));
     GSEVT_CUDA_OK(cudaStreamSynchronize(s));   // counts is pageable host memory: wait first (see gsevt_engine_status)
     GSEVT_CUDA_OK(cudaMemcpyAsync(counts.data(), e->bk_counts, (size_t)nc * 4, cudaMemcpyDeviceToHost, s));
@@ -1337,9 +1340,10 @@ GSEVT_API int gsevt_engine_split_attach(GsevtEngine* e, int32_t rank, int32_t n,
     }
     if (!e->comm) { int rc = dev_alloc(e, &e->comm, 1); if (rc) return rc; }
     if (!e->vis_list) {
-        int rc = dev_alloc(e, &e->vis_list, 2 * (size_t)e->map->P) | dev_alloc(e, &e->vis_count, 1);
+        int rc = dev_alloc(e, &e->vis_list, 2 * (size_t)e->map->P) | dev_alloc(e, &e->vis_count, 2) |
+                 dev_alloc(e, &e->surv_list, (size_t)e->map->P);
         if (rc) return rc;
-        GSEVT_CUDA_OK(cudaMemset(e->vis_count, 0, 4));
+        GSEVT_CUDA_OK(cudaMemset(e->vis_count, 0, 8));
     }
     GSEVT_CUDA_OK(cudaMemcpy(e->comm, &h, sizeof(h), cudaMemcpyHostToDevice));
     // a fresh group starts at sequence 0 with clean slots (every rank attaches before any rank iterates:
@@ -1373,9 +1377,9 @@ GSEVT_API int gsevt_engine_set_binning(GsevtEngine* e, int32_t mode) {
 
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e) {
     // preprocess_map, bucket_scatter, bucket_sort, blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, engine_update:
-    // all of them this library's own kernels
-    (void)e;
-    return 9;
+    // all of them this library's own kernels; the screen-tile split runs the projection as two kernels (strip pre-test +
+    // projection of the survivors)
+    return e && split_kernels(e) ? 10 : 9;
 }
 
 }  // extern "C"

@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) bucket_sort_kernel(BucketArgs
     __shared__ uint32_t s_red[2][NW];
     __shared__ uint32_t s_wc[NW][NT];
     __shared__ uint32_t s_tot[NT];
-    if (a.vis_count && blockIdx.x == 0 && threadIdx.x == 0) *a.vis_count = 0u;   // consumed by this iteration's scatter
+    if (a.vis_count && blockIdx.x == 0 && threadIdx.x == 0) {   // split mode: both lists were consumed earlier in this iteration
+        *a.vis_count = 0u;
+        *a.surv_count = 0u;
+    }
     const uint32_t b = a.bk_order ? a.bk_order[blockIdx.x] : blockIdx.x;   // largest buckets first
     const uint32_t start = a.bk_start[b], cap = a.bk_cap[b], subcap = cap / R;
     if (threadIdx.x < R) {

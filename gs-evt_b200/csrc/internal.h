@@ -104,6 +104,8 @@ struct PreMapArgs {
     const float* sh_planar;   // [48][P]
     const float* sh_aos;      // [P][48] (split kernel: scattered survivors)
     const float* smax2;       // [P] largest eigenvalue of the 3-D covariance (strip pre-test of the screen-tile split)
+    uint32_t* surv_list;      // split kernels: Gaussians that passed the strip pre-test, unordered, [P]
+    uint32_t* surv_count;     // their number (zero on entry; bucket_sort clears it for the next iteration)
     uint32_t* vis_list;       // split kernel: the visible pairs (view * P + Gaussian), unordered, [2P]
     uint32_t* vis_count;      // split kernel: their number (zero on entry; bucket_sort clears it for the next iteration)
     int split_pretest;        // run the strip pre-test (the engine's strip is a proper part of the tile grid; needs ctl + smax2)
@@ -168,6 +170,7 @@ struct BucketArgs {
     int sparse;                 // screen-tile split: the scatter walks vis_list (written by the split projection kernel)
     const uint32_t* vis_list;   // [vis_count] visible pairs, unordered
     uint32_t* vis_count;
+    uint32_t* surv_count;       // (cleared together with vis_count)
     int* overflow;
     const EngineCtl* ctl;
 };

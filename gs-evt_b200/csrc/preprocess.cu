@@ -270,60 +270,85 @@ __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a)
 }
 
 // Screen-tile split: the strip pre-test only pays when whole WARPS skip the projection, and in a map without spatial order
-// every warp holds a few Gaussians of every strip.  So a CTA first runs the pre-test over SPLIT_CHUNKS x 256 consecutive
-// Gaussians (20 bytes and ~40 instructions each, the failures' rect words zeroed on the spot) and queues the survivors in
-// shared memory; then it projects the queue 256 at a time with full warps.  On a rank of an 8-way split ~14 % of the
-// map survives: the replicated part of the iteration falls from two EWA projections per Gaussian to the pre-test.
-constexpr int SPLIT_CHUNKS = 16;
+// every warp holds a few Gaussians of every strip.  Two kernels:
+//   strip_pretest_kernel          a light streaming pass (20 bytes and ~40 instructions per Gaussian and view, 8 CTAs per
+//                                 SM): the pre-test over the whole map, the failures' rect words zeroed on the spot, the
+//                                 survivors of every 2048 consecutive Gaussians queued in shared memory and appended to a
+//                                 global list with ONE reservation per CTA;
+//   preprocess_map_list_kernel    the full projection over that list with full warps (grid-stride over the device-side
+//                                 count; SH from the per-Gaussian copy, 192 contiguous bytes per lane), which also writes the
+//                                 list of visible pairs the bucket scatter walks in split mode.
+// On a rank of an 8-way split ~15 % of the map survives: the replicated part of the iteration falls from two EWA
+// projections per Gaussian to the pre-test.
+constexpr int PRETEST_PER_CTA = 2048;
 
-template <int D>
-__global__ void __launch_bounds__(256, 2) preprocess_map_split_kernel(PreMapArgs a, int chunks) {
+__global__ void __launch_bounds__(256) strip_pretest_kernel(PreMapArgs a) {
     if (a.ctl->level_done) return;
     __shared__ ViewParams s_vp[2];
-    __shared__ int s_queue[SPLIT_CHUNKS * 256];
-    __shared__ int s_n;
+    __shared__ int s_queue[PRETEST_PER_CTA];
+    __shared__ int s_n, s_base;
     if (threadIdx.x == 0) s_n = 0;
     load_views(s_vp, a.views, 2);
     __syncthreads();
     const float row0 = (float)(a.ctl->strip_y0 * GSEVT_TILE), row1 = (float)(a.ctl->strip_y1 * GSEVT_TILE);
-    const int base = blockIdx.x * (chunks * 256) + threadIdx.x;
+    const int base = blockIdx.x * PRETEST_PER_CTA + threadIdx.x;
     const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
-#pragma unroll 4
-    for (int c = 0; c < chunks; c++) {
-        const int idx = base + c * 256;
-        bool pass = false;
-        if (idx < a.P) {
-            const float4 xo = __ldg(a.xyz_opacity + idx);
-            const float smax2 = __ldg(a.smax2 + idx);
-            pass = strip_may_touch(s_vp[0], xo.x, xo.y, xo.z, smax2, row0, row1) ||
-                   strip_may_touch(s_vp[1], xo.x, xo.y, xo.z, smax2, row0, row1);
-            if (!pass) {
-                a.rect_raw[idx] = 0u;
-                a.rect_raw[(size_t)a.P + idx] = 0u;
-            }
+    for (int c0 = 0; c0 < PRETEST_PER_CTA / 256; c0 += 4) {
+        float4 xo[4];
+        float sm[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {   // four independent load pairs in flight per thread
+            const int idx = base + (c0 + u) * 256;
+            xo[u] = idx < a.P ? __ldg(a.xyz_opacity + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sm[u] = idx < a.P ? __ldg(a.smax2 + idx) : 0.f;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (bal) {
-            int pos = 0;
-            if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_n, __popc(bal));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (pass) s_queue[pos + __popc(bal & lt)] = idx;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int idx = base + (c0 + u) * 256;
+            bool pass = false;
+            if (idx < a.P) {
+                pass = strip_may_touch(s_vp[0], xo[u].x, xo[u].y, xo[u].z, sm[u], row0, row1) ||
+                       strip_may_touch(s_vp[1], xo[u].x, xo[u].y, xo[u].z, sm[u], row0, row1);
+                if (!pass) {
+                    a.rect_raw[idx] = 0u;
+                    a.rect_raw[(size_t)a.P + idx] = 0u;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (bal) {
+                int pos = 0;
+                if ((threadIdx.x & 31) == 0) pos = atomicAdd(&s_n, __popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (pass) s_queue[pos + __popc(bal & lt)] = idx;
+            }
         }
     }
     __syncthreads();
     const int n = s_n;
-    // project the queue with full warps; the visible (view, Gaussian) pairs of every round go to the global list the
-    // bucket scatter walks in split mode (one reservation per round; the list is unordered, like the scatter itself)
+    if (threadIdx.x == 0) s_base = n ? (int)atomicAdd(a.surv_count, (uint32_t)n) : 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += 256) a.surv_list[s_base + t] = (uint32_t)s_queue[t];
+}
+
+template <int D>
+__global__ void __launch_bounds__(256, 2) preprocess_map_list_kernel(PreMapArgs a) {
+    if (a.ctl->level_done) return;
+    __shared__ ViewParams s_vp[2];
     __shared__ uint32_t s_wn[8];
     __shared__ uint32_t s_base;
-    for (int t0 = 0; t0 < n; t0 += 256) {
-        const int t = t0 + (int)threadIdx.x;
+    load_views(s_vp, a.views, 2);
+    __syncthreads();
+    const uint32_t n = *a.surv_count;
+    for (uint32_t t0 = blockIdx.x * 256u; t0 < n; t0 += gridDim.x * 256u) {
+        const uint32_t t = t0 + threadIdx.x;
         uint32_t vis = 0;
         int idx = 0;
         if (t < n) {
-            idx = s_queue[t];
+            idx = (int)__ldg(a.surv_list + t);
             vis = project_store<D, true>(a, s_vp, idx, __ldg(a.xyz_opacity + idx));
         }
+        // the visible (view, Gaussian) pairs of the round go to the list the bucket scatter walks in split mode (one
+        // reservation per round; the list is unordered, like the scatter itself)
         const uint32_t mine = (vis & 1u) + (vis >> 1);
         uint32_t incl = mine;
 #pragma unroll
@@ -352,16 +377,13 @@ size_t preprocess_map_raw_items(int P) { return (2 * (size_t)P + 1023) / 1024 * 
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
     if (a.split_pretest) {
-        // chunks of 256 Gaussians per CTA: as many as the queue holds on large maps (survivors fill whole warps), fewer on
-        // small ones so that the grid still covers the 148 SMs a few times
-        int chunks = a.P / (256 * 148 * 4);
-        chunks = chunks < 2 ? 2 : (chunks > SPLIT_CHUNKS ? SPLIT_CHUNKS : chunks);
-        const int blocks = (a.P + chunks * 256 - 1) / (chunks * 256);
+        strip_pretest_kernel<<<(a.P + PRETEST_PER_CTA - 1) / PRETEST_PER_CTA, 256, 0, s>>>(a);
+        const int blocks = 148 * 4;   // 2 resident CTAs per SM, two waves; grid-stride over the survivors
         switch (a.D) {
-            case 0: preprocess_map_split_kernel<0><<<blocks, 256, 0, s>>>(a, chunks); break;
-            case 1: preprocess_map_split_kernel<1><<<blocks, 256, 0, s>>>(a, chunks); break;
-            case 2: preprocess_map_split_kernel<2><<<blocks, 256, 0, s>>>(a, chunks); break;
-            default: preprocess_map_split_kernel<3><<<blocks, 256, 0, s>>>(a, chunks); break;
+            case 0: preprocess_map_list_kernel<0><<<blocks, 256, 0, s>>>(a); break;
+            case 1: preprocess_map_list_kernel<1><<<blocks, 256, 0, s>>>(a); break;
+            case 2: preprocess_map_list_kernel<2><<<blocks, 256, 0, s>>>(a); break;
+            default: preprocess_map_list_kernel<3><<<blocks, 256, 0, s>>>(a); break;
         }
         return;
     }

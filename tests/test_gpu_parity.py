@@ -765,3 +765,89 @@ def test_full_size_properties_1M(built, cuda_dev):
     # linearity of the backward pass in the upstream gradient
     a2 = H.run_operator(_ours(), sc, v, cuda_dev, dcol=2.0 * dcol, want_map_grads=False)
     assert H.rel_max(a2["pose"], 2.0 * a["pose"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_bulk_id_staging_matches_plain_loads(built, cuda_dev, monkeypatch):
+    """The cp.async.bulk + mbarrier staging of the tile id lists (blend.cu, GSEVT_BLEND_BULK=1; off by default because it
+    measured slower) must be a pure change of plumbing: same lists in, bit-identical images, n_contrib / final_T and — the
+    backward walks the forward's hit masks in the same order — the same loss; gradients equal to the atomics' noise.  Lists
+    of several batches exercise the ring's slot reuse."""
+    sc = H.small_scene(150000, 320, 240, seed=5)
+    res = {}
+    for bulk in ("0", "1"):
+        monkeypatch.setenv("GSEVT_BLEND_BULK", bulk)
+        eng, b, sign, _ = _engine(sc, cuda_dev)
+        out = []
+        for level in (0, 1, 2):
+            L, g = eng.eval(level, True)
+            T, n = eng.image_state(level)
+            gl, gn = eng.gray_images(level)
+            out.append((L, g, T.cpu().numpy(), n.cpu().numpy(), gl.cpu().numpy(), gn.cpu().numpy()))
+        eng.begin_level(0, True)
+        eng.iterate(12)
+        eng.stream.synchronize()
+        res[bulk] = (out, eng.losses(), eng.get_state())
+        eng.close()
+    assert max(int(o[3].max()) for o in res["0"][0]) > 2 * 256      # several batches per tile: the ring's slots are reused
+    for (L0, g0, T0, n0, a0, b0), (L1, g1, T1, n1, a1, b1) in zip(res["0"][0], res["1"][0]):
+        assert L0 == L1 and np.array_equal(n0, n1) and H.bits_equal(T0, T1) and H.bits_equal(a0, a1) and H.bits_equal(b0, b1)
+        assert H.rel_max(g1, g0) < 1e-5
+    assert np.allclose(res["0"][1], res["1"][1], rtol=1e-5) and all(np.allclose(x, y, atol=1e-5) for x, y in zip(res["0"][2], res["1"][2]))
+
+
+@pytest.mark.gpu
+def test_concurrent_hypotheses_match_one_at_a_time(built, cuda_dev):
+    """BASELINE.json configs[3] in small: 6 perturbed seeds tracked to convergence through the three pyramid levels, once
+    one at a time on one engine and once three at a time on three engines / streams (gsevt.hypotheses.track_concurrently).
+    Same hypotheses in, same answers out: the concurrent run is the same optimisation per hypothesis, only interleaved on
+    the GPU.  The scene is the trackable one (structure splats, events sampled from the intensity change rendered at the
+    true state), so that every hypothesis has a minimum to converge to: both runs must end within 2 mm of each other and
+    within a centimetre of the truth, with losses equal to 1 %."""
+    import torch
+    from gsevt import hypotheses as hyp
+    from gsevt import synth
+    from gsevt.engine import EventFrameBuilder, PackedMap, TrackingEngine
+    W, Hh = 320, 240
+    D = synth.DESK
+    fx, fy = D["fx"] * W / D["W"], D["fy"] * W / D["W"]
+    act = synth.activate(synth.synth_map(20000, seed=0, W=W, H=Hh, fx=fx, fy=fy, structure=300, fine_opacity_shift=-3.0))
+    A = {k: torch.from_numpy(v).to(cuda_dev) for k, v in act.items()}
+    pm = PackedMap(A["xyz"], A["scales"], A["rotations"], A["opacities"], A["shs"], 3)
+    state = (np.asarray(D["R"], np.float32).reshape(3, 3), np.asarray(D["T"], np.float32), np.asarray(D["angular_vel"], np.float32),
+             np.asarray(D["linear_vel"], np.float32))
+    K = np.array([fx, 0, W / 2, 0, fy, Hh / 2, 0, 0, 1.0]).reshape(3, 3)
+    b = EventFrameBuilder(W, Hh, K, D["dist"], levels=3, device=cuda_dev)
+    z = np.zeros(1, np.int16)
+    dummy = b.build(z, z, z.astype(np.uint8))
+    mk = lambda: TrackingEngine(pm, W, Hh, fx, fy, levels=3, converged_threshold=1e-4, max_optim_iter=200)
+    e0 = mk()
+    e0.set_state(*state)
+    e0.begin_frame(0.05, dummy[0], dummy[1])
+    e0.eval(0, True)
+    gl, gn = e0.gray_images(0)
+    e0.close()
+    ev = synth.threshold_events((gn - gl).cpu().numpy(), 7500, 0, 49999, K, D["dist"], seed=11)
+    sign, unsign = b.build(ev[:, 1].astype(np.int16), ev[:, 2].astype(np.int16), ev[:, 3].astype(np.uint8))
+    tables = {}
+    for n_eng in (1, 3):
+        engs = [mk() for _ in range(n_eng)]
+        t = hyp.Tickets()
+
+        def nxt():
+            h = t.next()
+            return None if h >= 6 else (h, hyp.perturb(*state, h, sigma_t=0.005, sigma_deg=0.1, vel_frac=0.05))
+
+        rows = hyp.track_concurrently(engs, nxt, 0.05, sign, unsign, levels=3, chunk=8)
+        tables[n_eng] = hyp.gather_results(rows, 6)
+        for e in engs:
+            e.close()
+    a, c = tables[1], tables[3]
+    assert np.array_equal(a[:, 0], np.arange(6)) and np.array_equal(c[:, 0], np.arange(6))
+    assert np.all(a[:, 2] >= 3) and np.all(a[:, 2] <= 3 * 401) and np.all(c[:, 2] <= 3 * 401)
+    dT = np.linalg.norm(a[:, 12:15] - c[:, 12:15], axis=1)
+    err = np.linalg.norm(a[:, 12:15] - np.asarray(D["T"], np.float64), axis=1)
+    print("serial vs concurrent |dT| (mm):", (dT * 1e3).round(3), " error vs truth (mm):", (err * 1e3).round(2), " losses:", a[:, 1].round(4))
+    assert dT.max() < 2e-3 and err.max() < 1e-2, (dT, err)
+    assert np.allclose(a[:, 1], c[:, 1], rtol=1e-2), (a[:, 1], c[:, 1])
+    assert a[:, 1].max() < 1.0       # the event frame correlates with the render: this is a tracking problem, not noise

@@ -26,7 +26,7 @@ if has ref; then
 fi
 if has launches; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-      --log-file "$OUT/${TAG}_launches.csv" python bench.py --steps 8 --warmup 3 --no-cpu-baseline \
+      --log-file "$OUT/${TAG}_launches.csv" python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-extras --no-parity-check \
       > "$OUT/${TAG}_launches.log" 2>&1
   tail -2 "$OUT/${TAG}_launches.log"
 fi
@@ -35,7 +35,8 @@ if has full; then
   timeout 1200 ncu --set full --clock-control none --import-source on \
       -k regex:'preprocess_map|bucket_scatter|bucket_sort|blend_fwd|blend_bwd|geom_compact|geom_bwd|loss_stats|engine_update' \
       -s "${NCU_SKIP:-120}" -c "${NCU_COUNT:-40}" -o "$OUT/${TAG}_full" -f \
-      python bench.py --steps 6 --warmup 3 --no-cpu-baseline > "$OUT/${TAG}_full.log" 2>&1
+      python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-extras --no-parity-check > "$OUT/${TAG}_full.log" 2>&1
+  ncu -i "$OUT/${TAG}_full.ncu-rep" --page raw --csv > "$OUT/${TAG}_full_raw.csv" 2>/dev/null
   tail -2 "$OUT/${TAG}_full.log"
   ls -la "$OUT/${TAG}_full.ncu-rep"
 fi
