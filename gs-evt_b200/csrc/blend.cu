@@ -140,6 +140,19 @@ struct IdRing {
     }
 };
 
+// Single-instruction approximations for the engine backward (gated at 1e-3, not bit for bit): MUFU.EX2 / MUFU.RCP without the
+// range fix-ups of __expf / __fdividef (the arguments here are power <= 0 and 1 - alpha in [0.01, 1]).
+__device__ __forceinline__ float fast_exp(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // alpha and its ingredients in the reference's rounding order (forward.cu:342-353).
 __device__ __forceinline__ float eval_power(float dx, float dy, float A, float B, float C) {
     const float q = __fmaf_rn(dx, __fmul_rn(dx, A), __fmul_rn(dy, __fmul_rn(dy, C)));
@@ -266,12 +279,12 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
                 }
             }
             unsigned hits = __ballot_sync(0xffffffffu, hit);
-            uint32_t blended = 0;   // engine: bit b set <=> some pixel of this warp blended instance j0 + b
+            uint32_t mine = 0;      // engine: bit b set <=> THIS pixel blended instance j0 + b (or-reduced over the warp below)
+            int last_b = -1;        // last instance of this group this pixel blended
             while (hits) {
                 const int b = __ffs(hits) - 1;
                 const int j = j0 + b;
                 hits &= hits - 1;
-                bool contributed = false;
                 if (!done) {
                     const float4 r0 = s_r0[buf][j];
                     const float dx = __fadd_rn(r0.x, -pxf), dy = __fadd_rn(r0.y, -pyf);
@@ -295,17 +308,18 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
                                     acc[0] = __fmaf_rn(T, __fmul_rn(alpha, r1.z), acc[0]);
                                 }
                                 T = test_T;
-                                last_contributor = (uint32_t)(base + j + 1);
-                                contributed = true;
+                                last_b = b;
+                                if constexpr (!OPERATOR) mine |= 1u << b;
                             }
                         }
                     }
                 }
-                if constexpr (!OPERATOR) {
-                    if (__any_sync(0xffffffffu, contributed)) blended |= 1u << b;
-                }
             }
+            if (last_b >= 0) last_contributor = (uint32_t)(base + j0 + last_b + 1);
             if constexpr (!OPERATOR) {
+                // which instances of the group some pixel of this warp blended: ONE warp reduction per group of 32
+                // positions (a vote per hit cost 3 instructions x 26 hits per group)
+                const uint32_t blended = __reduce_or_sync(0xffffffffu, mine);
                 if (hitrow && lane == 0) hitrow[(base + j0) >> 5] = blended;
             }
         }
@@ -517,7 +531,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
         // bit, so exp is ex2.approx (2 instructions instead of 11) and 1 / (1 - alpha) is rcp.approx (instead of 14) — except
         // within 1e-6 of the alpha >= 1/255 test, which must fall as it did in the forward pass: a pair blended there and
         // skipped here would leave T off by (1 - alpha) for everything in front of it.
-        float G = OPERATOR ? expf(power) : __expf(power);
+        float G = OPERATOR ? expf(power) : fast_exp(power);
         float alpha = fminf(0.99f, __fmul_rn(r1.y, G));
         if constexpr (!OPERATOR) {
             if (fabsf(alpha - kAlphaMin) < 1e-6f) {
@@ -533,7 +547,7 @@ __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
 #pragma unroll
         for (int k = 0; k < KR; k++) v[k] = 0.0f;
         if (!skip) {
-            const float inv = OPERATOR ? __frcp_rn(1.0f - alpha) : __fdividef(1.0f, 1.0f - alpha);
+            const float inv = OPERATOR ? __frcp_rn(1.0f - alpha) : fast_rcp(1.0f - alpha);
             T = T * inv;
             const float w = alpha * T;
             float dL_dalpha = 0.0f;
