@@ -425,6 +425,9 @@ struct GsevtEngine {
     uint32_t* hit_base = nullptr;        // [2 tiles]
     uint2* ranges = nullptr;
     uint32_t* hitmask = nullptr; size_t hitmask_stride = 0;   // forward -> backward: what each warp blended
+    int pdl = 0;                         // GSEVT_PDL=1: programmatic dependent launches along the iteration's kernel chain (internal.h);
+                                         // measured 2.6 % SLOWER (0.6775 vs 0.6605 ms): the early-resident dependents take slots from
+                                         // the predecessor's tail, and the graph's kernel-to-kernel gaps were only ~1.5 us to begin with
     int blend_bulk = 0;                  // GSEVT_BLEND_BULK=1: id lists staged with cp.async.bulk + mbarrier (blend.cu); measured 1.3 %
                                          // slower per iteration than per-thread loads on the B200 (profiles/README.md), hence off
     float* gray = nullptr; float* final_T = nullptr; uint32_t* n_contrib = nullptr;
@@ -450,6 +453,8 @@ struct GsevtEngine {
 #define GSEVT_MAILBOX_BYTES ((size_t)2 << 20)
 
 namespace gsevt {
+
+thread_local int g_pdl = 0;
 
 template <typename T>
 static int dev_alloc(GsevtEngine* e, T** p, size_t n) {
@@ -568,6 +573,7 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     const int P = m->P;
     int stage = 0;
     auto mark = [&]() { if (ev) cudaEventRecord(ev[stage], s); stage++; };
+    struct PdlScope { PdlScope(int on) { g_pdl = on; } ~PdlScope() { g_pdl = 0; } } pdl_scope(e->pdl);
     // the two ViewParams blocks are current on entry: written by the previous iteration's update kernel, or by
     // the stand-alone pose kernel after any host-side change of state / level (probe_buckets, set_state, ...)
     mark();
@@ -689,6 +695,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     GsevtEngine* e = new GsevtEngine();
     e->map = map; e->cfg = *cfg; e->nlevels = cfg->levels;
     if (const char* v = getenv("GSEVT_BLEND_BULK")) e->blend_bulk = atoi(v) != 0;
+    if (const char* v = getenv("GSEVT_PDL")) e->pdl = atoi(v) != 0;
     size_t ev_off = 0;
     for (int l = 0; l < cfg->levels; l++) {
         LevelInfo& L = e->lv[l];

@@ -167,6 +167,7 @@ __device__ __forceinline__ float eval_power(float dx, float dy, float A, float B
 template <int C, bool OPERATOR, bool BULK = false>
 __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     static_assert(!(OPERATOR && BULK), "the operator's packed lists are not aligned for bulk copies");
+    pdl_prologue();
     if (a.ctl && a.ctl->level_done) return;
     __shared__ __align__(16) uint32_t s_ids[BULK ? kIdSlots : 1][256];
     __shared__ __align__(8) uint64_t s_bar[BULK ? kIdSlots : 1];
@@ -354,8 +355,8 @@ void launch_blend_fwd_gray(const BlendFwdArgs& a, cudaStream_t s) {
     dim3 grid(a.grid_x, a.tile_rows, a.nviews);
     if (a.tile_rows <= 0) return;
     if (a.tile_order) grid = dim3((unsigned)(a.grid_x * a.tile_rows * a.nviews), 1, 1);
-    if (a.bulk_ids) blend_fwd_kernel<1, false, true><<<grid, 256, 0, s>>>(a);
-    else blend_fwd_kernel<1, false><<<grid, 256, 0, s>>>(a);
+    if (a.bulk_ids) launch_k(blend_fwd_kernel<1, false, true>, grid, dim3(256), 0, s, a);
+    else launch_k(blend_fwd_kernel<1, false, false>, grid, dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -394,6 +395,7 @@ __device__ __forceinline__ float warp_reduce_scatter(float (&v)[N], int lane) {
 template <int C, bool OPERATOR, bool BULK = false>
 __global__ void __launch_bounds__(256) blend_bwd_kernel(BlendBwdArgs a) {
     static_assert(!(OPERATOR && BULK), "the operator's packed lists are not aligned for bulk copies");
+    pdl_prologue();
     if (a.ctl && a.ctl->level_done) return;
     constexpr int K = BwdCfg<OPERATOR>::K, KR = BwdCfg<OPERATOR>::KR;
     __shared__ __align__(16) uint32_t s_ids[BULK ? kIdSlots : 1][256];
@@ -656,8 +658,8 @@ void launch_blend_bwd_gray(const BlendBwdArgs& a, cudaStream_t s) {
     dim3 grid(a.grid_x, a.tile_rows, a.nviews);
     if (a.tile_rows <= 0) return;
     if (a.tile_order) grid = dim3((unsigned)(a.grid_x * a.tile_rows * a.nviews), 1, 1);
-    if (a.bulk_ids) blend_bwd_kernel<1, false, true><<<grid, 256, 0, s>>>(a);
-    else blend_bwd_kernel<1, false><<<grid, 256, 0, s>>>(a);
+    if (a.bulk_ids) launch_k(blend_bwd_kernel<1, false, true>, grid, dim3(256), 0, s, a);
+    else launch_k(blend_bwd_kernel<1, false, false>, grid, dim3(256), 0, s, a);
 }
 
 }  // namespace gsevt

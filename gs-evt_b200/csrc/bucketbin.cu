@@ -39,6 +39,7 @@ using namespace sortcore;
 
 template <bool COUNT_ONLY, int S>
 __global__ void __launch_bounds__(256) bucket_scatter_kernel(BucketArgs a) {
+    pdl_prologue();
     if (a.ctl && a.ctl->level_done) return;
     const uint32_t j = blockIdx.x * 256u + threadIdx.x;            // pair id = view * P + Gaussian
     const uint32_t n2 = 2u * (uint32_t)a.P;
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(BucketArgs a) {
 // projection kernel wrote (preprocess.cu) instead of the dense rect array.  Grid-stride over the device-side count.
 template <int S>
 __global__ void __launch_bounds__(256) bucket_scatter_list_kernel(BucketArgs a) {
+    pdl_prologue();
     if (a.ctl && a.ctl->level_done) return;
     const uint32_t n = *a.vis_count;
     for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {   // uniform per CTA: whole warps stay for big_rects
@@ -138,6 +140,7 @@ constexpr int SORT_THREADS = 512;
 
 template <int S>
 __global__ void __launch_bounds__(SORT_THREADS, 2) bucket_sort_kernel(BucketArgs a) {
+    pdl_prologue();
     if (a.ctl && a.ctl->level_done) return;
     extern __shared__ __align__(16) uint64_t s_buf[];
     constexpr int NT = 1 << (2 * S);                    // tiles per bucket
@@ -388,11 +391,11 @@ void launch_bucket_scatter(const BucketArgs& a, bool count_only, cudaStream_t s)
         else bucket_scatter_kernel<true, 1><<<blocks, 256, 0, s>>>(a);
     } else if (a.sparse) {
         const unsigned lb = blocks < 148u * 8u ? blocks : 148u * 8u;   // 8 CTAs per SM, grid-stride over the visible pairs
-        if (a.s == 0) bucket_scatter_list_kernel<0><<<lb, 256, 0, s>>>(a);
-        else bucket_scatter_list_kernel<1><<<lb, 256, 0, s>>>(a);
+        if (a.s == 0) launch_k(bucket_scatter_list_kernel<0>, dim3(lb), dim3(256), 0, s, a);
+        else launch_k(bucket_scatter_list_kernel<1>, dim3(lb), dim3(256), 0, s, a);
     } else {
-        if (a.s == 0) bucket_scatter_kernel<false, 0><<<blocks, 256, 0, s>>>(a);
-        else bucket_scatter_kernel<false, 1><<<blocks, 256, 0, s>>>(a);
+        if (a.s == 0) launch_k(bucket_scatter_kernel<false, 0>, dim3(blocks), dim3(256), 0, s, a);
+        else launch_k(bucket_scatter_kernel<false, 1>, dim3(blocks), dim3(256), 0, s, a);
     }
 }
 
@@ -413,8 +416,8 @@ void bucket_sort_smem(int max_keys, int* elems, int* bins, size_t* bytes) {
 
 void launch_bucket_sort(const BucketArgs& a, cudaStream_t s) {
     if (a.nb <= 0) return;
-    if (a.s == 0) bucket_sort_kernel<0><<<2 * a.nb, SORT_THREADS, a.smem_bytes, s>>>(a);
-    else bucket_sort_kernel<1><<<2 * a.nb, SORT_THREADS, a.smem_bytes, s>>>(a);
+    if (a.s == 0) launch_k(bucket_sort_kernel<0>, dim3(2 * a.nb), dim3(SORT_THREADS), a.smem_bytes, s, a);
+    else launch_k(bucket_sort_kernel<1>, dim3(2 * a.nb), dim3(SORT_THREADS), a.smem_bytes, s, a);
 }
 
 // padded cursor array -> packed counts, one per (bucket, sub-segment) (probe)

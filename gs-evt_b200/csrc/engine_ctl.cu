@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineC
                                                                           const int* __restrict__ overflow,
                                                                           ViewParams* views, const float* bg3,
                                                                           SplitComm* comm) {
+    pdl_prologue();
     if (ctl->level_done) return;
     __shared__ double s_d[16];
     __shared__ double s_t[16];
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineC
 
 void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, const int* overflow,
                           ViewParams* views, const float* bg3, SplitComm* comm, cudaStream_t s) {
-    engine_update_kernel<<<1, 32 * GSEVT_NPART, 0, s>>>(ctl, partials, nblocks, host_flag, overflow, views, bg3, comm);
+    launch_k(engine_update_kernel, dim3(1), dim3(32 * GSEVT_NPART), 0, s, ctl, partials, nblocks, host_flag, overflow, views, bg3, comm);
 }
 
 // ---- per-frame helpers ----------------------------------------------------------------------------

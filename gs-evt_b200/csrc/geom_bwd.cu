@@ -60,6 +60,7 @@ __device__ __forceinline__ void build_cur(SharedCam& c) {
 
 template <bool ENGINE>
 __global__ void __launch_bounds__(256) geom_bwd_kernel(GeomBwdArgs a) {
+    pdl_prologue();
     if (a.ctl && a.ctl->level_done) return;
     __shared__ SharedCam s_cam[2];
     __shared__ float s_red[8][GSEVT_NPART];
@@ -407,7 +408,7 @@ void launch_geom_bwd_aos(const GeomBwdArgs& a, cudaStream_t s) {
     geom_bwd_kernel<false><<<geom_bwd_blocks(a.P, a.nviews), 256, 0, s>>>(a);
 }
 void launch_geom_bwd_map(const GeomBwdArgs& a, cudaStream_t s) {
-    geom_bwd_kernel<true><<<geom_bwd_blocks(a.P, a.nviews), 256, 0, s>>>(a);
+    launch_k(geom_bwd_kernel<true>, dim3(geom_bwd_blocks(a.P, a.nviews)), dim3(256), 0, s, a);
 }
 
 // Streaming compaction: list of (view, Gaussian) pairs with a non-zero blend gradient.  Every CTA owns a contiguous
@@ -417,6 +418,7 @@ constexpr int GC_PER_CTA = 2048;
 __global__ void __launch_bounds__(256) geom_compact_kernel(int n, int per_cta, const uint32_t* __restrict__ rect_raw,
                                                            const float4* __restrict__ grad8, uint32_t* __restrict__ list,
                                                            uint32_t* __restrict__ count, const EngineCtl* __restrict__ ctl) {
+    pdl_prologue();
     if (ctl && ctl->level_done) return;
     __shared__ uint32_t s_list[GC_PER_CTA];
     __shared__ uint32_t s_n, s_base;
@@ -470,7 +472,7 @@ void launch_geom_compact(int n_pairs, const uint32_t* rect_raw, const float4* gr
     per = (per + 255) / 256 * 256;
     if (per > GC_PER_CTA) per = GC_PER_CTA;
     const int blocks = (n_pairs + per - 1) / per;
-    geom_compact_kernel<<<blocks, 256, 0, s>>>(n_pairs, per, rect_raw, grad8, list, count, ctl);
+    launch_k(geom_compact_kernel, dim3(blocks), dim3(256), 0, s, n_pairs, per, rect_raw, grad8, list, count, ctl);
 }
 
 // partials[12][nblocks] -> out12, fixed summation order, double accumulation.

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace gsevt {
@@ -296,6 +297,37 @@ void launch_workload_counters(int P, const uint32_t* rect_raw, const float4* gra
                               unsigned long long* out, cudaStream_t s);
 
 void set_error(const char* fmt, ...);
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// The engine's iteration is a chain of nine short kernels (13 .. 260 us); between two of them the GPU drains, the next
+// grid is launched and its first CTAs are rasterised — a few microseconds each time.  With the launch attribute below a
+// kernel may be LAUNCHED as soon as every CTA of its predecessor has started: its CTAs become resident on the slots the
+// predecessor's tail frees and wait in pdl_prologue() until the predecessor has completed and its writes are visible.
+// Every kernel of the chain calls pdl_prologue() before it touches global memory (so completion is transitive along the
+// chain) and triggers its own dependents at once.  g_pdl is set by the engine runtime around enqueue_iteration().
+// Measured [r2]: 0.6775 ms per iteration with the attribute, 0.6605 ms without (A/B/A/B, 1 M / 640x480) — off by default
+// (GSEVT_PDL=1 enables it); without the attribute the two griddepcontrol instructions are no-ops.
+extern thread_local int g_pdl;
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
 }  // namespace gsevt
 
 #define GSEVT_CUDA_OK(expr)                                                                  \

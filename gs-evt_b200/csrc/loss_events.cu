@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict
                                                          int HW, int pix0, int npix, EngineCtl* __restrict__ ctl,
                                                          double* __restrict__ partials, int nblocks,
                                                          uint32_t* __restrict__ zero_me, SplitComm* comm, int* host_flag) {
+    pdl_prologue();
     if (ctl->level_done) return;
     __shared__ double s_w[8][3];
     __shared__ double s_x[8];
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict
 
 void launch_loss_stats(const float* gray, const float* event_frame, int HW, int pix0, int npix, EngineCtl* ctl,
                        double* partials, int nblocks, uint32_t* zero_me, SplitComm* comm, int* host_flag, cudaStream_t s) {
-    loss_stats_kernel<<<nblocks, 256, 0, s>>>(gray, event_frame, HW, pix0, npix, ctl, partials, nblocks, zero_me, comm, host_flag);
+    launch_k(loss_stats_kernel, dim3(nblocks), dim3(256), 0, s, gray, event_frame, HW, pix0, npix, ctl, partials, nblocks, zero_me, comm, host_flag);
 }
 
 // ---- workload counters (bench / profiling only) ---------------------------------------------------

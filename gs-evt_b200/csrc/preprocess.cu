@@ -261,6 +261,7 @@ __device__ __forceinline__ uint32_t project_store(const PreMapArgs& a, const Vie
 
 template <int D, int MINB>
 __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a) {
+    pdl_prologue();
     if (a.ctl && a.ctl->level_done) return;
     __shared__ ViewParams s_vp[2];
     load_views(s_vp, a.views, 2);
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(256, MINB) preprocess_map_kernel(PreMapArgs a)
 constexpr int PRETEST_PER_CTA = 2048;
 
 __global__ void __launch_bounds__(256) strip_pretest_kernel(PreMapArgs a) {
+    pdl_prologue();
     if (a.ctl->level_done) return;
     __shared__ ViewParams s_vp[2];
     __shared__ int s_queue[PRETEST_PER_CTA];
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(256) strip_pretest_kernel(PreMapArgs a) {
 
 template <int D>
 __global__ void __launch_bounds__(256, 2) preprocess_map_list_kernel(PreMapArgs a) {
+    pdl_prologue();
     if (a.ctl->level_done) return;
     __shared__ ViewParams s_vp[2];
     __shared__ uint32_t s_wn[8];
@@ -377,13 +380,13 @@ size_t preprocess_map_raw_items(int P) { return (2 * (size_t)P + 1023) / 1024 * 
 void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
     if (a.P <= 0) return;
     if (a.split_pretest) {
-        strip_pretest_kernel<<<(a.P + PRETEST_PER_CTA - 1) / PRETEST_PER_CTA, 256, 0, s>>>(a);
+        launch_k(strip_pretest_kernel, dim3((a.P + PRETEST_PER_CTA - 1) / PRETEST_PER_CTA), dim3(256), 0, s, a);
         const int blocks = 148 * 4;   // 2 resident CTAs per SM, two waves; grid-stride over the survivors
         switch (a.D) {
-            case 0: preprocess_map_list_kernel<0><<<blocks, 256, 0, s>>>(a); break;
-            case 1: preprocess_map_list_kernel<1><<<blocks, 256, 0, s>>>(a); break;
-            case 2: preprocess_map_list_kernel<2><<<blocks, 256, 0, s>>>(a); break;
-            default: preprocess_map_list_kernel<3><<<blocks, 256, 0, s>>>(a); break;
+            case 0: launch_k(preprocess_map_list_kernel<0>, dim3(blocks), dim3(256), 0, s, a); break;
+            case 1: launch_k(preprocess_map_list_kernel<1>, dim3(blocks), dim3(256), 0, s, a); break;
+            case 2: launch_k(preprocess_map_list_kernel<2>, dim3(blocks), dim3(256), 0, s, a); break;
+            default: launch_k(preprocess_map_list_kernel<3>, dim3(blocks), dim3(256), 0, s, a); break;
         }
         return;
     }
@@ -393,12 +396,12 @@ void launch_preprocess_map(const PreMapArgs& a, cudaStream_t s) {
     // latter for experiments.
     static const int minb = [] { const char* v = getenv("GSEVT_PRE_MINB"); return v && atoi(v) == 3 ? 3 : 2; }();
     switch (a.D) {
-        case 0: preprocess_map_kernel<0, 3><<<blocks, 256, 0, s>>>(a); break;
-        case 1: preprocess_map_kernel<1, 3><<<blocks, 256, 0, s>>>(a); break;
-        case 2: preprocess_map_kernel<2, 3><<<blocks, 256, 0, s>>>(a); break;
+        case 0: launch_k(preprocess_map_kernel<0, 3>, dim3(blocks), dim3(256), 0, s, a); break;
+        case 1: launch_k(preprocess_map_kernel<1, 3>, dim3(blocks), dim3(256), 0, s, a); break;
+        case 2: launch_k(preprocess_map_kernel<2, 3>, dim3(blocks), dim3(256), 0, s, a); break;
         default:
-            if (minb == 2) preprocess_map_kernel<3, 2><<<blocks, 256, 0, s>>>(a);
-            else preprocess_map_kernel<3, 3><<<blocks, 256, 0, s>>>(a);
+            if (minb == 2) launch_k(preprocess_map_kernel<3, 2>, dim3(blocks), dim3(256), 0, s, a);
+            else launch_k(preprocess_map_kernel<3, 3>, dim3(blocks), dim3(256), 0, s, a);
             break;
     }
 }
