@@ -36,11 +36,24 @@ class Tickets:
         self._key = f"gsevt/hypothesis_ticket/{next(_search_calls)}"
         self._local = itertools.count()
         self._store = store
+        self._stride = None
         if store is None and dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-            from torch.distributed import distributed_c10d as c10d
-            self._store = c10d._get_default_store()
+            try:
+                from torch.distributed import distributed_c10d as c10d
+                self._store = c10d._get_default_store()
+            except Exception:
+                # no access to the group's store in this torch build: fall back to the static partition h mod world,
+                # expressed as a ticket sequence (rank, rank + world, ...), so that callers need no second code path
+                self._stride = (dist.get_rank(), dist.get_world_size())
+
+    @property
+    def dynamic(self):
+        return self._stride is None
 
     def next(self):
+        if self._stride is not None:
+            r, w = self._stride
+            return r + w * next(self._local)
         if self._store is None:
             return next(self._local)
         return int(self._store.add(self._key, 1)) - 1
