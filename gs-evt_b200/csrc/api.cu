@@ -583,6 +583,9 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     launch_bucket_scatter(ba, false, s);
     mark();
     launch_bucket_sort(ba, s);
+    // (an engine whose strip is empty — more ranks than tile rows — launches neither binning kernel: nobody consumes the
+    // split projection's two lists, so clear their counters here)
+    if (ba.nb <= 0 && e->vis_count && split_kernels(e)) cudaMemsetAsync(e->vis_count, 0, 8, s);
     mark();
     BlendFwdArgs f;
     memset(&f, 0, sizeof(f));

@@ -317,10 +317,19 @@ __global__ void __launch_bounds__(32 * GSEVT_NPART) engine_update_kernel(EngineC
     constexpr int HOT_WORDS = (int)(offsetof(EngineCtl, losses) / 4);
     __shared__ __align__(16) uint32_t s_ctl[HOT_WORDS];
     for (int i = threadIdx.x; i < HOT_WORDS; i += blockDim.x) s_ctl[i] = reinterpret_cast<const uint32_t*>(ctl)[i];
+    // The two camera blocks of the next iteration are built in shared memory as well (the projection product reads back
+    // the view matrix it has just written: in place, 2 x 64 dependent L2 round trips) and copied out by all threads.
+    constexpr int VIEW_WORDS = (int)(2 * sizeof(ViewParams) / 4);
+    __shared__ __align__(16) uint32_t s_views[VIEW_WORDS];
+    __shared__ float s_bg[3];
+    if (threadIdx.x < 3) s_bg[threadIdx.x] = bg3[threadIdx.x];
+    for (int i = threadIdx.x; i < VIEW_WORDS; i += blockDim.x) s_views[i] = reinterpret_cast<const uint32_t*>(views)[i];
     __syncthreads();
-    if (threadIdx.x == 0) engine_control(reinterpret_cast<EngineCtl*>(s_ctl), ctl->losses, s_g, host_flag, views, bg3);
+    if (threadIdx.x == 0)
+        engine_control(reinterpret_cast<EngineCtl*>(s_ctl), ctl->losses, s_g, host_flag, reinterpret_cast<ViewParams*>(s_views), s_bg);
     __syncthreads();
     for (int i = threadIdx.x; i < HOT_WORDS; i += blockDim.x) reinterpret_cast<uint32_t*>(ctl)[i] = s_ctl[i];
+    for (int i = threadIdx.x; i < VIEW_WORDS; i += blockDim.x) reinterpret_cast<uint32_t*>(views)[i] = s_views[i];
 }
 
 void launch_engine_update(EngineCtl* ctl, const float* partials, int nblocks, int* host_flag, const int* overflow,
