@@ -768,15 +768,20 @@ def test_full_size_properties_1M(built, cuda_dev):
 
 
 @pytest.mark.gpu
-def test_bulk_id_staging_matches_plain_loads(built, cuda_dev, monkeypatch):
-    """The cp.async.bulk + mbarrier staging of the tile id lists (blend.cu, GSEVT_BLEND_BULK=1; off by default because it
-    measured slower) must be a pure change of plumbing: same lists in, bit-identical images, n_contrib / final_T and — the
-    backward walks the forward's hit masks in the same order — the same loss; gradients equal to the atomics' noise.  Lists
-    of several batches exercise the ring's slot reuse."""
+@pytest.mark.parametrize("switch", ["GSEVT_BLEND_BULK", "GSEVT_PDL"])
+def test_optional_paths_match_the_default(built, cuda_dev, monkeypatch, switch):
+    """The two measured-and-not-adopted variants stay in the library behind environment switches, so they stay tested:
+      GSEVT_BLEND_BULK=1  cp.async.bulk + mbarrier staging of the tile id lists (blend.cu); lists of several batches
+                          exercise the ring's slot reuse;
+      GSEVT_PDL=1         programmatic dependent launch along the iteration's kernel chain (internal.h), captured into the
+                          CUDA graph.
+    Both must be pure changes of plumbing: same lists in, bit-identical images, n_contrib / final_T and — the backward
+    walks the forward's hit masks in the same order — the same loss; gradients equal to the atomics' noise; a run of
+    graph-launched iterations ends where the default build's does."""
     sc = H.small_scene(150000, 320, 240, seed=5)
     res = {}
-    for bulk in ("0", "1"):
-        monkeypatch.setenv("GSEVT_BLEND_BULK", bulk)
+    for on in ("0", "1"):
+        monkeypatch.setenv(switch, on)
         eng, b, sign, _ = _engine(sc, cuda_dev)
         out = []
         for level in (0, 1, 2):
@@ -787,14 +792,15 @@ def test_bulk_id_staging_matches_plain_loads(built, cuda_dev, monkeypatch):
         eng.begin_level(0, True)
         eng.iterate(12)
         eng.stream.synchronize()
-        res[bulk] = (out, eng.losses(), eng.get_state())
+        assert eng.status().iters_executed == 12
+        res[on] = (out, eng.losses(), eng.get_state())
         eng.close()
     assert max(int(o[3].max()) for o in res["0"][0]) > 2 * 256      # several batches per tile: the ring's slots are reused
     for (L0, g0, T0, n0, a0, b0), (L1, g1, T1, n1, a1, b1) in zip(res["0"][0], res["1"][0]):
         assert L0 == L1 and np.array_equal(n0, n1) and H.bits_equal(T0, T1) and H.bits_equal(a0, a1) and H.bits_equal(b0, b1)
         assert H.rel_max(g1, g0) < 1e-5
     # 12 free-running Adam steps: the two runs separate by the float-atomics noise of the gradients (the same separation
-    # two runs of ONE build show), far below anything a staging error would cause
+    # two runs of ONE build show), far below anything a plumbing error would cause
     assert np.allclose(res["0"][1], res["1"][1], rtol=1e-3) and all(np.allclose(x, y, atol=1e-3) for x, y in zip(res["0"][2], res["1"][2]))
 
 

@@ -13,7 +13,7 @@ grep -E "passed|failed" "$OUT/${TAG}_pytest_gpu.log" | tail -2
   echo "== racecheck: bulk id staging (GSEVT_BLEND_BULK=1), smoke()"
   GSEVT_BLEND_BULK=1 timeout 300 compute-sanitizer --tool racecheck python __graft_entry__.py smoke 2>&1 | tail -3
   echo "== memcheck: bulk id staging test"
-  timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k bulk 2>&1 | tail -4
+  timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "optional_paths and BULK" 2>&1 | tail -4
   # (the sanitizer serialises kernels, so ranks that wait for each other cannot run under it: the missing-peer test drives
   # ONE rank of a 2-way split through the split projection kernels, the list scatter, the sort and the blend forward)
   echo "== memcheck: screen-tile split kernels (pre-test, list projection, list scatter), one rank of two"
