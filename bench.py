@@ -610,7 +610,7 @@ def roofline(stages, wl, P, HW, clocks, default_workload=True, tiles=1200):
     table = {}
     for name, ms in stages.items():
         row = {"ms": round(ms, 4)}
-        if name in bytes_alg and ms > 0:
+        if name in bytes_alg and ms > 0.002:   # (a stage folded into its neighbour reports ~0: no rate for it)
             row.update(bound="hbm", achieved_gbs=round(bytes_alg[name] / (ms * 1e-3) / 1e9, 1),
                        frac=round(bytes_alg[name] / (ms * 1e-3) / 1e9 / hbm_peak, 4), alg_bytes=int(bytes_alg[name]))
         if name in flops_alg and ms > 0:

@@ -425,6 +425,10 @@ struct GsevtEngine {
     uint32_t* hit_base = nullptr;        // [2 tiles]
     uint2* ranges = nullptr;
     uint32_t* hitmask = nullptr; size_t hitmask_stride = 0;   // forward -> backward: what each warp blended
+    int fuse_loss = 0;                   // GSEVT_FUSE_LOSS=1: loss sums in the forward's epilogue instead of a kernel of their own; measured
+                                         // no faster (0.6654 vs 0.6630 ms): the epilogue costs the forward what the launch cost the graph
+    double* tile_loss = nullptr;         // [tiles of level 0][3] per-tile loss sums (fused loss)
+    uint32_t* tile_arrive = nullptr;     // [tiles of level 0] arrival counters + 1 ticket word
     int pdl = 0;                         // GSEVT_PDL=1: programmatic dependent launches along the iteration's kernel chain (internal.h);
                                          // measured 2.6 % SLOWER (0.6775 vs 0.6605 ms): the early-resident dependents take slots from
                                          // the predecessor's tail, and the graph's kernel-to-kernel gaps were only ~1.5 us to begin with
@@ -595,10 +599,17 @@ static void enqueue_iteration(GsevtEngine* e, cudaStream_t s, cudaEvent_t* ev = 
     f.views = e->views; f.final_T = e->final_T; f.n_contrib = e->n_contrib; f.out_color = e->gray; f.ctl = e->ctl;
     f.hitmask = e->hitmask; f.hitmask_stride = e->hitmask_stride; f.hit_base = e->hit_base; f.tile_order = e->tile_order;
     f.bulk_ids = e->blend_bulk;
+    const float* evf = e->ev_sign + L.ev_offset;
+    // the loss is evaluated in the forward's epilogue; an engine with an empty strip launches no forward and still has to
+    // take part in the exchange of the sums: it keeps the stand-alone kernel
+    const bool fuse_loss = e->fuse_loss && f.tile_rows > 0;
+    if (fuse_loss) {
+        f.event_frame = evf; f.loss_partials = e->tile_loss; f.tile_arrive = e->tile_arrive; f.loss_ticket = e->tile_arrive + e->bk_max_buckets / 2;
+        f.ctl_rw = e->ctl; f.comm = e->comm; f.host_flag = e->host_flag_dev; f.zero_me = e->active_count;
+    }
     launch_blend_fwd_gray(f, s);
     mark();
-    const float* evf = e->ev_sign + L.ev_offset;
-    {
+    if (!fuse_loss) {
         // pixel rows of this engine's strip (the whole image unless split): one contiguous slice of the image
         const int py0 = e->strip_y0 * GSEVT_TILE < L.H ? e->strip_y0 * GSEVT_TILE : L.H;
         const int py1 = e->strip_y1 * GSEVT_TILE < L.H ? e->strip_y1 * GSEVT_TILE : L.H;
@@ -699,6 +710,7 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     e->map = map; e->cfg = *cfg; e->nlevels = cfg->levels;
     if (const char* v = getenv("GSEVT_BLEND_BULK")) e->blend_bulk = atoi(v) != 0;
     if (const char* v = getenv("GSEVT_PDL")) e->pdl = atoi(v) != 0;
+    if (const char* v = getenv("GSEVT_FUSE_LOSS")) e->fuse_loss = atoi(v) != 0;
     size_t ev_off = 0;
     for (int l = 0; l < cfg->levels; l++) {
         LevelInfo& L = e->lv[l];
@@ -743,6 +755,8 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     rc |= dev_alloc(e, &e->tile_order, (size_t)e->bk_max_buckets);
     rc |= dev_alloc(e, &e->ranges, (size_t)e->bk_max_buckets);
     rc |= dev_alloc(e, &e->hit_base, (size_t)e->bk_max_buckets);
+    rc |= dev_alloc(e, &e->tile_loss, (size_t)(e->bk_max_buckets / 2) * 3);
+    rc |= dev_alloc(e, &e->tile_arrive, (size_t)(e->bk_max_buckets / 2) + 1);
     if (bucket_sort_configure()) { set_error("bucket_sort: cannot reserve %d bytes of shared memory", GSEVT_BK_SMEM_MAX_BYTES); gsevt_engine_destroy(e); return GSEVT_ECUDA; }
     if (P >= (1 << 28)) { set_error("map too large: the tile filter packs a Gaussian index into 28 bits"); gsevt_engine_destroy(e); return GSEVT_EINVAL; }
     bucket_sort_smem(8, &e->bk_smem_elems, &e->bk_smem_bins, &e->bk_smem_bytes);
@@ -782,6 +796,8 @@ GSEVT_API int gsevt_engine_create(const GsevtMap* map, const GsevtEngineConfig* 
     cudaMemset(e->bk_cursor, 0, (size_t)e->bk_max_buckets * GSEVT_BK_SUB * GSEVT_BK_CURSOR_STRIDE * 4);
     cudaMemset(e->ranges, 0, (size_t)e->bk_max_buckets * sizeof(uint2));
     cudaMemset(e->hit_base, 0, (size_t)e->bk_max_buckets * 4);
+    cudaMemset(e->tile_arrive, 0, ((size_t)(e->bk_max_buckets / 2) + 1) * 4);
+    cudaMemset(e->tile_loss, 0, (size_t)(e->bk_max_buckets / 2) * 3 * 8);
     cudaMemset(e->loss_partials, 0, ((size_t)e->loss_nb * 3 + 2) * 8);
     cudaMemset(e->grad8, 0, 2 * p2 * 16);
     cudaMemset(e->rect_raw, 0, preprocess_map_raw_items(P) * 4);
@@ -1386,10 +1402,12 @@ GSEVT_API int gsevt_engine_set_binning(GsevtEngine* e, int32_t mode) {
 }
 
 GSEVT_API int gsevt_engine_launches_per_iteration(const GsevtEngine* e) {
-    // preprocess_map, bucket_scatter, bucket_sort, blend_fwd, loss_stats, blend_bwd, geom_compact, geom_bwd, engine_update:
+    // preprocess_map, bucket_scatter, bucket_sort, blend_fwd (+ loss), blend_bwd, geom_compact, geom_bwd, engine_update:
     // all of them this library's own kernels; the screen-tile split runs the projection as two kernels (strip pre-test +
     // projection of the survivors)
-    return e && split_kernels(e) ? 10 : 9;
+    if (!e) return 8;
+    const int loss_kernel = e->fuse_loss && e->strip_y1 > e->strip_y0 ? 0 : 1;   // the loss sums ride in the forward's epilogue
+    return 8 + loss_kernel + (split_kernels(e) ? 1 : 0);
 }
 
 }  // extern "C"

@@ -26,6 +26,7 @@
 // The per-pixel arithmetic (power, expf, alpha, transmittance test, accumulation) follows the
 // reference's rounding order so n_contrib / final_T are bit-identical given identical inputs.
 #include "internal.h"
+#include "loss_finish.cuh"
 
 namespace gsevt {
 
@@ -164,6 +165,73 @@ __device__ __forceinline__ float eval_power(float dx, float dy, float A, float B
 // ------------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------------
+// Loss evaluation fused into the engine's forward (what loss_stats_kernel does as a launch of its own): a tile is
+// rendered by two CTAs, one per view; whichever finishes SECOND (a per-tile arrival counter) has both renders of the tile
+// in L2 and sums {d^2, d*E, E^2} over its 256 pixels (d = gray_next - gray_last); the CTA that delivers the LAST tile of the
+// launch adds the per-tile sums in tile order (deterministic: no float atomics), runs the tile split's exchange and writes
+// the coefficients the backward needs.  Every sum order is fixed by the tile / pixel layout, so repeated evaluations
+// and the ranks of a split agree bit for bit.
+__device__ __forceinline__ void blend_fwd_loss_epilogue(const BlendFwdArgs& a, int tile, int pixx, int pixy, bool inside) {
+    __shared__ double s_w[8][3];
+    __shared__ double s_x[8];
+    __shared__ int s_role;   // 0: first view of the tile to finish, 1: second, 2: second AND last tile of the launch
+    const int HW = a.W * a.H;
+    __threadfence();                                   // this CTA's gray pixels are visible device-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) s_role = atomicAdd(a.tile_arrive + tile, 1u) == 1u ? 1 : 0;   // ... before its arrival is
+    __syncthreads();
+    if (s_role == 0) return;
+    __threadfence();
+    double sd2 = 0.0, s2 = 0.0, se2 = 0.0;
+    if (inside) {
+        const size_t pix = (size_t)pixy * a.W + pixx;
+        // the other view's pixels were written by another SM: read through L2
+        const float d = __ldcg(a.out_color + (size_t)HW + pix) - __ldcg(a.out_color + pix);
+        const float E = __ldg(a.event_frame + pix);
+        sd2 = (double)d * (double)d;
+        s2 = a.ctl->loss_signed ? (double)d * (double)E : (double)fabsf(d) * (double)fabsf(E);
+        se2 = (double)E * (double)E;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sd2 += __shfl_xor_sync(0xffffffffu, sd2, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        se2 += __shfl_xor_sync(0xffffffffu, se2, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_w[warp][0] = sd2; s_w[warp][1] = s2; s_w[warp][2] = se2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t0 = 0, t1 = 0, t2 = 0;
+        for (int w = 0; w < 8; w++) { t0 += s_w[w][0]; t1 += s_w[w][1]; t2 += s_w[w][2]; }
+        a.loss_partials[3 * tile + 0] = t0;
+        a.loss_partials[3 * tile + 1] = t1;
+        a.loss_partials[3 * tile + 2] = t2;
+        a.tile_arrive[tile] = 0u;                      // ready for the next iteration
+        __threadfence();
+        if (atomicAdd(a.loss_ticket, 1u) == (unsigned)(a.tile_rows * a.grid_x - 1)) s_role = 2;
+    }
+    __syncthreads();
+    if (s_role != 2 || threadIdx.x >= 32) return;
+    __threadfence();
+    // last tile delivered: warp 0 adds the strip's tiles in tile order (lane-strided, then a butterfly)
+    const int t_first = a.tile_y0 * a.grid_x, t_end = (a.tile_y0 + a.tile_rows) * a.grid_x;
+    double t0 = 0, t1 = 0, t2 = 0;
+    for (int t = t_first + lane; t < t_end; t += 32) {
+        t0 += __ldcg(a.loss_partials + 3 * t + 0);
+        t1 += __ldcg(a.loss_partials + 3 * t + 1);
+        t2 += __ldcg(a.loss_partials + 3 * t + 2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    if (lane == 0) *a.loss_ticket = 0u;
+    loss_finish(t0, t1, t2, a.ctl_rw, a.comm, a.host_flag, a.zero_me, s_x);
+}
+
 template <int C, bool OPERATOR, bool BULK = false>
 __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
     static_assert(!(OPERATOR && BULK), "the operator's packed lists are not aligned for bulk copies");
@@ -343,6 +411,9 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(BlendFwdArgs a) {
             const float bgg = GSEVT_GRAY_R * vp.bg[0] + GSEVT_GRAY_G * vp.bg[1] + GSEVT_GRAY_B * vp.bg[2];
             a.out_color[(size_t)view * HW + pix] = __fmaf_rn(bgg, T, acc[0]);
         }
+    }
+    if constexpr (!OPERATOR) {
+        if (a.loss_partials) blend_fwd_loss_epilogue(a, tile_y * a.grid_x + tile_x, pixx, pixy, inside);
     }
 }
 

@@ -207,6 +207,15 @@ struct BlendFwdArgs {
     const uint32_t* tile_order;  // engine: tile (view * tiles + ty * grid_x + tx) of CTA i, longest lists first; NULL: 3-D grid
     int bulk_ids;                // engine: stage the id lists with cp.async.bulk + mbarrier (lists must start on 16-byte boundaries)
     const EngineCtl* ctl;
+    // engine: loss evaluation fused into the forward (NULL loss_partials: not fused, loss_stats_kernel follows)
+    const float* event_frame;    // [HW] at this level (signed)
+    double* loss_partials;       // [tiles of the level][3]
+    uint32_t* tile_arrive;       // [tiles of the level] views of the tile rendered so far; zero between iterations
+    uint32_t* loss_ticket;       // tiles delivered so far; zero between iterations
+    EngineCtl* ctl_rw;
+    struct SplitComm* comm;
+    int* host_flag;
+    uint32_t* zero_me;           // the geometry backward's work-list counter, cleared for this iteration
 };
 void launch_blend_fwd_rgb(const BlendFwdArgs& a, cudaStream_t s);
 void launch_blend_fwd_gray(const BlendFwdArgs& a, cudaStream_t s);

@@ -17,6 +17,7 @@
 // (closed form of autograd through norm / div / abs / sub / norm; derivation in DESIGN.md).
 #include "internal.h"
 #include "split_comm.cuh"
+#include "loss_finish.cuh"
 
 namespace gsevt {
 
@@ -217,36 +218,8 @@ __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict
         t1 += __shfl_xor_sync(0xffffffffu, t1, o);
         t2 += __shfl_xor_sync(0xffffffffu, t2, o);
     }
-    if (comm) {
-        // screen-tile split: these are the sums over this rank's strip; exchange them over peer memory
-        if (threadIdx.x == 0) { s_x[0] = t0; s_x[1] = t1; s_x[2] = t2; }
-        __syncwarp();
-        const bool ok = split_exchange(comm, 0, 3, s_x, s_x + 4);
-        __syncwarp();
-        t0 = s_x[4]; t1 = s_x[5]; t2 = s_x[6];
-        if (!ok && threadIdx.x == 0) {
-            ctl->comm_error = 1;
-            ctl->level_done = 3;
-            if (host_flag) *host_flag = 3;
-            __threadfence_system();
-        }
-    }
-    if (threadIdx.x != 0) return;
-    if (zero_me) *zero_me = 0u;   // per-iteration counter of the backward's work list (consumed two kernels later)
-    *ticket = 0u;
-    const double n = sqrt(t0);
-    double L2 = 1.0 - 2.0 * t1 / n + t2;
-    if (L2 < 0.0) L2 = 0.0;
-    const double L = sqrt(L2);
-    if (n > 0.0 && L > 0.0) {
-        ctl->loss_alpha = (float)(t1 / (n * n * n * L));
-        ctl->loss_beta = (float)(1.0 / (L * n));
-        ctl->last_loss = (float)L;
-    } else {
-        ctl->loss_alpha = 0.0f;
-        ctl->loss_beta = 0.0f;
-        ctl->last_loss = n > 0.0 ? (float)L : (float)sqrt(t2);
-    }
+    if (threadIdx.x == 0) *ticket = 0u;
+    loss_finish(t0, t1, t2, ctl, comm, host_flag, zero_me, s_x);
 }
 
 void launch_loss_stats(const float* gray, const float* event_frame, int HW, int pix0, int npix, EngineCtl* ctl,
