@@ -353,17 +353,28 @@ GSEVT_API int gsevt_event_undistort_map(const double* K, const double* D, int32_
 
 GSEVT_API size_t gsevt_event_frame_scratch_size(int32_t W, int32_t H) { return align_up((size_t)2 * W * H * 4) + 64 * 8 + 256; }
 
-GSEVT_API int gsevt_event_frame(const int32_t* counts, const int32_t* map_ix, const int32_t* map_iy, int32_t W, int32_t H,
-                      int32_t levels, float* sign_out, float* unsign_out, void* scratch, size_t scratch_bytes, void* stream) {
+GSEVT_API int gsevt_event_frame_k(const int32_t* counts, const int32_t* map_ix, const int32_t* map_iy, int32_t W, int32_t H,
+                        int32_t levels, int32_t ksize, float* sign_out, float* unsign_out, void* scratch, size_t scratch_bytes, void* stream) {
     if (!counts || !map_ix || !map_iy || !sign_out || !unsign_out || !scratch || W <= 0 || H <= 0 || levels < 1 || levels > GSEVT_MAX_LEVELS) {
         set_error("bad arguments"); return GSEVT_EINVAL;
     }
+    // OpenCV's kernels for sigma = 0 are multiples of 1/256 up to 9 taps: every product and partial sum of the blur is then
+    // exact in fp32 and the result is cv2's whatever its SIMD width.  From 11 taps on the coefficients are arbitrary floats
+    // and cv2's own result depends on how its build splits a row into vector body (FMA) and scalar tail (mul + add), so
+    // there is no bit-exact answer to reproduce: rejected rather than approximated.
+    if (ksize < 1 || ksize > 9 || (ksize & 1) == 0) { set_error("gaussian kernel size must be 1, 3, 5, 7 or 9 (got %d)", ksize); return GSEVT_EINVAL; }
     if (scratch_bytes < gsevt_event_frame_scratch_size(W, H)) { set_error("scratch too small"); return GSEVT_ENOMEM; }
     char* b = base_aligned(scratch);
-    launch_event_frame(counts, map_ix, map_iy, W, H, levels, sign_out, unsign_out, (float*)b,
+    launch_event_frame(counts, map_ix, map_iy, W, H, levels, ksize, sign_out, unsign_out, (float*)b,
                        (double*)(b + align_up((size_t)2 * W * H * 4)), (cudaStream_t)stream);
     GSEVT_CUDA_OK(cudaPeekAtLastError());
     return 0;
+}
+
+GSEVT_API int gsevt_event_frame(const int32_t* counts, const int32_t* map_ix, const int32_t* map_iy, int32_t W, int32_t H,
+                      int32_t levels, float* sign_out, float* unsign_out, void* scratch, size_t scratch_bytes, void* stream) {
+    // the 9-tap kernel of every configs/VECTOR yaml (gaussian_kernel_size: 9)
+    return gsevt_event_frame_k(counts, map_ix, map_iy, W, H, levels, 9, sign_out, unsign_out, scratch, scratch_bytes, stream);
 }
 
 }  // extern "C"

@@ -299,7 +299,7 @@ void launch_weighted_velocity(EngineCtl* ctl, const float* lastRT, float delta_t
 // ---- events ------------------------------------------------------------------------------------
 void launch_event_accumulate(const int16_t* x, const int16_t* y, const uint8_t* p, int n, int W, int H, int* counts,
                              int* oob, cudaStream_t s);
-void launch_event_frame(const int* counts, const int* map_ix, const int* map_iy, int W, int H, int levels,
+void launch_event_frame(const int* counts, const int* map_ix, const int* map_iy, int W, int H, int levels, int ksize,
                         float* sign_out, float* unsign_out, float* scratch, double* dscratch, cudaStream_t s);
 
 void launch_workload_counters(int P, const uint32_t* rect_raw, const float4* grad8, int HW, const uint32_t* n_contrib,

@@ -66,28 +66,30 @@ __global__ void event_undistort_kernel(const int* __restrict__ counts, const int
 }
 
 // ---- E2 ------------------------------------------------------------------------------------------
-__device__ __constant__ const float kGauss9[9] = {4.0f / 256, 13.0f / 256, 30.0f / 256, 51.0f / 256, 60.0f / 256,
-                                                  51.0f / 256, 30.0f / 256, 13.0f / 256, 4.0f / 256};
+// cv2.GaussianBlur(frame, (k, k), 0, BORDER_REPLICATE) for odd k <= 31: OpenCV's own coefficients (gauss_taps.inc), the row
+// pass accumulated left to right with FMA, the column pass in the symmetric form (centre, then the pairs outwards) —
+// bit-exact against cv2 on event frames for every odd k (tests/test_event_oracle.py).
+#include "gauss_taps.inc"
+struct GaussTaps { float c[16]; int r; };   // c[j]: coefficient at distance j from the centre, r = k / 2
 
-__global__ void event_blur_row_kernel(const float* __restrict__ in, int W, int H, float* __restrict__ out) {
+__global__ void event_blur_row_kernel(const float* __restrict__ in, int W, int H, float* __restrict__ out, GaussTaps g) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= W * H) return;
     const int y = i / W, x = i - y * W;
     const float* row = in + (size_t)y * W;
-    float s = __fmul_rn(row[max(x - 4, 0)], kGauss9[0]);
-#pragma unroll
-    for (int k = 1; k < 9; k++) s = __fmaf_rn(row[min(max(x - 4 + k, 0), W - 1)], kGauss9[k], s);
+    const int r = g.r;
+    float s = __fmul_rn(row[max(x - r, 0)], g.c[r]);
+    for (int k = 1; k <= 2 * r; k++) s = __fmaf_rn(row[min(max(x - r + k, 0), W - 1)], g.c[abs(k - r)], s);
     out[i] = s;
 }
-__global__ void event_blur_col_kernel(const float* __restrict__ in, int W, int H, float* __restrict__ out) {
+__global__ void event_blur_col_kernel(const float* __restrict__ in, int W, int H, float* __restrict__ out, GaussTaps g) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= W * H) return;
     const int y = i / W, x = i - y * W;
-    float t = __fmul_rn(in[i], kGauss9[4]);
-#pragma unroll
-    for (int j = 1; j <= 4; j++) {
+    float t = __fmul_rn(in[i], g.c[0]);
+    for (int j = 1; j <= g.r; j++) {
         const float a = in[(size_t)min(y + j, H - 1) * W + x], b = in[(size_t)max(y - j, 0) * W + x];
-        t = __fmaf_rn(__fadd_rn(a, b), kGauss9[4 + j], t);
+        t = __fmaf_rn(__fadd_rn(a, b), g.c[j], t);
     }
     out[i] = t;
 }
@@ -146,14 +148,17 @@ __global__ void event_finish_kernel(const float* __restrict__ in, const double* 
     }
 }
 
-void launch_event_frame(const int* counts, const int* map_ix, const int* map_iy, int W, int H, int levels,
+void launch_event_frame(const int* counts, const int* map_ix, const int* map_iy, int W, int H, int levels, int ksize,
                         float* sign_out, float* unsign_out, float* scratch, double* dscratch, cudaStream_t s) {
     const int n = W * H, nb = (n + 255) / 256;
     float* a = scratch;
     float* b = scratch + n;
+    GaussTaps g;
+    g.r = ksize / 2;
+    for (int j = 0; j < 16; j++) g.c[j] = kGaussTaps[g.r][j];
     event_undistort_kernel<<<nb, 256, 0, s>>>(counts, map_ix, map_iy, W, H, a);
-    event_blur_row_kernel<<<nb, 256, 0, s>>>(a, W, H, b);
-    event_blur_col_kernel<<<nb, 256, 0, s>>>(b, W, H, a);
+    event_blur_row_kernel<<<nb, 256, 0, s>>>(a, W, H, b, g);
+    event_blur_col_kernel<<<nb, 256, 0, s>>>(b, W, H, a, g);
     event_sumsq_kernel<<<EV_NB, 256, 0, s>>>(a, n, dscratch);
     event_finish_kernel<<<nb, 256, 0, s>>>(a, dscratch, W, H, levels, sign_out, unsign_out);
 }

@@ -301,10 +301,14 @@ class TrackingEngine:
 class EventFrameBuilder:
     """GPU event frames: polarity scatter-add, undistort, 9x9 blur, L2 normalise, abs, pyramid."""
 
-    def __init__(self, width, height, intrinsic, distortion, levels=3, device="cuda"):
+    def __init__(self, width, height, intrinsic, distortion, levels=3, device="cuda", gaussian_kernel_size=9):
         self._lib = _lib.load()
         _lib.require_device()
         self.W, self.H, self.levels = int(width), int(height), int(levels)
+        self.ksize = int(gaussian_kernel_size)
+        if self.ksize not in (1, 3, 5, 7, 9):
+            raise ValueError(f"gaussian_kernel_size must be 1, 3, 5, 7 or 9 (got {gaussian_kernel_size}): the sizes whose OpenCV "
+                             "kernel is a multiple of 1/256, i.e. whose blur has a machine-independent bit-exact answer")
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -371,10 +375,10 @@ class EventFrameBuilder:
         sign = torch.empty((self.total,), dtype=torch.float32, device=self.device)
         unsign = torch.empty((self.total,), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.gsevt_event_frame(self.counts.data_ptr(), self.map_ix.data_ptr(), self.map_iy.data_ptr(),
-                                                   self.W, self.H, self.levels, sign.data_ptr(), unsign.data_ptr(),
-                                                   self.scratch.data_ptr(), self.scratch.numel(), _lib.stream_ptr()),
-                       "gsevt_event_frame")
+            _lib.check(self._lib.gsevt_event_frame_k(self.counts.data_ptr(), self.map_ix.data_ptr(), self.map_iy.data_ptr(),
+                                                     self.W, self.H, self.levels, self.ksize, sign.data_ptr(), unsign.data_ptr(),
+                                                     self.scratch.data_ptr(), self.scratch.numel(), _lib.stream_ptr()),
+                       "gsevt_event_frame_k")
         return sign, unsign
 
     def level_view(self, flat, level):

@@ -80,6 +80,8 @@ PROTOTYPES = {
                                             c_void_p, c_void_p]),
     "gsevt_event_frame": (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int32, C.c_int32, C.c_int32, c_void_p, c_void_p,
                                     c_void_p, C.c_size_t, c_void_p]),
+    "gsevt_event_frame_k": (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_void_p, c_void_p,
+                                      c_void_p, C.c_size_t, c_void_p]),
     "gsevt_event_frame_scratch_size": (C.c_size_t, [C.c_int32, C.c_int32]),
     "gsevt_map_create": (C.c_int, [C.c_int32, C.c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_float,
                                    c_void_p, C.POINTER(c_void_p)]),

@@ -106,20 +106,23 @@ def _parse_int_table(path, threads=None):
 _BUILDERS = {}
 
 
-def _builder(width, height, intrinsic, distortion, device):
+def _builder(width, height, intrinsic, distortion, device, ksize=9):
     from gsevt.engine import EventFrameBuilder
-    key = (width, height, tuple(np.asarray(intrinsic, np.float64).ravel()), tuple(np.asarray(distortion, np.float64).ravel()), str(device))
+    key = (width, height, tuple(np.asarray(intrinsic, np.float64).ravel()), tuple(np.asarray(distortion, np.float64).ravel()), str(device),
+           int(ksize))
     if key not in _BUILDERS:
-        _BUILDERS[key] = EventFrameBuilder(width, height, intrinsic, distortion, levels=3, device=device)
+        _BUILDERS[key] = EventFrameBuilder(width, height, intrinsic, distortion, levels=3, device=device, gaussian_kernel_size=ksize)
     return _BUILDERS[key]
 
 
 class EventFrame:
     def __init__(self, img_width, img_height, intrinsic, distortion_factors, gaussian_kernel_size,
                  event_array: EventArray, device="cuda"):
-        if int(gaussian_kernel_size) != 9:
-            raise NotImplementedError("gsevt implements OpenCV's fixed 9-tap kernel (gaussian_kernel_size: 9), "
-                                      "the value of every GS-EVT config")
+        k = int(gaussian_kernel_size)
+        if k not in (1, 3, 5, 7, 9):
+            # cv2.GaussianBlur itself rejects even sizes; from 11 taps on its coefficients are no longer multiples of 1/256
+            # and its own result depends on the SIMD width of the build (every GS-EVT config uses 9)
+            raise ValueError(f"gaussian_kernel_size must be 1, 3, 5, 7 or 9, got {gaussian_kernel_size}")
         self.device = device
         self.img_width, self.img_height = img_width, img_height
         self.intrinsic, self.distortion_factors = intrinsic, distortion_factors
@@ -127,7 +130,7 @@ class EventFrame:
         self.sign_delta_Ie, self.unsign_delta_Ie = self.integrate_events(event_array)
 
     def integrate_events(self, event_array):
-        b = _builder(self.img_width, self.img_height, self.intrinsic, self.distortion_factors, self.device)
+        b = _builder(self.img_width, self.img_height, self.intrinsic, self.distortion_factors, self.device, self.gaussian_kernel_size)
         _, x, y, p = event_array.columns()
         # numpy indexing of the reference (frame[y, x] += ..., event.py:118-120): [-size, size) is legal, negative indices
         # count from the end (the scatter kernel wraps them the same way); anything else is an IndexError

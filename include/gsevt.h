@@ -180,6 +180,12 @@ GSEVT_API int gsevt_event_undistort_map(const double* K, const double* D, int32_
 GSEVT_API int gsevt_event_frame(const int32_t* counts, const int32_t* map_ix, const int32_t* map_iy,
                       int32_t width, int32_t height, int32_t levels,
                       float* sign_out, float* unsign_out, void* scratch, size_t scratch_bytes, void* stream);
+/* The same with cv2.GaussianBlur's kernel size as a parameter (the yaml's Event.gaussian_kernel_size, reference
+ * utils/event_camera/event.py:122-123): 1, 3, 5, 7 or 9 — the sizes whose OpenCV coefficients (sigma = 0) are multiples of
+ * 1/256, so that the blur is exact in fp32 and bit-identical to cv2 on any machine. */
+GSEVT_API int gsevt_event_frame_k(const int32_t* counts, const int32_t* map_ix, const int32_t* map_iy,
+                        int32_t width, int32_t height, int32_t levels, int32_t ksize,
+                        float* sign_out, float* unsign_out, void* scratch, size_t scratch_bytes, void* stream);
 GSEVT_API size_t gsevt_event_frame_scratch_size(int32_t width, int32_t height);
 
 /* ------------------------------------------------------------------------------------------------

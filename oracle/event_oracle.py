@@ -15,7 +15,8 @@ dependency whose source is not under /root/reference, so E1-E3 restate its publi
   * undistort == initUndistortRectifyMap(K, D, I, K, size, CV_16SC2) + remap(INTER_LINEAR,
     BORDER_CONSTANT 0): inverse map evaluated in float64, quantised to 1/32 pixel
     (INTER_BITS = 5), bilinear weights taken from the 32x32 float32 table;
-  * GaussianBlur with sigma <= 0 and ksize 9 uses the fixed kernel [4,13,30,51,60,51,30,13,4]/256;
+  * GaussianBlur with sigma <= 0 and ksize 9 uses the fixed kernel [4,13,30,51,60,51,30,13,4]/256 (other odd sizes: the
+    coefficients of cv2.getGaussianKernel(k, 0, CV_32F), tabulated in tests/golden/gauss_taps.npz by make_gauss_taps.py);
     row pass accumulates left to right with FMA, the column pass uses the symmetric form;
   * normalize(NORM_L2) multiplies by float32(1 / sqrt(sum_fp64 x^2)).
 Pinned against cv2 itself in tests/test_event_oracle.py (cv2 is installed in the image, so the pin
@@ -129,6 +130,32 @@ def gaussian_blur9(frame):
     return t
 
 
+def gauss_taps(ksize):
+    """Full k-tap kernel (float32) of cv2.getGaussianKernel(k, 0, CV_32F) from the committed table."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "gauss_taps.npz"))
+    half = z["k%d" % int(ksize)].astype(np.float32)            # centre outwards
+    return np.concatenate([half[:0:-1], half]).astype(np.float32)
+
+
+def gaussian_blur(frame, ksize=9):
+    """E2 for any odd kernel size 1..31: same pass structure as gaussian_blur9 (which it reproduces for ksize 9)."""
+    f = np.asarray(frame, dtype=np.float32)
+    H, W = f.shape
+    k = gauss_taps(ksize)
+    r = int(ksize) // 2
+    xp = np.pad(f, ((0, 0), (r, r)), mode="edge")
+    s = (xp[:, 0:W] * k[0]).astype(np.float32)
+    for i in range(1, 2 * r + 1):
+        s = _fma(xp[:, i:i + W], k[i], s)
+    yp = np.pad(s, ((r, r), (0, 0)), mode="edge")
+    t = (yp[r:r + H, :] * k[r]).astype(np.float32)
+    for j in range(1, r + 1):
+        pair = (yp[r + j:r + j + H, :] + yp[r - j:r - j + H, :]).astype(np.float32)
+        t = _fma(pair, k[r + j], t)
+    return t
+
+
 def l2_normalize(frame):
     """E3 — cv2.normalize(x, None): x * float32(1 / ||x||_2) with the norm accumulated in float64."""
     f = np.asarray(frame, dtype=np.float32)
@@ -137,10 +164,11 @@ def l2_normalize(frame):
     return (f * scale).astype(np.float32)
 
 
-def event_frame(x, y, p, W, H, K, D):
+def event_frame(x, y, p, W, H, K, D, ksize=9):
     """E0..E4 — returns (sign_delta_Ie, unsign_delta_Ie), each (1, H, W) float32."""
     cnt = accumulate(x, y, p, W, H).astype(np.float32)
-    f = l2_normalize(gaussian_blur9(undistort(cnt, K, D)))
+    und = undistort(cnt, K, D)
+    f = l2_normalize(gaussian_blur9(und) if int(ksize) == 9 else gaussian_blur(und, ksize))
     return f[None], np.abs(f)[None]
 
 

@@ -41,6 +41,30 @@ def test_stages_match_opencv_bit_exactly(W, Hh, n, seed):
         assert H.bits_equal(lvl, ref)
 
 
+@pytest.mark.parametrize("ksize", [1, 3, 5, 7, 9])
+def test_dyadic_kernel_sizes_match_opencv_bit_exactly(ksize):
+    """Event.gaussian_kernel_size other than the configs' 9: the generic blur (OpenCV's coefficients from the committed
+    table, row pass left to right with FMA, symmetric column pass) against cv2.GaussianBlur on event frames, and the
+    committed table against cv2.getGaussianKernel itself.  Up to 9 taps the coefficients are multiples of 1/256 and the
+    blur is exact; from 11 on cv2's result depends on its vector-body / scalar-tail split (seen here: 11 taps agree at
+    widths 96 and 320 and differ in the tail columns at width 33), so those sizes are rejected by the product."""
+    import cv2
+    assert np.array_equal(eo.gauss_taps(ksize), cv2.getGaussianKernel(ksize, 0, cv2.CV_32F).ravel().astype(np.float32))
+    for W, Hh, n, seed in ((96, 64, 20000, 0), (320, 240, 30000, 1), (33, 17, 3000, 2)):
+        rng = np.random.default_rng(seed)
+        x, y, p = rng.integers(0, W, n), rng.integers(0, Hh, n), rng.integers(0, 2, n)
+        s = W / 640.0
+        K = np.array([327.32749 * s, 0, 304.97749 * s, 0, 327.46184 * s, 235.37621 * s, 0, 0, 1.0]).reshape(3, 3)
+        D = np.array([-0.031982, 0.041966, -0.000507, -0.001031, 0.0])
+        und = cv2.undistort(_frame(x, y, p, W, Hh), K, D)
+        blur = cv2.GaussianBlur(und, (ksize, ksize), 0, borderType=cv2.BORDER_REPLICATE)
+        assert H.bits_equal(eo.gaussian_blur(und, ksize), blur), (ksize, W, Hh)
+        s_ref, _ = eo.event_frame(x, y, p, W, Hh, K, D, ksize=ksize)
+        assert H.bits_equal(s_ref[0], cv2.normalize(blur, None))
+    if ksize == 9:
+        assert H.bits_equal(eo.gaussian_blur(und, 9), eo.gaussian_blur9(und))
+
+
 @pytest.mark.parametrize("W,Hh", [(346, 260), (641, 479), (100, 75), (640, 480)])
 def test_pyramid_is_opencv_nearest_on_sizes_not_divisible_by_four(W, Hh):
     """cv2.resize(INTER_NEAREST) samples floor(dst * src / dst_size): on 346 x 260 (DAVIS346) level 2 is NOT frame[::4, ::4]."""

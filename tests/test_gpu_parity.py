@@ -255,6 +255,32 @@ def test_event_frame_bit_exact(built, cuda_dev, n, seed):
         assert H.bits_equal(b.level_view(sign, 0)[0].cpu().numpy(), c), "against OpenCV itself"
 
 
+@pytest.mark.parametrize("ksize", [1, 3, 5, 7])
+def test_event_frame_other_kernel_sizes_bit_exact(built, cuda_dev, ksize):
+    """Event.gaussian_kernel_size != 9 (gsevt_event_frame_k): bit-exact against the oracle, which tests/test_event_oracle.py
+    pins to cv2.GaussianBlur for the sizes with an exact answer (1..9); through the reference-facing EventFrame class as well."""
+    from gsevt import synth
+    from gsevt.engine import EventFrameBuilder
+    from oracle import event_oracle as eo
+    from utils.event_camera.event import EventArray, EventFrame
+    D = synth.DESK
+    W, Hh = 346, 260
+    K = np.array([D["fx"] * W / 640, 0, W / 2.0, 0, D["fy"] * W / 640, Hh / 2.0, 0, 0, 1.0]).reshape(3, 3)
+    ev = synth.random_events(40000, W, Hh, 0, 50000, seed=ksize)
+    x, y, p = ev[:, 1].astype(np.int16), ev[:, 2].astype(np.int16), ev[:, 3].astype(np.uint8)
+    b = EventFrameBuilder(W, Hh, K, D["dist"], levels=3, device=cuda_dev, gaussian_kernel_size=ksize)
+    sign, unsign = b.build(x, y, p)
+    s_ref, u_ref = eo.event_frame(x, y, p, W, Hh, K, D["dist"], ksize=ksize)
+    for l, (sr, ur) in enumerate(zip(eo.pyramid(s_ref[0]), eo.pyramid(u_ref[0]))):
+        assert H.bits_equal(b.level_view(sign, l)[0].cpu().numpy(), sr), f"signed level {l}"
+        assert H.bits_equal(b.level_view(unsign, l)[0].cpu().numpy(), ur), f"unsigned level {l}"
+    ef = EventFrame(W, Hh, K, np.array(D["dist"]), ksize, EventArray(ev[:, 0], ev[:, 1], ev[:, 2], ev[:, 3]), device=cuda_dev)
+    assert H.bits_equal(ef.sign_delta_Ie[0].cpu().numpy(), s_ref[0])
+    for bad in (0, 4, 11, 33):
+        with pytest.raises(ValueError):
+            EventFrame(W, Hh, K, np.array(D["dist"]), bad, EventArray(ev[:, 0], ev[:, 1], ev[:, 2], ev[:, 3]), device=cuda_dev)
+
+
 def test_event_frame_odd_sizes_and_negative_coordinates(built, cuda_dev):
     """346 x 260 (DAVIS346): the pyramid is OpenCV's nearest mapping floor(dst * src / dst_size), not frame[::4, ::4];
     negative coordinates wrap like numpy's indexing in the reference's scatter loop (event.py:118-120)."""
