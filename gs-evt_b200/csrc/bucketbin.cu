@@ -17,7 +17,9 @@
 //                    5 400 of them per cursor were 55 of this kernel's 64 us [measured r2].  Slot order is whatever the
 //                    atomics hand out.  Segments have a fixed capacity, sized when the level begins (count-only run of
 //                    this kernel + slack); a sub-segment that outgrows its share sets the overflow flag, the iteration
-//                    is voided on the device and the host re-sizes.
+//                    is voided on the device and the host re-sizes.  (bucket_scatter_list: the same scatter over the
+//                    list of visible pairs the split projection kernels write — screen-tile split, where 80-90 % of a
+//                    rank's pairs are empty.  The per-pair code lives in bucket_scatter.cuh.)
 //   bucket_sort      one CTA per bucket: counting sort of the bucket's keys on the depth in shared memory with one
 //                    shared-memory atomic per key + ranking inside the depth bins (below), then the sorted bucket is
 //                    FILTERED into its tiles — a tile's list is the subsequence of the bucket whose rect covers the

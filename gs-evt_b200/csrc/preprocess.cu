@@ -5,6 +5,9 @@
 //  * preprocess_aos_kernel  — operator path: caller's AoS tensors, one view.
 //  * preprocess_map_kernel  — engine path: packed frozen map (SoA, planar SH, precomputed cov3D),
 //                             BOTH views per thread so the 232 B/Gaussian map read happens once.
+//  * strip_pretest_kernel + preprocess_map_list_kernel — engine path under the screen-tile split: a conservative 20-byte
+//                             test of the whole map against this rank's strip of tile rows, then the exact projection of
+//                             the survivors only (full warps, per-Gaussian SH copy) — see the comment above them.
 // HBM-bound: grid = ceil(P/256) x 256 threads, all per-Gaussian loads coalesced (AoS inputs are
 // staged through shared memory in 16-byte vectors; planar SH is read as 48 coalesced lines per warp).
 #include <cstdlib>
