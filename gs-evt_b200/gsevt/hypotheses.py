@@ -14,6 +14,7 @@ another leaves idle; the host only polls the engines' mapped done-flags.
 """
 import itertools
 import math
+import time
 
 import numpy as np
 
@@ -173,9 +174,11 @@ def track_concurrently(engines, next_hypothesis, delta_tau, sign_pyramid, unsign
     for i in range(len(engines)):
         start(i)
     while any(s is not None for s in slots):
+        progressed = False
         for i, s in enumerate(slots):
             if s is None or not s["event"].query():
                 continue
+            progressed = True
             eng = engines[i]
             flag = eng.poll_done()
             if flag == 0:
@@ -196,4 +199,6 @@ def track_concurrently(engines, next_hypothesis, delta_tau, sign_pyramid, unsign
                     R, T, w, v = eng.get_state()
                     rows.append(pack_result(s["h"], float(st.last_loss), s["iters"], R, T, w, v))
                     start(i)
+        if not progressed:
+            time.sleep(2e-5)   # every engine has a chunk in flight: yield the core instead of spinning on the queries
     return rows
